@@ -1,0 +1,404 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A(M,K) . B(N,K)^T  (fp32 accumulate in TMEM)
+//
+//   warp 0      : TMEM allocation, then TMA producer (one elected lane)
+//   warp 1      : mbarrier init, then tcgen05.mma issuer (one elected lane)
+//   warps 2..5  : epilogue - tcgen05.ld accumulator rows -> per-warp smem transpose -> coalesced 128-bit
+//                 global traffic with fused bias / q-scale / GELU / GELU' / fp32 residual / atomic accumulate
+//
+// Operand tiles are staged by TMA into 128B-swizzled shared memory, 4 stages of (128 x 64) + (BLOCK_N x 64) bf16.
+// Either operand may be K-major (contraction dim contiguous in global memory: activations x weights^T) or
+// MN-major (row dim contiguous: the weight-gradient contraction over tokens, and dX = dY . W without a
+// transposed weight copy).  The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Split-K (for the weight gradients, whose output has < 148 tiles)
+// reduces with fp32 atomics straight into the gradient buffer.
+//
+// This one kernel carries every dense contraction of the hot path (reference call sites:
+// OATrans/model/video_transformer.py:102,133 (qkv/proj), :46-49 (Mlp), :69 (patch conv as GEMM),
+// OATrans/model/oa_model.py:68-75 (projections), OATrans/model/model.py:164-172 (sim matrix),
+// HF DistilBERT linears) and their autograd counterparts.
+#include <cuda.h>
+
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kStagingFloats = 32 * 33;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, split_k, k_blocks;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  float* out_f32;
+  long long ld_f32;
+  __nv_bfloat16* out_bf16;
+  long long ld_bf16;
+  __nv_bfloat16* out2_bf16;
+  long long ld2;
+  const __nv_bfloat16* aux_bf16;
+  long long ld_aux;
+  int act;
+  int scale_cols;
+  float scale;
+  float alpha;
+  int accumulate;
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
+  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
+};
+
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  uint2 raw = *reinterpret_cast<const uint2*>(p);
+  float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
+  uint2 raw;
+  raw.x = pack_bf16x2(v.x, v.y);
+  raw.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                // [kStages][16 KB]
+  uint8_t* smem_b = smem + kStages * S::kABytes;          // [kStages][BLOCK_N*128 B]
+  float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * kStages; // [2]        MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+    }
+    __syncwarp();
+    tmem_alloc<kTmemCols>(tmem_slot);
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = tiles_mn * p.split_k;
+  const int kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int mn = tile - split * tiles_mn;
+        const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem_a + stage * S::kABytes;
+          uint8_t* sb = smem_b + stage * S::kBBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    // K-major: 8-row groups 1024 B apart; k-step of 16 elements = 32 B inside the swizzle row.
+    // MN-major: 8-k-row groups 1024 B apart, 64-wide MN atoms BLOCK_K*128 B apart; k-step of 16 rows = 2048 B.
+    constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 0, b_lbo = B_MN ? BLOCK_K * 128 : 0;
+    constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2, b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+    uint32_t stage = 0, phase = 0;
+    int local_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+      const int split = tile / tiles_mn;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+      const uint32_t acc = local_iter & 1;
+      const uint32_t acc_phase = (local_iter >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may address
+    float* stg = staging + (warp - 2) * kStagingFloats;
+    int local_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
+      const uint32_t acc = local_iter & 1;
+      const uint32_t acc_phase = (local_iter >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row_base = m_blk * BLOCK_M + q * 32;
+      const int col_base = n_blk * BLOCK_N;
+      const bool first_split = (split == 0);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {
+          // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int cc = (lane & 7) * 4;
+          const int row = row_base + r;
+          const int col = col_base + c * 32 + cc;
+          if (row < p.M && col < p.N) {
+            float4 x = make_float4(stg[r * 33 + cc], stg[r * 33 + cc + 1], stg[r * 33 + cc + 2], stg[r * 33 + cc + 3]);
+            x.x *= p.alpha; x.y *= p.alpha; x.z *= p.alpha; x.w *= p.alpha;
+            if (p.bias != nullptr && first_split) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (col < p.scale_cols) { x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale; }
+            if (p.act == 1) {
+              // forward GELU: keep the bf16 pre-activation for backward, activate the rounded value
+              __nv_bfloat16* pre = p.out2_bf16 + static_cast<long long>(row) * p.ld2 + col;
+              st_bf16x4(pre, x);
+              x.x = gelu_erf(bf16_round(x.x)); x.y = gelu_erf(bf16_round(x.y));
+              x.z = gelu_erf(bf16_round(x.z)); x.w = gelu_erf(bf16_round(x.w));
+            } else if (p.act == 2) {
+              const float4 u = ld_bf16x4(p.aux_bf16 + static_cast<long long>(row) * p.ld_aux + col);
+              x.x *= gelu_erf_grad(u.x); x.y *= gelu_erf_grad(u.y);
+              x.z *= gelu_erf_grad(u.z); x.w *= gelu_erf_grad(u.w);
+            } else if (p.act == 3) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            if (p.residual != nullptr && first_split) {
+              const float4 rr = *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+            if (p.out_f32 != nullptr) {
+              float* o = p.out_f32 + static_cast<long long>(row) * p.ld_f32 + col;
+              if (p.accumulate) {
+                atomicAdd(o + 0, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+              } else {
+                *reinterpret_cast<float4*>(o) = x;
+              }
+            }
+            if (p.out_bf16 != nullptr) st_bf16x4(p.out_bf16 + static_cast<long long>(row) * p.ld_bf16 + col, x);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor, dim0 contiguous (length d0), dim1 with stride ld elements; box = {64, box1}; 128B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(OAT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return set_error(OAT_ERR_ARG, "TMA operand needs 16-byte aligned base and row pitch (ptr=%p ld=%llu)", ptr,
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(OAT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return OAT_OK;
+}
+
+static int pick_split_k(int tiles_mn, int k_blocks, int sms, int requested) {
+  if (requested > 0) return requested < k_blocks ? requested : (k_blocks > 0 ? k_blocks : 1);
+  if (tiles_mn >= sms || k_blocks < 16) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64 && s * 8 <= k_blocks; ++s) {
+    // every split must own at least one k-block
+    const int per = (k_blocks + s - 1) / s;
+    if ((s - 1) * per >= k_blocks) continue;
+    const long long t = 1LL * tiles_mn * s;
+    const long long waves = (t + sms - 1) / sms;
+    const double eff = double(t) / double(waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&ta, a->A, a->K, a->M, a->lda, BLOCK_M);
+  else rc = make_tmap_bf16_2d(&ta, a->A, a->M, a->K, a->lda, BLOCK_K);
+  if (rc != OAT_OK) return rc;
+  if (!B_MN) rc = make_tmap_bf16_2d(&tb, a->B, a->K, a->N, a->ldb, BLOCK_N);
+  else rc = make_tmap_bf16_2d(&tb, a->B, a->N, a->K, a->ldb, BLOCK_K);
+  if (rc != OAT_OK) return rc;
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_m_blocks = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (a->N + BLOCK_N - 1) / BLOCK_N;
+  p.k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
+  const int sms = num_sms();
+  p.split_k = pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, sms, a->split_k);
+  {  // no empty splits
+    const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
+    p.split_k = (p.k_blocks + per - 1) / per;
+  }
+  if (p.split_k > 1 && !(a->accumulate && a->out_f32 != nullptr && a->out_bf16 == nullptr && a->act == 0))
+    return set_error(OAT_ERR_ARG, "split-K needs accumulate=1 into an fp32 output and no activation");
+  p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
+  p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->ld_bf16;
+  p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p.ld2 = a->ld2;
+  p.aux_bf16 = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16); p.ld_aux = a->ld_aux;
+  p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
+  p.accumulate = a->accumulate;
+
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", S::kTotal, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long tiles = 1LL * p.num_m_blocks * p.num_n_blocks * p.split_k;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+}  // namespace oat
+
+extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
+  using namespace oat;
+  OAT_REQUIRE(a != nullptr, "oat_gemm_bf16: null args");
+  OAT_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "oat_gemm_bf16: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+  OAT_REQUIRE(a->N % 4 == 0, "oat_gemm_bf16: N=%d must be a multiple of 4", a->N);
+  OAT_REQUIRE(a->out_f32 != nullptr || a->out_bf16 != nullptr, "oat_gemm_bf16: no output");
+  OAT_REQUIRE(a->act != 1 || a->out2_bf16 != nullptr, "oat_gemm_bf16: GELU forward needs out2_bf16");
+  OAT_REQUIRE(a->act != 2 || a->aux_bf16 != nullptr, "oat_gemm_bf16: GELU backward needs aux_bf16");
+  OAT_REQUIRE(a->scale_cols % 4 == 0, "oat_gemm_bf16: scale_cols must be a multiple of 4");
+  cudaStream_t s = as_stream(stream);
+  const bool amn = a->a_major != 0, bmn = a->b_major != 0;
+  // 256-wide tiles unless the problem is narrow
+  const bool wide = (a->N % 256 == 0) || a->N > 512;
+  if (wide) {
+    if (!amn && !bmn) return launch_gemm<256, false, false>(a, s);
+    if (!amn && bmn) return launch_gemm<256, false, true>(a, s);
+    if (amn && bmn) return launch_gemm<256, true, true>(a, s);
+    return launch_gemm<256, true, false>(a, s);
+  } else {
+    if (!amn && !bmn) return launch_gemm<128, false, false>(a, s);
+    if (!amn && bmn) return launch_gemm<128, false, true>(a, s);
+    if (amn && bmn) return launch_gemm<128, true, true>(a, s);
+    return launch_gemm<128, true, false>(a, s);
+  }
+}

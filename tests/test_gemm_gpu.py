@@ -1,0 +1,101 @@
+"""tcgen05 GEMM vs torch fp32 matmul on the same bf16-rounded operands (tolerance: fp32 accumulation order only)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(torch.bfloat16).cuda()
+
+
+def _ref(A, B, a_major, b_major):
+    a = A.float() if a_major == 0 else A.float().t()
+    b = B.float() if b_major == 0 else B.float().t()
+    return a @ b.t()
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 768), (1857, 2304, 768), (256, 128, 200), (64, 256, 2112)])
+def test_gemm_plain(M, N, K, a_major, b_major):
+    from oa_transformer_b200 import ops
+    A = _mk((M, K) if a_major == 0 else (K, M + (-M) % 8), 1)
+    B = _mk((N, K) if b_major == 0 else (K, N), 2)
+    if a_major == 1:
+        A = A[:, :M]
+    if K % 8 != 0 and (a_major == 0 or b_major == 0):
+        pytest.skip("K-major operands need a 16-byte row pitch")
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(A, B, a_major=a_major, b_major=b_major, out_f32=out)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_major, b_major)
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, "max abs err %g (scale %g)" % (err, scale)
+
+
+def test_gemm_epilogue_bias_scale_residual_bf16():
+    from oa_transformer_b200 import ops
+    M, N, K = 500, 2304, 768
+    A, B = _mk((M, K), 3), _mk((N, K), 4)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, scale_cols=768, scale=0.125, residual=res, out_f32=o32, out_bf16=o16)
+    ref = A.float() @ B.float().t() + bias
+    ref[:, :768] *= 0.125
+    ref = ref + res
+    assert torch.allclose(o32, ref, rtol=1e-3, atol=2e-3)
+    assert torch.allclose(o16.float(), ref, rtol=1e-2, atol=2e-2)
+
+
+def test_gemm_gelu_forward_backward():
+    from oa_transformer_b200 import ops
+    M, N, K = 300, 3072, 768
+    A, B = _mk((M, K), 5), _mk((N, K), 6)
+    B = (B.float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_bf16=act, out2_bf16=pre)
+    u = A.float() @ B.float().t() + bias
+    assert torch.allclose(pre.float(), u, rtol=1e-2, atol=1e-2)
+    g = torch.nn.functional.gelu(pre.float())
+    assert torch.allclose(act.float(), g, rtol=1e-2, atol=1e-2)
+    # backward: dU = (dG @ W) * gelu'(pre)   with W = [N_out, K_in] stored row-major -> MN-major B operand
+    dG = _mk((M, 768), 7)
+    W2 = (_mk((768, N), 8).float() * 0.05).to(torch.bfloat16)  # fc2.weight [768, 3072]
+    dU = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dG, W2, b_major=1, act=ops.ACT_GELU_BWD, aux=pre, out_bf16=dU)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dG.float() @ W2.float())
+    assert torch.allclose(dU.float(), x.grad, rtol=2e-2, atol=2e-2)
+
+
+def test_gemm_wgrad_splitk_accumulate():
+    from oa_transformer_b200 import ops
+    T, Nout, Kin = 5000, 768, 768
+    dY, X = _mk((T, Nout), 9), _mk((T, Kin), 10)
+    dW = torch.ones(Nout, Kin, device="cuda")
+    ops.gemm(dY, X, a_major=1, b_major=1, out_f32=dW, accumulate=True)
+    ref = dY.float().t() @ X.float() + 1.0
+    err = (dW - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-2, err
+    # forced split counts
+    for s in (1, 3, 7):
+        dW.zero_()
+        ops.gemm(dY, X, a_major=1, b_major=1, out_f32=dW, accumulate=True, split_k=s)
+        err = (dW - (ref - 1.0)).abs().max().item()
+        assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (s, err)
+
+
+def test_gemm_many_tiles_persistent():
+    from oa_transformer_b200 import ops
+    M, N, K = 128 * 150 + 17, 768, 256  # more tiles than SMs, TMEM double-buffer phases wrap several times
+    A, B = _mk((M, K), 11), _mk((N, K), 12)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, out_bf16=out)
+    ref = A.float() @ B.float().t()
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=0.15)
