@@ -64,6 +64,81 @@ typedef struct oat_gemm_args {
 } oat_gemm_args;
 int oat_gemm_bf16(const oat_gemm_args* args, oat_stream_t stream);
 
+/* ---- LayerNorm over the embedding dimension (D in {128,256,512,768,1024}) ------------------------------------
+ * Forward: y = (x - mean) * rstd * gamma + beta per row; writes bf16 (GEMM operand) and/or fp32 outputs and the
+ * row statistics needed by backward. Replaces nn.LayerNorm(eps=1e-6) at video_transformer.py:164,167,174,346 and
+ * DistilBERT's LayerNorm(eps=1e-12). Rows may be strided (ldx) so that only the CLS rows are normalised for :351.
+ * Backward: dy = dy_bf16 (+ dy_f32); dx = add1 + add2 + LN'(dy); dgamma/dbeta are ACCUMULATED (atomics). */
+int oat_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t rows,
+                      int32_t D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
+                      oat_stream_t stream);
+int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float* dy_f32, int64_t lddyf, const float* x,
+                      int64_t ldx, const float* mean, const float* rstd, const float* gamma, int64_t rows, int32_t D,
+                      const float* add1, const float* add2, int64_t ldadd, float* dx, int64_t lddx, void* dx_bf16,
+                      int64_t lddxb, float* dgamma, float* dbeta, oat_stream_t stream);
+
+/* ---- attention ------------------------------------------------------------------------------------------------
+ * qkv: bf16 [B*T, 3*H*64] as produced by the qkv GEMM (q already scaled by 64^-0.5, columns q | k | v, head-major).
+ * mode 0 "space": T = 1 + F*n; token (f,i) attends to [CLS] + the n tokens of frame f.
+ * mode 1 "time" : token (f,i) attends to [CLS] + tokens (f',i) of every frame f'.
+ *   In both, the CLS query (token 0) attends to all T keys.           (video_transformer.py:99-135)
+ * mode 2 "plain": every token attends to every key with key_mask[b*T+j] != 0 (DistilBERT self-attention).
+ * out: bf16 [B*T, H*64]; lse: fp32 [B*H*T] log-sum-exp per query (saved for backward).
+ * Backward consumes dout (bf16, same layout as out) and writes dqkv (bf16, same layout as qkv; the q part is the
+ * gradient w.r.t. the UNSCALED projection, i.e. multiplied by `scale`). cls_acc: fp32 [B*H*3*64] scratch. */
+typedef struct oat_attn_args {
+  int32_t mode, B, T, H, F, n;
+  const void* qkv; int64_t ld_qkv;
+  void* out; int64_t ld_out;
+  float* lse;
+  const int32_t* key_mask;
+  const void* dout; int64_t ld_dout;
+  void* dqkv; int64_t ld_dqkv;
+  float scale;
+  float* cls_acc;
+} oat_attn_args;
+int oat_attn_fwd(const oat_attn_args* args, oat_stream_t stream);
+int oat_attn_bwd(const oat_attn_args* args, oat_stream_t stream);
+
+/* ---- operand packing and token bookkeeping (HBM-bound) ---------------------------------------------------------
+ * oat_cast_bf16: dst[r, c] = bf16(src[r, c]) for c < cols, 0 for cols <= c < cols_padded (optional ReLU first:
+ *   the ReLU of txt_proj, oa_model.py:68). Used for weights, region features (2054 -> padded pitch) and CLS rows.
+ * oat_relu_bwd: dx = (x > 0) ? dy : 0.
+ * oat_im2col_patches: video fp32 [BF, C, H, W] -> bf16 [BF*(H/P)*(W/P), C*P*P] in Conv2d weight order
+ *   (VideoPatchEmbed, video_transformer.py:69-76: kernel = stride = P makes the convolution a GEMM).
+ * oat_assemble_tokens: x[b,0] = cls + pos[0]; x[b,1+f*n+i] = patch + pos[1+i] + temporal[f] (i < N);
+ *   x[b,1+f*n+N+o] = object + temporal[f]; n = N + O; optional token-type rows [2, D]
+ *   (forward_features, video_transformer.py:303-325; oa_video_transformer_region.py:250-261).
+ * oat_assemble_tokens_bwd: scatters dx to bf16 dpatch / dobject and ACCUMULATES dcls, dpos, dtemporal, dtype.
+ * oat_colsum_bf16: out[c] += sum_r x[r, c]  (bias gradients).
+ * oat_text_embed(_bwd): DistilBERT word + position embedding sum and its scatter-add gradient. */
+int oat_cast_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
+                  int32_t cols_padded, int32_t relu, oat_stream_t stream);
+int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,
+                 int64_t rows, int32_t cols, oat_stream_t stream);
+int oat_im2col_patches(const float* video, void* out_bf16, int64_t BF, int32_t C, int32_t H, int32_t W, int32_t P,
+                       oat_stream_t stream);
+int oat_assemble_tokens(const float* patch, const float* object, const float* cls_token, const float* pos_embed,
+                        const float* temporal_embed, const float* type_embed, float* x, int32_t B, int32_t F,
+                        int32_t N, int32_t O, int32_t D, oat_stream_t stream);
+int oat_assemble_tokens_bwd(const float* dx, void* dpatch_bf16, void* dobject_bf16, float* dcls, float* dpos,
+                            float* dtemporal, float* dtype_embed, int32_t B, int32_t F, int32_t N, int32_t O,
+                            int32_t D, oat_stream_t stream);
+int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int32_t cols, float* out, oat_stream_t stream);
+int oat_text_embed(const int64_t* ids, const float* word_emb, const float* pos_emb, float* out, int64_t rows,
+                   int32_t L, int32_t D, oat_stream_t stream);
+int oat_text_embed_bwd(const int64_t* ids, const float* dsum, float* dword, float* dpos, int64_t rows, int32_t L,
+                       int32_t D, oat_stream_t stream);
+
+/* ---- similarity matrix + symmetric InfoNCE, forward and backward ------------------------------------------------
+ * text, video: fp32 [n, P] GATHERED embeddings (rows = the global batch). Writes sims [n, n] (optional), the scalar
+ * loss, and dL/dtext, dL/dvideo [n, P] (optional). The caller slices its local rows: the all-gather backward is a
+ * slice without reduction (trainer_dist.py:40-45). Replaces model/model.py:164-172 + model/loss.py:13-25. */
+size_t oat_infonce_workspace_bytes(int32_t n, int32_t P);
+int oat_infonce_fwd_bwd(const float* text, const float* video, int32_t n, int32_t P, float temperature, float eps,
+                        float* sims_out, float* loss, float* dtext, float* dvideo, void* workspace,
+                        size_t workspace_bytes, oat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

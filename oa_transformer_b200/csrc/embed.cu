@@ -1,0 +1,304 @@
+// Data-movement kernels around the contractions: fp32 -> bf16 operand packing, patch extraction (im2col for the
+// k16/s16 patch "convolution"), token assembly (CLS + positional + temporal embeddings, frame-major patch tokens
+// followed by that frame's object tokens), their gradients, column sums for bias gradients, and the DistilBERT
+// embedding lookup / scatter. All HBM-bound: 128-bit accesses, grid sized by rows, no shared-memory staging needed
+// (every element is touched once).
+//
+// Reference call sites: VideoPatchEmbed.forward OATrans/model/video_transformer.py:71-76; forward_features
+// :303-325 (token index 1 + f*n + i, pos_embed[1+i] tiled over frames, temporal_embed[f] repeated inside a frame);
+// object_embed OATrans/model/oa_video_transformer_region.py:250,257-261; HF DistilBERT Embeddings.
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+// ------------------------------------------------------------------------------------------------ cast / pack
+__global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                 long long ldd, long long rows, int cols, int cols_padded, int relu) {
+  const int vec_per_row = cols_padded >> 2;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const int c = static_cast<int>(idx - r * vec_per_row) << 2;
+    float v[4];
+    const float* s = src + r * lds + c;
+    if (c + 3 < cols && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+      const float4 f = *reinterpret_cast<const float4*>(s);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < cols) ? s[k] : 0.f;
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    uint2 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = pk;
+  }
+}
+
+// dx[r, c] = relu_mask(x[r, c]) * dy_bf16[r, c]  (fp32 out) - backward of the ReLU in txt_proj (oa_model.py:68)
+__global__ void relu_bwd_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
+                                long long lddy, float* __restrict__ dx, long long lddx, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / cols;
+    const int c = static_cast<int>(idx - r * cols);
+    dx[r * lddx + c] = x[r * ldx + c] > 0.f ? __bfloat162float(dy[r * lddy + c]) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ patches
+// video fp32 [BF, C, H, W] -> bf16 [BF*gh*gw, C*P*P], k = c*P*P + i*P + j (the flattened Conv2d weight order)
+__global__ void im2col_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__ out, long long BF, int C,
+                              int H, int W, int P) {
+  const int gw = W / P, gh = H / P;
+  const int w8 = W >> 3;
+  const long long total = BF * C * H * w8;
+  const int K = C * P * P;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x8 = static_cast<int>(idx % w8);
+    long long rest = idx / w8;
+    const int y = static_cast<int>(rest % H); rest /= H;
+    const int c = static_cast<int>(rest % C);
+    const long long bf = rest / C;
+    const float* s = video + ((bf * C + c) * H + y) * static_cast<long long>(W) + x8 * 8;
+    const float4 a = *reinterpret_cast<const float4*>(s);
+    const float4 b = *reinterpret_cast<const float4*>(s + 4);
+    const int x = x8 * 8;
+    const int gx = x / P, j = x - gx * P, gy = y / P, i = y - gy * P;
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+    pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + ((bf * gh + gy) * gw + gx) * static_cast<long long>(K) + c * P * P + i * P + j) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ token assembly
+// x[b, 0]           = cls_token + pos_embed[0]
+// x[b, 1+f*n+i]     = patch[(b*F+f)*N+i] + pos_embed[1+i] + temporal[f] (+ type[0])          i <  N
+// x[b, 1+f*n+N+o]   = object[(b*F+f)*O+o] + temporal[f] (+ type[1])                          o <  O
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ object,
+                                       const float* __restrict__ cls_token, const float* __restrict__ pos_embed,
+                                       const float* __restrict__ temporal, const float* __restrict__ type_embed,
+                                       float* __restrict__ x, int B, int F, int N, int O, int D) {
+  const int n = N + O, T = 1 + F * n, d4 = D >> 2;
+  const long long total = static_cast<long long>(B) * T * d4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4) << 2;
+    const long long bt = idx / d4;
+    const int tok = static_cast<int>(bt % T);
+    const int b = static_cast<int>(bt / T);
+    float4 v;
+    if (tok == 0) {
+      const float4 a = *reinterpret_cast<const float4*>(cls_token + c);
+      const float4 p = *reinterpret_cast<const float4*>(pos_embed + c);
+      v = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else {
+      const int f = (tok - 1) / n, i = (tok - 1) - f * n;
+      const float4 te = *reinterpret_cast<const float4*>(temporal + static_cast<long long>(f) * D + c);
+      if (i < N) {
+        const float4 a = *reinterpret_cast<const float4*>(patch + ((static_cast<long long>(b) * F + f) * N + i) * D + c);
+        const float4 p = *reinterpret_cast<const float4*>(pos_embed + static_cast<long long>(1 + i) * D + c);
+        v = make_float4(a.x + p.x + te.x, a.y + p.y + te.y, a.z + p.z + te.z, a.w + p.w + te.w);
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(object + ((static_cast<long long>(b) * F + f) * O + (i - N)) * D + c);
+        v = make_float4(a.x + te.x, a.y + te.y, a.z + te.z, a.w + te.w);
+      }
+      if (type_embed != nullptr) {
+        const float4 ty = *reinterpret_cast<const float4*>(type_embed + (i < N ? 0 : D) + c);
+        v.x += ty.x; v.y += ty.y; v.z += ty.z; v.w += ty.w;
+      }
+    }
+    *reinterpret_cast<float4*>(x + bt * D + c) = v;
+  }
+}
+
+// Gradient of the assembly: scatters dx (fp32 [B,T,D]) into bf16 operand buffers for the patch / object embedding
+// weight gradients and reduces the embedding-table gradients over the batch (one thread per (token, 4 dims),
+// looping over b, then a handful of atomics).
+__global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, __nv_bfloat16* __restrict__ dpatch,
+                                           __nv_bfloat16* __restrict__ dobject, float* __restrict__ dcls,
+                                           float* __restrict__ dpos, float* __restrict__ dtemporal,
+                                           float* __restrict__ dtype_embed, int B, int F, int N, int O, int D) {
+  const int n = N + O, T = 1 + F * n, d4 = D >> 2;
+  const long long total = static_cast<long long>(T) * d4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4) << 2;
+    const int tok = static_cast<int>(idx / d4);
+    const int f = tok == 0 ? 0 : (tok - 1) / n, i = tok == 0 ? 0 : (tok - 1) - f * n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      const float4 g = *reinterpret_cast<const float4*>(dx + (static_cast<long long>(b) * T + tok) * D + c);
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      if (tok != 0) {
+        uint2 pk;
+        pk.x = pack_bf16x2(g.x, g.y);
+        pk.y = pack_bf16x2(g.z, g.w);
+        if (i < N) {
+          if (dpatch != nullptr)
+            *reinterpret_cast<uint2*>(dpatch + ((static_cast<long long>(b) * F + f) * N + i) * D + c) = pk;
+        } else if (dobject != nullptr) {
+          *reinterpret_cast<uint2*>(dobject + ((static_cast<long long>(b) * F + f) * O + (i - N)) * D + c) = pk;
+        }
+      }
+    }
+    auto add4 = [&](float* p) {
+      atomicAdd(p + 0, acc.x); atomicAdd(p + 1, acc.y); atomicAdd(p + 2, acc.z); atomicAdd(p + 3, acc.w);
+    };
+    if (tok == 0) {
+      if (dcls != nullptr) add4(dcls + c);
+      if (dpos != nullptr) add4(dpos + c);
+    } else {
+      if (dtemporal != nullptr) add4(dtemporal + static_cast<long long>(f) * D + c);
+      if (i < N && dpos != nullptr) add4(dpos + static_cast<long long>(1 + i) * D + c);
+      if (dtype_embed != nullptr) add4(dtype_embed + (i < N ? 0 : D) + c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a slab of rows for all columns.
+constexpr int kColsumRowsPerCta = 256;
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int cols,
+                                   float* __restrict__ out) {
+  const long long r0 = static_cast<long long>(blockIdx.x) * kColsumRowsPerCta;
+  const long long r1 = min(rows, r0 + kColsumRowsPerCta);
+  for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
+    float s0 = 0.f, s1 = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      s0 += v.x; s1 += v.y;
+    }
+    atomicAdd(out + c, s0);
+    atomicAdd(out + c + 1, s1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ text embeddings
+// out[b*L + l] = word_emb[ids[b*L+l]] + pos_emb[l]   (fp32; the LayerNorm kernel follows)
+__global__ void text_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                  const float* __restrict__ pos, float* __restrict__ out, long long rows, int L, int D) {
+  const int d4 = D >> 2;
+  const long long total = rows * d4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4) << 2;
+    const long long r = idx / d4;
+    const float4 w = *reinterpret_cast<const float4*>(word + ids[r] * D + c);
+    const float4 p = *reinterpret_cast<const float4*>(pos + (r % L) * D + c);
+    *reinterpret_cast<float4*>(out + r * D + c) = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, w.w + p.w);
+  }
+}
+__global__ void text_embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dsum,
+                                      float* __restrict__ dword, float* __restrict__ dpos, long long rows, int L, int D) {
+  const long long total = rows * D;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % D);
+    const long long r = idx / D;
+    const float g = dsum[idx];
+    if (dword != nullptr) atomicAdd(dword + ids[r] * D + c, g);
+    if (dpos != nullptr) atomicAdd(dpos + (r % L) * D + c, g);
+  }
+}
+
+static unsigned grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace oat
+
+using namespace oat;
+
+extern "C" int oat_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols,
+                             int32_t cols_padded, int32_t relu, oat_stream_t stream) {
+  OAT_REQUIRE(cols > 0 && cols_padded >= cols && cols_padded % 4 == 0 && ldd % 4 == 0 && ldd >= cols_padded,
+              "oat_cast_bf16: cols=%d cols_padded=%d ldd=%lld (padded width and pitch must be multiples of 4)", cols,
+              cols_padded, (long long)ldd);
+  if (rows <= 0) return OAT_OK;
+  const long long total = rows * (cols_padded / 4);
+  cast_bf16_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded, relu);
+  return check_launch("cast_bf16_kernel");
+}
+
+extern "C" int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,
+                            int64_t rows, int32_t cols, oat_stream_t stream) {
+  if (rows <= 0) return OAT_OK;
+  relu_bwd_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(
+      x, ldx, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), lddy, dx, lddx, rows, cols);
+  return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int oat_im2col_patches(const float* video, void* out_bf16, int64_t BF, int32_t C, int32_t H, int32_t W,
+                                  int32_t P, oat_stream_t stream) {
+  OAT_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "oat_im2col_patches: H=%d W=%d must be multiples of P=%d (P %% 8 == 0)", H, W, P);
+  if (BF <= 0) return OAT_OK;
+  const long long total = BF * C * H * (W / 8);
+  im2col_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(video, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                    BF, C, H, W, P);
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int oat_assemble_tokens(const float* patch, const float* object, const float* cls_token,
+                                   const float* pos_embed, const float* temporal_embed, const float* type_embed,
+                                   float* x, int32_t B, int32_t F, int32_t N, int32_t O, int32_t D,
+                                   oat_stream_t stream) {
+  OAT_REQUIRE(D % 4 == 0 && B > 0 && F > 0 && N > 0 && O >= 0, "oat_assemble_tokens: bad geometry");
+  OAT_REQUIRE(O == 0 || object != nullptr, "oat_assemble_tokens: object tokens requested without object embeddings");
+  const long long total = static_cast<long long>(B) * (1 + F * (N + O)) * (D / 4);
+  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(patch, object, cls_token, pos_embed,
+                                                                             temporal_embed, type_embed, x, B, F, N, O, D);
+  return check_launch("assemble_tokens_kernel");
+}
+
+extern "C" int oat_assemble_tokens_bwd(const float* dx, void* dpatch_bf16, void* dobject_bf16, float* dcls,
+                                       float* dpos, float* dtemporal, float* dtype_embed, int32_t B, int32_t F,
+                                       int32_t N, int32_t O, int32_t D, oat_stream_t stream) {
+  OAT_REQUIRE(D % 4 == 0 && B > 0 && F > 0 && N > 0 && O >= 0, "oat_assemble_tokens_bwd: bad geometry");
+  const long long total = static_cast<long long>(1 + F * (N + O)) * (D / 4);
+  assemble_tokens_bwd_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(
+      dx, reinterpret_cast<__nv_bfloat16*>(dpatch_bf16), reinterpret_cast<__nv_bfloat16*>(dobject_bf16), dcls, dpos,
+      dtemporal, dtype_embed, B, F, N, O, D);
+  return check_launch("assemble_tokens_bwd_kernel");
+}
+
+extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int32_t cols, float* out,
+                               oat_stream_t stream) {
+  OAT_REQUIRE(cols % 2 == 0 && ld % 2 == 0, "oat_colsum_bf16: cols and ld must be even");
+  if (rows <= 0) return OAT_OK;
+  const unsigned grid = static_cast<unsigned>((rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta);
+  colsum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows,
+                                                          cols, out);
+  return check_launch("colsum_bf16_kernel");
+}
+
+extern "C" int oat_text_embed(const int64_t* ids, const float* word_emb, const float* pos_emb, float* out,
+                              int64_t rows, int32_t L, int32_t D, oat_stream_t stream) {
+  OAT_REQUIRE(D % 4 == 0 && L > 0, "oat_text_embed: bad geometry");
+  if (rows <= 0) return OAT_OK;
+  text_embed_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(ids), word_emb, pos_emb, out, rows, L, D);
+  return check_launch("text_embed_kernel");
+}
+
+extern "C" int oat_text_embed_bwd(const int64_t* ids, const float* dsum, float* dword, float* dpos, int64_t rows,
+                                  int32_t L, int32_t D, oat_stream_t stream) {
+  if (rows <= 0) return OAT_OK;
+  text_embed_bwd_kernel<<<grid_for(rows * D, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(ids), dsum, dword, dpos, rows, L, D);
+  return check_launch("text_embed_bwd_kernel");
+}

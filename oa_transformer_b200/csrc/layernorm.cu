@@ -1,0 +1,223 @@
+// LayerNorm forward / backward over the embedding dimension - HBM-bound row kernels, one warp per row,
+// 128-bit loads, fp32 statistics by warp shuffle, values held in registers between the two passes.
+//
+// Reference call sites: nn.LayerNorm(eps=1e-6) norm1/norm2/norm3/norm in OATrans/model/video_transformer.py:164-174,346
+// (pre-LN), and HF DistilBERT's LayerNorm(eps=1e-12) after the embeddings and after each residual add (post-LN).
+// Forward writes the bf16 operand of the next GEMM (and optionally the fp32 value for a post-LN residual stream);
+// backward fuses the residual-gradient adds and emits the bf16 copy the next dgrad/wgrad GEMM consumes.
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+constexpr int kLnWarps = 8;
+
+template <int NV>  // D = NV * 128
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, long long rows, __nv_bfloat16* __restrict__ y_bf16,
+                     long long ldy, float* __restrict__ y_f32, long long ldyf, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  if (lane == 0) {
+    if (mean_out != nullptr) mean_out[row] = mean;
+    if (rstd_out != nullptr) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+    const float4 b = reinterpret_cast<const float4*>(beta)[i * 32 + lane];
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y_f32 != nullptr) reinterpret_cast<float4*>(y_f32 + row * ldyf)[i * 32 + lane] = o;
+    if (y_bf16 != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(y_bf16 + row * ldy)[i * 32 + lane] = pk;
+    }
+  }
+}
+
+// dx = add1 + add2 + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  dy = dy_bf16 + dy_f32
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy   (per-lane register partials -> smem -> one atomic per column)
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb, const float* __restrict__ dy_f32,
+                     long long lddyf, const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows,
+                     const float* __restrict__ add1, const float* __restrict__ add2, long long ldadd,
+                     float* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int D = NV * 128;
+  __shared__ float red[kLnWarps][D];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 gm[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gm[i] = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = static_cast<long long>(blockIdx.x) * kLnWarps + warp; row < rows;
+       row += static_cast<long long>(gridDim.x) * kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 xv = reinterpret_cast<const float4*>(x + row * ldx)[i * 32 + lane];
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy_bf16 != nullptr) {
+        const uint2 raw = reinterpret_cast<const uint2*>(dy_bf16 + row * lddyb)[i * 32 + lane];
+        const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+        d = make_float4(a.x, a.y, b.x, b.y);
+      }
+      if (dy_f32 != nullptr) {
+        const float4 f = reinterpret_cast<const float4*>(dy_f32 + row * lddyf)[i * 32 + lane];
+        d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+      }
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 o;
+      o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+      o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+      o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+      o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+      if (add1 != nullptr) {
+        const float4 a = reinterpret_cast<const float4*>(add1 + row * ldadd)[i * 32 + lane];
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (add2 != nullptr) {
+        const float4 a = reinterpret_cast<const float4*>(add2 + row * ldadd)[i * 32 + lane];
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (dx != nullptr) reinterpret_cast<float4*>(dx + row * lddx)[i * 32 + lane] = o;
+      if (dx_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * lddxb)[i * 32 + lane] = pk;
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  // cross-warp reduction of the per-lane column partials, then one atomic per column per CTA
+  for (int pass = 0; pass < 2; ++pass) {
+    float4* src = pass == 0 ? dg : db;
+    float* dst = pass == 0 ? dgamma : dbeta;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(red[warp])[i * 32 + lane] = src[i];
+    __syncthreads();
+    if (dst != nullptr) {
+      for (int c = threadIdx.x; c < D; c += kLnWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+        atomicAdd(dst + c, s);
+      }
+    }
+  }
+}
+
+template <int NV>
+static int launch_ln_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                         long long rows, void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean,
+                         float* rstd, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
+  layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(x, ldx, gamma, beta, eps, rows,
+                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, y_f32, ldyf,
+                                                          mean, rstd);
+  return check_launch("layernorm_fwd_kernel");
+}
+
+template <int NV>
+static int launch_ln_bwd(const void* dyb, long long lddyb, const float* dyf, long long lddyf, const float* x,
+                         long long ldx, const float* mean, const float* rstd, const float* gamma, long long rows,
+                         const float* add1, const float* add2, long long ldadd, float* dx, long long lddx,
+                         void* dxb, long long lddxb, float* dgamma, float* dbeta, cudaStream_t s) {
+  long long want = (rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dyb), lddyb, dyf, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2,
+      ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+}  // namespace oat
+
+extern "C" int oat_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                                 int64_t rows, int32_t D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf,
+                                 float* mean, float* rstd, oat_stream_t stream) {
+  using namespace oat;
+  OAT_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024, "oat_layernorm_fwd: D=%d must be a multiple of 128, <= 1024", D);
+  OAT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldyf % 4 == 0, "oat_layernorm_fwd: leading dims must be multiples of 4");
+  if (rows == 0) return OAT_OK;
+  cudaStream_t s = as_stream(stream);
+  switch (D / 128) {
+    case 1: return launch_ln_fwd<1>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    case 2: return launch_ln_fwd<2>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    case 4: return launch_ln_fwd<4>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    case 6: return launch_ln_fwd<6>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    case 8: return launch_ln_fwd<8>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    default: return set_error(OAT_ERR_ARG, "oat_layernorm_fwd: unsupported D=%d (128, 256, 512, 768, 1024)", D);
+  }
+}
+
+extern "C" int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float* dy_f32, int64_t lddyf,
+                                 const float* x, int64_t ldx, const float* mean, const float* rstd,
+                                 const float* gamma, int64_t rows, int32_t D, const float* add1, const float* add2,
+                                 int64_t ldadd, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, float* dgamma,
+                                 float* dbeta, oat_stream_t stream) {
+  using namespace oat;
+  OAT_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024, "oat_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
+  OAT_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "oat_layernorm_bwd: no incoming gradient");
+  if (rows == 0) return OAT_OK;
+  cudaStream_t s = as_stream(stream);
+#define OAT_LN_BWD(NV)                                                                                              \
+  return launch_ln_bwd<NV>(dy_bf16, lddyb, dy_f32, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2, ldadd, dx, \
+                           lddx, dx_bf16, lddxb, dgamma, dbeta, s)
+  switch (D / 128) {
+    case 1: OAT_LN_BWD(1);
+    case 2: OAT_LN_BWD(2);
+    case 4: OAT_LN_BWD(4);
+    case 6: OAT_LN_BWD(6);
+    case 8: OAT_LN_BWD(8);
+    default: return set_error(OAT_ERR_ARG, "oat_layernorm_bwd: unsupported D=%d (128, 256, 512, 768, 1024)", D);
+  }
+#undef OAT_LN_BWD
+}

@@ -1,0 +1,201 @@
+// Batch-wide similarity + symmetric InfoNCE (forward and backward).
+//
+// Reference: sim_matrix, OATrans/model/model.py:164-172 (rows L2-normalised with the norm clamped at eps, then
+// a_n @ b_n^T; rows = text, columns = video, trainer_dist.py:161) and NormSoftmaxLoss.forward,
+// OATrans/model/loss.py:13-25 (log_softmax(x/T) over rows and over columns, mean of the two diagonals, negated).
+//
+// Pipeline (all on the caller's stream; the (Bg x Bg) matrix is tiny next to the towers, so the goal is accuracy
+// and few launches, not tensor throughput):
+//   1. normalise: one warp per row -> fp32 unit rows + a bf16 "hi | hi | lo" / "hi | lo | hi" split packing so
+//      that the tcgen05 bf16 GEMM (K = 3*P) reproduces the fp32 dot product to ~2^-16 relative;
+//   2. sims = A' . B'^T on the tcgen05 GEMM (oat_gemm_bf16);
+//   3. row and column log-sum-exp of sims/T (one CTA per row / column);
+//   4. loss scalar + dL/dsims = (softmax_row + softmax_col - 2 I) / (Bg T);
+//   5. dL/d(unit rows) by fp32 SIMT products, then through the normalisation to dL/d(embeddings).
+// The gradient rows of the LOCAL samples are sliced by the caller: the all-gather backward is a slice with no
+// reduction (trainer_dist.py:40-45).
+#include <string.h>
+
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+// a [rows, P] fp32 -> an [rows, P] fp32 (unit rows), inv_norm [rows], pack [rows, 3P] bf16
+// order = 0: hi | hi | lo     order = 1: hi | lo | hi
+__global__ void loss_normalize_kernel(const float* __restrict__ a, float* __restrict__ an, float* __restrict__ inv_norm,
+                                      __nv_bfloat16* __restrict__ pack, int rows, int P, float eps, int order) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* r = a + static_cast<long long>(row) * P;
+  float ss = 0.f;
+  for (int c = lane; c < P; c += 32) ss += r[c] * r[c];
+  const float nrm = sqrtf(warp_sum(ss));
+  const float inv = 1.0f / fmaxf(nrm, eps);
+  if (lane == 0) inv_norm[row] = inv;
+  for (int c = lane; c < P; c += 32) {
+    const float v = r[c] * inv;
+    an[static_cast<long long>(row) * P + c] = v;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = pack + static_cast<long long>(row) * 3 * P;
+    o[c] = hi;
+    o[P + c] = order == 0 ? hi : lo;
+    o[2 * P + c] = order == 0 ? lo : hi;
+  }
+}
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) r += sh[w];
+  __syncthreads();
+  return r;
+}
+
+// blockIdx < n: row LSE of sims[i, :]/T ; blockIdx >= n: column LSE of sims[:, j]/T
+__global__ void loss_lse_kernel(const float* __restrict__ sims, int n, int ld, float inv_t,
+                                float* __restrict__ row_lse, float* __restrict__ col_lse) {
+  __shared__ float sh[32];
+  const bool is_col = blockIdx.x >= n;
+  const int k = is_col ? blockIdx.x - n : blockIdx.x;
+  const long long stride = is_col ? ld : 1;
+  const float* p = sims + (is_col ? k : static_cast<long long>(k) * ld);
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, p[i * stride] * inv_t);
+  mx = block_max(mx, sh);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += expf(p[i * stride] * inv_t - mx);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) (is_col ? col_lse : row_lse)[k] = mx + logf(s);
+}
+
+// dsims[i,j] = (exp(s/T - row_lse_i) + exp(s/T - col_lse_j) - 2 [i==j]) / (n T); loss = -(1/n) sum_i (2 s_ii/T - row_lse_i - col_lse_i)
+__global__ void loss_grad_logits_kernel(const float* __restrict__ sims, int n, int ld, float inv_t,
+                                        const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                                        float* __restrict__ dsims, float* __restrict__ loss) {
+  const int i = blockIdx.x;
+  const float rl = row_lse[i];
+  const float g = inv_t / n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float z = sims[static_cast<long long>(i) * ld + j] * inv_t;
+    float d = expf(z - rl) + expf(z - col_lse[j]);
+    if (i == j) {
+      d -= 2.f;
+      atomicAdd(loss, -(2.f * z - rl - col_lse[j]) / n);
+    }
+    if (dsims != nullptr) dsims[static_cast<long long>(i) * ld + j] = d * g;
+  }
+}
+
+// side 0: dan[i,:] = sum_j dsims[i,j] bn[j,:] ; side 1: dbn[j,:] = sum_i dsims[i,j] an[i,:]
+// then through x_n = x * inv (inv = 1/max(|x|, eps)): dx = inv * (dxn - x_n (x_n . dxn)) if the clamp is inactive,
+// else dx = inv * dxn.
+__global__ void loss_grad_embed_kernel(const float* __restrict__ dsims, int n, int ld, int P, const float* __restrict__ other_n,
+                                       const float* __restrict__ self_n, const float* __restrict__ inv_norm, float eps,
+                                       int side, float* __restrict__ dself) {
+  __shared__ float sh[32];
+  const int r = blockIdx.x;
+  const float inv = inv_norm[r];
+  const bool clamped = inv >= (1.0f / eps);
+  for (int c0 = 0; c0 < P; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    float acc = 0.f;
+    if (c < P) {
+      for (int k = 0; k < n; ++k) {
+        const float w = side == 0 ? dsims[static_cast<long long>(r) * ld + k] : dsims[static_cast<long long>(k) * ld + r];
+        acc += w * other_n[static_cast<long long>(k) * P + c];
+      }
+    }
+    // the projection needs the full-row dot product: only valid when P <= blockDim.x (checked on the host)
+    const float xn = c < P ? self_n[static_cast<long long>(r) * P + c] : 0.f;
+    const float dot = block_sum(acc * xn, sh);
+    if (c < P) dself[static_cast<long long>(r) * P + c] = clamped ? inv * acc : inv * (acc - xn * dot);
+  }
+}
+
+}  // namespace oat
+
+using namespace oat;
+
+extern "C" size_t oat_infonce_workspace_bytes(int32_t n, int32_t P) {
+  // an, bn [n,P] fp32 | inv_a, inv_b, row_lse, col_lse [n] | sims, dsims [n,n] fp32 | packA, packB [n,3P] bf16
+  const size_t np = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);   // sims pitch / padded row count
+  size_t f = static_cast<size_t>(2) * np * P + 4 * np + 2 * np * np;
+  size_t bytes = f * 4 + static_cast<size_t>(2) * np * 3 * P * 2;
+  return (bytes + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" int oat_infonce_fwd_bwd(const float* text, const float* video, int32_t n, int32_t P, float temperature,
+                                   float eps, float* sims_out, float* loss, float* dtext, float* dvideo,
+                                   void* workspace, size_t workspace_bytes, oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && P > 0 && P % 8 == 0 && P <= 1024, "oat_infonce_fwd_bwd: n=%d P=%d (P multiple of 8, <= 1024)", n, P);
+  OAT_REQUIRE(workspace != nullptr && workspace_bytes >= oat_infonce_workspace_bytes(n, P),
+              "oat_infonce_fwd_bwd: workspace too small");
+  OAT_REQUIRE(loss != nullptr, "oat_infonce_fwd_bwd: null loss");
+  cudaStream_t s = as_stream(stream);
+  const size_t np = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);
+  const int ld = static_cast<int>(np);
+  float* an = reinterpret_cast<float*>(workspace);
+  float* bn = an + np * P;
+  float* inv_a = bn + np * P;
+  float* inv_b = inv_a + np;
+  float* row_lse = inv_b + np;
+  float* col_lse = row_lse + np;
+  float* sims = col_lse + np;
+  float* dsims = sims + np * np;
+  __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(dsims + np * np);
+  __nv_bfloat16* pb = pa + np * 3 * P;
+  if (np != static_cast<size_t>(n)) {  // zero the padding rows of the packed video operand (padded sims columns)
+    cudaError_t e0 = cudaMemsetAsync(pb + static_cast<size_t>(n) * 3 * P, 0, (np - n) * 3 * P * 2, s);
+    if (e0 != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e0));
+  }
+
+  const int wpb = 8;
+  loss_normalize_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, s>>>(text, an, inv_a, pa, n, P, eps, 0);
+  loss_normalize_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, s>>>(video, bn, inv_b, pb, n, P, eps, 1);
+  int rc = check_launch("loss_normalize_kernel");
+  if (rc != OAT_OK) return rc;
+
+  oat_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = pa; g.lda = 3 * P; g.a_major = 0;
+  g.B = pb; g.ldb = 3 * P; g.b_major = 0;
+  g.M = n; g.N = ld; g.K = 3 * P;
+  g.alpha = 1.0f; g.scale = 1.0f;
+  g.out_f32 = sims; g.ld_f32 = ld;
+  rc = oat_gemm_bf16(&g, stream);
+  if (rc != OAT_OK) return rc;
+  if (sims_out != nullptr) {
+    cudaError_t e = cudaMemcpy2DAsync(sims_out, sizeof(float) * n, sims, sizeof(float) * ld, sizeof(float) * n, n,
+                                      cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  }
+  const float inv_t = 1.0f / temperature;
+  loss_lse_kernel<<<2 * n, 256, 0, s>>>(sims, n, ld, inv_t, row_lse, col_lse);
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), s);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  const bool want_grad = dtext != nullptr || dvideo != nullptr;
+  loss_grad_logits_kernel<<<n, 256, 0, s>>>(sims, n, ld, inv_t, row_lse, col_lse, want_grad ? dsims : nullptr, loss);
+  rc = check_launch("loss_grad_logits_kernel");
+  if (rc != OAT_OK) return rc;
+  if (want_grad) {
+    const int threads = ((P + 31) / 32) * 32;
+    if (dtext != nullptr) loss_grad_embed_kernel<<<n, threads, 0, s>>>(dsims, n, ld, P, bn, an, inv_a, eps, 0, dtext);
+    if (dvideo != nullptr) loss_grad_embed_kernel<<<n, threads, 0, s>>>(dsims, n, ld, P, an, bn, inv_b, eps, 1, dvideo);
+    rc = check_launch("loss_grad_embed_kernel");
+  }
+  return rc;
+}

@@ -62,3 +62,159 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
     check(lib().oat_gemm_bf16(ctypes.byref(a), stream_ptr()), "oat_gemm_bf16")
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+_i64, _i32, _f32, _vp, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f32=None, mean=None, rstd=None):
+    """Row LayerNorm of fp32 x (rows x D, row pitch ldx) -> bf16 and/or fp32 outputs, plus mean / rstd."""
+    D = gamma.numel()
+    rows = x.shape[0] if rows is None else rows
+    ldx = x.stride(0) if ldx is None else ldx
+    check(lib().oat_layernorm_fwd(
+        ptr(x), _i64(ldx), ptr(gamma), ptr(beta), _f32(eps), _i64(rows), _i32(D),
+        ptr(y_bf16), _i64(y_bf16.stride(0) if y_bf16 is not None else 0),
+        ptr(y_f32), _i64(y_f32.stride(0) if y_f32 is not None else 0),
+        ptr(mean), ptr(rstd), stream_ptr()), "oat_layernorm_fwd")
+
+
+def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None, ldx=None, lddyf=None, add1=None,
+                  add2=None, dx=None, dx_bf16=None, lddx=None, lddxb=None, dgamma=None, dbeta=None):
+    D = gamma.numel()
+    rows = x.shape[0] if rows is None else rows
+    ldx = x.stride(0) if ldx is None else ldx
+    ldadd = add1.stride(0) if add1 is not None else (add2.stride(0) if add2 is not None else 0)
+    if add1 is not None and add2 is not None:
+        assert add1.stride(0) == add2.stride(0)
+    check(lib().oat_layernorm_bwd(
+        ptr(dy_bf16), _i64(dy_bf16.stride(0) if dy_bf16 is not None else 0),
+        ptr(dy_f32), _i64((dy_f32.stride(0) if lddyf is None else lddyf) if dy_f32 is not None else 0),
+        ptr(x), _i64(ldx), ptr(mean), ptr(rstd), ptr(gamma), _i64(rows), _i32(D),
+        ptr(add1), ptr(add2), _i64(ldadd),
+        ptr(dx), _i64((dx.stride(0) if lddx is None else lddx) if dx is not None else 0),
+        ptr(dx_bf16), _i64((dx_bf16.stride(0) if lddxb is None else lddxb) if dx_bf16 is not None else 0),
+        ptr(dgamma), ptr(dbeta), stream_ptr()), "oat_layernorm_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", _i32), ("B", _i32), ("T", _i32), ("H", _i32), ("F", _i32), ("n", _i32),
+        ("qkv", _vp), ("ld_qkv", _i64),
+        ("out", _vp), ("ld_out", _i64),
+        ("lse", _vp),
+        ("key_mask", _vp),
+        ("dout", _vp), ("ld_dout", _i64),
+        ("dqkv", _vp), ("ld_dqkv", _i64),
+        ("scale", _f32),
+        ("cls_acc", _vp),
+    ]
+
+
+MODE_SPACE, MODE_TIME, MODE_PLAIN = 0, 1, 2
+
+
+def _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask):
+    a = AttnArgs()
+    a.mode, a.B, a.T, a.H, a.F, a.n = mode, B, T, H, F, n
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    a.qkv, a.ld_qkv = ptr(qkv), qkv.stride(0)
+    a.out, a.ld_out = ptr(out), out.stride(0)
+    a.lse = ptr(lse)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.int32 and key_mask.numel() == B * T
+    a.key_mask = ptr(key_mask)
+    return a
+
+
+def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None):
+    """qkv bf16 [B*T, 3*H*64] (q pre-scaled) -> out bf16 [B*T, H*64], lse fp32 [B*H*T]."""
+    a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
+    check(lib().oat_attn_fwd(ctypes.byref(a), stream_ptr()), "oat_attn_fwd")
+
+
+def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None):
+    a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
+    assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16
+    a.dout, a.ld_dout = ptr(dout), dout.stride(0)
+    a.dqkv, a.ld_dqkv = ptr(dqkv), dqkv.stride(0)
+    a.scale = scale
+    a.cls_acc = ptr(cls_acc)
+    check(lib().oat_attn_bwd(ctypes.byref(a), stream_ptr()), "oat_attn_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ packing / tokens
+def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
+    """dst (bf16, 2-D) <- src (fp32). Columns [cols, dst.shape[1]) are zero-filled."""
+    rows = dst.shape[0] if rows is None else rows
+    cols = src.shape[-1] if cols is None else cols
+    lds = (src.stride(0) if src.dim() == 2 else cols) if lds is None else lds
+    check(lib().oat_cast_bf16(ptr(src), _i64(lds), ptr(dst), _i64(dst.stride(0)), _i64(rows), _i32(cols),
+                              _i32(dst.shape[1]), _i32(1 if relu else 0), stream_ptr()), "oat_cast_bf16")
+
+
+def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx):
+    check(lib().oat_relu_bwd(ptr(x), _i64(ldx), ptr(dy_bf16), _i64(dy_bf16.stride(0)), ptr(dx), _i64(dx.stride(0)),
+                             _i64(rows), _i32(cols), stream_ptr()), "oat_relu_bwd")
+
+
+def im2col_patches(video, out, P=16):
+    B, Fr, C, H, W = video.shape
+    assert video.is_contiguous() and video.dtype == torch.float32
+    check(lib().oat_im2col_patches(ptr(video), ptr(out), _i64(B * Fr), _i32(C), _i32(H), _i32(W), _i32(P),
+                                   stream_ptr()), "oat_im2col_patches")
+
+
+def assemble_tokens(patch, obj, cls_token, pos_embed, temporal, type_embed, x, B, Fr, N, O, D):
+    check(lib().oat_assemble_tokens(ptr(patch), ptr(obj), ptr(cls_token), ptr(pos_embed), ptr(temporal),
+                                    ptr(type_embed), ptr(x), _i32(B), _i32(Fr), _i32(N), _i32(O), _i32(D),
+                                    stream_ptr()), "oat_assemble_tokens")
+
+
+def assemble_tokens_bwd(dx, dpatch, dobj, dcls, dpos, dtemporal, dtype_embed, B, Fr, N, O, D):
+    check(lib().oat_assemble_tokens_bwd(ptr(dx), ptr(dpatch), ptr(dobj), ptr(dcls), ptr(dpos), ptr(dtemporal),
+                                        ptr(dtype_embed), _i32(B), _i32(Fr), _i32(N), _i32(O), _i32(D),
+                                        stream_ptr()), "oat_assemble_tokens_bwd")
+
+
+def colsum_bf16(x, out):
+    """out[c] += sum_r x[r, c] (x bf16 2-D, out fp32)."""
+    check(lib().oat_colsum_bf16(ptr(x), _i64(x.stride(0)), _i64(x.shape[0]), _i32(x.shape[1]), ptr(out),
+                                stream_ptr()), "oat_colsum_bf16")
+
+
+def text_embed(ids, word, pos, out, L):
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    check(lib().oat_text_embed(ptr(ids), ptr(word), ptr(pos), ptr(out), _i64(ids.numel()), _i32(L),
+                               _i32(word.shape[1]), stream_ptr()), "oat_text_embed")
+
+
+def text_embed_bwd(ids, dsum, dword, dpos, L):
+    check(lib().oat_text_embed_bwd(ptr(ids), ptr(dsum), ptr(dword), ptr(dpos), _i64(ids.numel()), _i32(L),
+                                   _i32(dsum.shape[1]), stream_ptr()), "oat_text_embed_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ loss
+def infonce_workspace_bytes(n, P):
+    f = lib().oat_infonce_workspace_bytes
+    f.restype = _sz
+    return int(f(_i32(n), _i32(P)))
+
+
+def infonce_fwd_bwd(text, video, temperature=0.05, eps=1e-8, want_sims=False, want_grad=True, workspace=None):
+    """text, video: fp32 [n, P] gathered embeddings -> (loss[1], sims or None, dtext or None, dvideo or None)."""
+    n, P = text.shape
+    assert text.dtype == torch.float32 and video.shape == (n, P) and text.is_contiguous() and video.is_contiguous()
+    nbytes = infonce_workspace_bytes(n, P)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=text.device)
+    loss = torch.empty(1, dtype=torch.float32, device=text.device)
+    sims = torch.empty(n, n, dtype=torch.float32, device=text.device) if want_sims else None
+    dt = torch.empty_like(text) if want_grad else None
+    dv = torch.empty_like(video) if want_grad else None
+    check(lib().oat_infonce_fwd_bwd(ptr(text), ptr(video), _i32(n), _i32(P), _f32(temperature), _f32(eps), ptr(sims),
+                                    ptr(loss), ptr(dt), ptr(dv), ptr(workspace), _sz(nbytes), stream_ptr()),
+          "oat_infonce_fwd_bwd")
+    return loss, sims, dt, dv

@@ -149,17 +149,11 @@ def video_tokens(video, p, cfg, objects=None, prefix="video_model."):
     return torch.cat([cls, x.reshape(B, Fr * n, D)], dim=1), n
 
 
-def divided_attention(x, p, pre, mode, Fr, n, cfg):
-    """VarAttention.forward (video_transformer.py:99-135). mode 'space': patch queries of frame f attend to
-    [CLS] + the n tokens of frame f ('b (f n) d -> (b f) n d'); mode 'time': token (f, i) attends to [CLS] + tokens
-    (f', i) for all f' ('b (f n) d -> (b n) f d'). The CLS query attends to every key (:110). q is scaled by
-    head_dim^-0.5 before any product (:105)."""
-    B, T, D = x.shape
-    h = cfg.heads
-    d = D // h
-    qkv = linear(x, p[pre + "qkv.weight"], p[pre + "qkv.bias"], cfg).reshape(B, T, 3, h, d)
-    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))        # (B, h, T, d)
-    q = q * (d ** -0.5)
+def divided_attention_core(q, k, v, mode, Fr, n, cfg):
+    """The attention arithmetic of VarAttention.forward (video_transformer.py:108-131) on already-projected,
+    already-scaled q and k, v of shape (B, h, T, d): CLS query over all keys; patch queries over [CLS] + their group.
+    Returns (B, T, h*d)."""
+    B, h, T, d = q.shape
     cls_out = _softmax_attention(q[:, :, 0:1], k, v, cfg)                  # (B, h, 1, d)
 
     def grp(t):
@@ -174,7 +168,20 @@ def divided_attention(x, p, pre, mode, Fr, n, cfg):
     if mode != "space":
         out = out.transpose(2, 3)
     out = torch.cat([cls_out, out.reshape(B, h, Fr * n, d)], dim=2)       # CLS first (:128)
-    out = out.permute(0, 2, 1, 3).reshape(B, T, D)                         # '(b h) n d -> b n (h d)' (:131)
+    return out.permute(0, 2, 1, 3).reshape(B, T, h * d)                    # '(b h) n d -> b n (h d)' (:131)
+
+
+def divided_attention(x, p, pre, mode, Fr, n, cfg):
+    """VarAttention.forward (video_transformer.py:99-135). mode 'space': patch queries of frame f attend to
+    [CLS] + the n tokens of frame f ('b (f n) d -> (b f) n d'); mode 'time': token (f, i) attends to [CLS] + tokens
+    (f', i) for all f' ('b (f n) d -> (b n) f d'). The CLS query attends to every key (:110). q is scaled by
+    head_dim^-0.5 before any product (:105)."""
+    B, T, D = x.shape
+    h = cfg.heads
+    d = D // h
+    qkv = linear(x, p[pre + "qkv.weight"], p[pre + "qkv.bias"], cfg).reshape(B, T, 3, h, d)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))        # (B, h, T, d)
+    out = divided_attention_core(q * (d ** -0.5), k, v, mode, Fr, n, cfg)
     return linear(out, p[pre + "proj.weight"], p[pre + "proj.bias"], cfg)
 
 
