@@ -134,6 +134,15 @@ int oat_text_embed_bwd(const int64_t* ids, const float* dsum, float* dword, floa
  * text, video: fp32 [n, P] GATHERED embeddings (rows = the global batch). Writes sims [n, n] (optional), the scalar
  * loss, and dL/dtext, dL/dvideo [n, P] (optional). The caller slices its local rows: the all-gather backward is a
  * slice without reduction (trainer_dist.py:40-45). Replaces model/model.py:164-172 + model/loss.py:13-25. */
+size_t oat_sim_workspace_bytes(int32_t n, int32_t m, int32_t P);
+/* sims[n, m] (pitch m) = unit(text[n,P]) . unit(video[m,P])^T; the workspace keeps what the backward needs. */
+int oat_sim_matrix_fwd(const float* text, const float* video, int32_t n, int32_t m, int32_t P, float eps,
+                       float* sims, void* workspace, size_t workspace_bytes, oat_stream_t stream);
+int oat_sim_matrix_bwd(const float* dsims, int32_t n, int32_t m, int32_t P, float eps, float* dtext, float* dvideo,
+                       void* workspace, size_t workspace_bytes, oat_stream_t stream);
+/* loss[0] = NormSoftmaxLoss(sims[n,n]); dsims (optional, same pitch) = dL/dsims; scratch: fp32 [2n]. */
+int oat_norm_softmax_loss(const float* sims, int32_t n, int64_t ld, float temperature, float* loss, float* dsims,
+                          float* scratch, oat_stream_t stream);
 size_t oat_infonce_workspace_bytes(int32_t n, int32_t P);
 int oat_infonce_fwd_bwd(const float* text, const float* video, int32_t n, int32_t P, float temperature, float eps,
                         float* sims_out, float* loss, float* dtext, float* dvideo, void* workspace,

@@ -347,12 +347,13 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.num_n_blocks = (a->N + BLOCK_N - 1) / BLOCK_N;
   p.k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   const int sms = num_sms();
-  p.split_k = pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, sms, a->split_k);
+  const bool can_split = a->accumulate && a->out_f32 != nullptr && a->out_bf16 == nullptr && a->act == 0;
+  p.split_k = (a->split_k == 0 && !can_split) ? 1 : pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, sms, a->split_k);
   {  // no empty splits
     const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
     p.split_k = (p.k_blocks + per - 1) / per;
   }
-  if (p.split_k > 1 && !(a->accumulate && a->out_f32 != nullptr && a->out_bf16 == nullptr && a->act == 0))
+  if (p.split_k > 1 && !can_split)
     return set_error(OAT_ERR_ARG, "split-K needs accumulate=1 into an fp32 output and no activation");
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32;

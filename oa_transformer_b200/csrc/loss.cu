@@ -103,7 +103,7 @@ __global__ void loss_grad_logits_kernel(const float* __restrict__ sims, int n, i
 // side 0: dan[i,:] = sum_j dsims[i,j] bn[j,:] ; side 1: dbn[j,:] = sum_i dsims[i,j] an[i,:]
 // then through x_n = x * inv (inv = 1/max(|x|, eps)): dx = inv * (dxn - x_n (x_n . dxn)) if the clamp is inactive,
 // else dx = inv * dxn.
-__global__ void loss_grad_embed_kernel(const float* __restrict__ dsims, int n, int ld, int P, const float* __restrict__ other_n,
+__global__ void loss_grad_embed_kernel(const float* __restrict__ dsims, int n_other, int ld, int P, const float* __restrict__ other_n,
                                        const float* __restrict__ self_n, const float* __restrict__ inv_norm, float eps,
                                        int side, float* __restrict__ dself) {
   __shared__ float sh[32];
@@ -114,7 +114,7 @@ __global__ void loss_grad_embed_kernel(const float* __restrict__ dsims, int n, i
     const int c = c0 + threadIdx.x;
     float acc = 0.f;
     if (c < P) {
-      for (int k = 0; k < n; ++k) {
+      for (int k = 0; k < n_other; ++k) {
         const float w = side == 0 ? dsims[static_cast<long long>(r) * ld + k] : dsims[static_cast<long long>(k) * ld + r];
         acc += w * other_n[static_cast<long long>(k) * P + c];
       }
@@ -130,72 +130,117 @@ __global__ void loss_grad_embed_kernel(const float* __restrict__ dsims, int n, i
 
 using namespace oat;
 
-extern "C" size_t oat_infonce_workspace_bytes(int32_t n, int32_t P) {
-  // an, bn [n,P] fp32 | inv_a, inv_b, row_lse, col_lse [n] | sims, dsims [n,n] fp32 | packA, packB [n,3P] bf16
-  const size_t np = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);   // sims pitch / padded row count
-  size_t f = static_cast<size_t>(2) * np * P + 4 * np + 2 * np * np;
-  size_t bytes = f * 4 + static_cast<size_t>(2) * np * 3 * P * 2;
+namespace {
+struct SimWs {
+  float *an, *bn, *inv_a, *inv_b, *sims_pad;
+  __nv_bfloat16 *pa, *pb;
+  size_t mp;
+};
+size_t pad4(size_t v) { return (v + 3) & ~static_cast<size_t>(3); }
+size_t sim_ws_bytes(size_t n, size_t m, size_t P) {
+  const size_t mp = pad4(m);
+  size_t f = n * P + mp * P + pad4(n) + mp + n * mp;
+  size_t bytes = f * 4 + (pad4(n) + mp) * 3 * P * 2;
   return (bytes + 255) & ~static_cast<size_t>(255);
 }
+SimWs carve(void* ws, size_t n, size_t m, size_t P) {
+  SimWs w;
+  w.mp = pad4(m);
+  w.an = reinterpret_cast<float*>(ws);
+  w.bn = w.an + n * P;
+  w.inv_a = w.bn + w.mp * P;
+  w.inv_b = w.inv_a + pad4(n);
+  w.sims_pad = w.inv_b + w.mp;
+  w.pa = reinterpret_cast<__nv_bfloat16*>(w.sims_pad + n * w.mp);
+  w.pb = w.pa + pad4(n) * 3 * P;
+  return w;
+}
+}  // namespace
 
+extern "C" size_t oat_sim_workspace_bytes(int32_t n, int32_t m, int32_t P) { return sim_ws_bytes(n, m, P); }
+
+// sims[n, m] = unit(text) . unit(video)^T ; the workspace keeps the unit rows and 1/norms for the backward.
+extern "C" int oat_sim_matrix_fwd(const float* text, const float* video, int32_t n, int32_t m, int32_t P, float eps,
+                                  float* sims, void* workspace, size_t workspace_bytes, oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && m > 0 && P > 0 && P % 8 == 0 && P <= 1024, "oat_sim_matrix_fwd: n=%d m=%d P=%d (P multiple of 8, <= 1024)", n, m, P);
+  OAT_REQUIRE(workspace != nullptr && workspace_bytes >= sim_ws_bytes(n, m, P), "oat_sim_matrix_fwd: workspace too small");
+  OAT_REQUIRE(sims != nullptr, "oat_sim_matrix_fwd: null output");
+  cudaStream_t s = as_stream(stream);
+  SimWs w = carve(workspace, n, m, P);
+  if (w.mp != static_cast<size_t>(m)) {  // zero the padding rows of the packed video operand (padded sims columns)
+    cudaError_t e0 = cudaMemsetAsync(w.pb + static_cast<size_t>(m) * 3 * P, 0, (w.mp - m) * 3 * P * 2, s);
+    if (e0 != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e0));
+  }
+  const int wpb = 8;
+  loss_normalize_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, s>>>(text, w.an, w.inv_a, w.pa, n, P, eps, 0);
+  loss_normalize_kernel<<<(m + wpb - 1) / wpb, wpb * 32, 0, s>>>(video, w.bn, w.inv_b, w.pb, m, P, eps, 1);
+  int rc = check_launch("loss_normalize_kernel");
+  if (rc != OAT_OK) return rc;
+  oat_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = w.pa; g.lda = 3 * P; g.a_major = 0;
+  g.B = w.pb; g.ldb = 3 * P; g.b_major = 0;
+  g.M = n; g.N = static_cast<int32_t>(w.mp); g.K = 3 * P;
+  g.alpha = 1.0f; g.scale = 1.0f;
+  g.out_f32 = w.sims_pad; g.ld_f32 = static_cast<int64_t>(w.mp);
+  rc = oat_gemm_bf16(&g, stream);
+  if (rc != OAT_OK) return rc;
+  cudaError_t e = cudaMemcpy2DAsync(sims, sizeof(float) * m, w.sims_pad, sizeof(float) * w.mp, sizeof(float) * m, n,
+                                    cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+  return OAT_OK;
+}
+
+// dtext[n,P], dvideo[m,P] from dsims[n,m] (pitch m) through the product and the normalisation.
+extern "C" int oat_sim_matrix_bwd(const float* dsims, int32_t n, int32_t m, int32_t P, float eps, float* dtext,
+                                  float* dvideo, void* workspace, size_t workspace_bytes, oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && m > 0 && P > 0 && P <= 1024, "oat_sim_matrix_bwd: bad sizes");
+  OAT_REQUIRE(workspace != nullptr && workspace_bytes >= sim_ws_bytes(n, m, P), "oat_sim_matrix_bwd: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  SimWs w = carve(workspace, n, m, P);
+  const int threads = ((P + 31) / 32) * 32;
+  if (dtext != nullptr) loss_grad_embed_kernel<<<n, threads, 0, s>>>(dsims, m, m, P, w.bn, w.an, w.inv_a, eps, 0, dtext);
+  if (dvideo != nullptr) loss_grad_embed_kernel<<<m, threads, 0, s>>>(dsims, n, m, P, w.an, w.bn, w.inv_b, eps, 1, dvideo);
+  return check_launch("loss_grad_embed_kernel");
+}
+
+// loss = NormSoftmaxLoss(sims) and dL/dsims (same pitch as sims). scratch: fp32 [2n].
+extern "C" int oat_norm_softmax_loss(const float* sims, int32_t n, int64_t ld, float temperature, float* loss,
+                                     float* dsims, float* scratch, oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && ld >= n && temperature > 0.f, "oat_norm_softmax_loss: bad arguments");
+  OAT_REQUIRE(loss != nullptr && scratch != nullptr, "oat_norm_softmax_loss: null loss/scratch");
+  cudaStream_t s = as_stream(stream);
+  const float inv_t = 1.0f / temperature;
+  loss_lse_kernel<<<2 * n, 256, 0, s>>>(sims, n, static_cast<int>(ld), inv_t, scratch, scratch + n);
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), s);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  loss_grad_logits_kernel<<<n, 256, 0, s>>>(sims, n, static_cast<int>(ld), inv_t, scratch, scratch + n, dsims, loss);
+  return check_launch("loss_grad_logits_kernel");
+}
+
+extern "C" size_t oat_infonce_workspace_bytes(int32_t n, int32_t P) {
+  // sim workspace | sims [n,n] | dsims [n,n] | lse scratch [2n]
+  return sim_ws_bytes(n, n, P) + ((static_cast<size_t>(2) * n * n + 2 * static_cast<size_t>(n)) * 4 + 255 & ~static_cast<size_t>(255));
+}
+
+// Fused convenience: sims -> loss -> gradients of the gathered embeddings in one call (same kernels as above).
 extern "C" int oat_infonce_fwd_bwd(const float* text, const float* video, int32_t n, int32_t P, float temperature,
                                    float eps, float* sims_out, float* loss, float* dtext, float* dvideo,
                                    void* workspace, size_t workspace_bytes, oat_stream_t stream) {
-  OAT_REQUIRE(n > 0 && P > 0 && P % 8 == 0 && P <= 1024, "oat_infonce_fwd_bwd: n=%d P=%d (P multiple of 8, <= 1024)", n, P);
   OAT_REQUIRE(workspace != nullptr && workspace_bytes >= oat_infonce_workspace_bytes(n, P),
               "oat_infonce_fwd_bwd: workspace too small");
-  OAT_REQUIRE(loss != nullptr, "oat_infonce_fwd_bwd: null loss");
-  cudaStream_t s = as_stream(stream);
-  const size_t np = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);
-  const int ld = static_cast<int>(np);
-  float* an = reinterpret_cast<float*>(workspace);
-  float* bn = an + np * P;
-  float* inv_a = bn + np * P;
-  float* inv_b = inv_a + np;
-  float* row_lse = inv_b + np;
-  float* col_lse = row_lse + np;
-  float* sims = col_lse + np;
-  float* dsims = sims + np * np;
-  __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(dsims + np * np);
-  __nv_bfloat16* pb = pa + np * 3 * P;
-  if (np != static_cast<size_t>(n)) {  // zero the padding rows of the packed video operand (padded sims columns)
-    cudaError_t e0 = cudaMemsetAsync(pb + static_cast<size_t>(n) * 3 * P, 0, (np - n) * 3 * P * 2, s);
-    if (e0 != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e0));
-  }
-
-  const int wpb = 8;
-  loss_normalize_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, s>>>(text, an, inv_a, pa, n, P, eps, 0);
-  loss_normalize_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, s>>>(video, bn, inv_b, pb, n, P, eps, 1);
-  int rc = check_launch("loss_normalize_kernel");
-  if (rc != OAT_OK) return rc;
-
-  oat_gemm_args g;
-  memset(&g, 0, sizeof(g));
-  g.A = pa; g.lda = 3 * P; g.a_major = 0;
-  g.B = pb; g.ldb = 3 * P; g.b_major = 0;
-  g.M = n; g.N = ld; g.K = 3 * P;
-  g.alpha = 1.0f; g.scale = 1.0f;
-  g.out_f32 = sims; g.ld_f32 = ld;
-  rc = oat_gemm_bf16(&g, stream);
+  const size_t simb = sim_ws_bytes(n, n, P);
+  float* sims = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + simb);
+  float* dsims = sims + static_cast<size_t>(n) * n;
+  float* scratch = dsims + static_cast<size_t>(n) * n;
+  int rc = oat_sim_matrix_fwd(text, video, n, n, P, eps, sims, workspace, simb, stream);
   if (rc != OAT_OK) return rc;
   if (sims_out != nullptr) {
-    cudaError_t e = cudaMemcpy2DAsync(sims_out, sizeof(float) * n, sims, sizeof(float) * ld, sizeof(float) * n, n,
-                                      cudaMemcpyDeviceToDevice, s);
+    cudaError_t e = cudaMemcpyAsync(sims_out, sims, sizeof(float) * n * n, cudaMemcpyDeviceToDevice, as_stream(stream));
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
   }
-  const float inv_t = 1.0f / temperature;
-  loss_lse_kernel<<<2 * n, 256, 0, s>>>(sims, n, ld, inv_t, row_lse, col_lse);
-  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), s);
-  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   const bool want_grad = dtext != nullptr || dvideo != nullptr;
-  loss_grad_logits_kernel<<<n, 256, 0, s>>>(sims, n, ld, inv_t, row_lse, col_lse, want_grad ? dsims : nullptr, loss);
-  rc = check_launch("loss_grad_logits_kernel");
-  if (rc != OAT_OK) return rc;
-  if (want_grad) {
-    const int threads = ((P + 31) / 32) * 32;
-    if (dtext != nullptr) loss_grad_embed_kernel<<<n, threads, 0, s>>>(dsims, n, ld, P, bn, an, inv_a, eps, 0, dtext);
-    if (dvideo != nullptr) loss_grad_embed_kernel<<<n, threads, 0, s>>>(dsims, n, ld, P, an, bn, inv_b, eps, 1, dvideo);
-    rc = check_launch("loss_grad_embed_kernel");
-  }
-  return rc;
+  rc = oat_norm_softmax_loss(sims, n, n, temperature, loss, want_grad ? dsims : nullptr, scratch, stream);
+  if (rc != OAT_OK || !want_grad) return rc;
+  return oat_sim_matrix_bwd(dsims, n, n, P, eps, dtext, dvideo, workspace, simb, stream);
 }

@@ -1,0 +1,449 @@
+"""Forward/backward schedules of the two towers over liboat kernels.
+
+PyTorch supplies device buffers and the stream; every arithmetic step is a C-ABI launch (ops.py). The schedules
+follow the reference modules line by line:
+  video: SpaceTimeTransformer.forward_features (OATrans/model/video_transformer.py:303-351) with SpaceTimeBlock
+         (:161-176, frozen-in-time residual wiring) and VarAttention (:99-135), then vid_proj (oa_model.py:129-133)
+  text : HF DistilBertModel as called by FrozenInTime.compute_text (OATrans/model/oa_model.py:106-123)
+
+Arithmetic contract (mirrored by oracle/oracle.py in bf16 mode): GEMM / attention operands are bf16, accumulation
+fp32; residual stream, LayerNorm, softmax, logits, loss and every parameter gradient are fp32; activation gradients
+that feed a GEMM are bf16.
+"""
+import torch
+
+from . import ops
+
+BF = torch.bfloat16
+F32 = torch.float32
+HEAD_DIM = 64
+Q_SCALE = HEAD_DIM ** -0.5
+OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py:593-650)
+OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
+
+
+class _Buffers:
+    """Shape-keyed cache of device buffers so that a training loop re-uses its activation storage every step."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+            if zero:
+                t.zero_()
+        elif zero:
+            t.zero_()
+        return t
+
+
+def _w16(bufs, name, w, rows=None, cols=None, pitch=None):
+    """bf16 operand copy of an fp32 weight (re-packed every step: the optimizer owns the fp32 master)."""
+    w2 = w.detach().reshape(w.shape[0], -1)
+    rows = w2.shape[0] if rows is None else rows
+    cols = w2.shape[1] if cols is None else cols
+    dst = bufs.get(name, (rows, pitch or cols), BF)
+    ops.cast_bf16(w2, dst, rows=rows, cols=cols)
+    return dst
+
+
+class GradBook:
+    """Flat fp32 gradient storage with one view per parameter (zeroed once per backward)."""
+
+    def __init__(self, named_params, device):
+        self.names = [n for n, _ in named_params]
+        sizes = [p.numel() for _, p in named_params]
+        self.flat = torch.zeros(sum(sizes), dtype=F32, device=device)
+        self.views = {}
+        off = 0
+        for (n, p), s in zip(named_params, sizes):
+            self.views[n] = self.flat[off:off + s].view(p.shape)
+            off += s
+
+    def zero(self):
+        self.flat.zero_()
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+
+# ==================================================================================================== video tower
+class VideoEngine:
+    """Space-time ViT over [CLS] + F x (N patch tokens + O object tokens), then the 768 -> P projection."""
+
+    def __init__(self, device, heads=12, eps=1e-6, patch=16):
+        self.device = device
+        self.H = heads
+        self.eps = eps
+        self.patch = patch
+        self.bufs = _Buffers(device)
+        self.saved = None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
+                save=True):
+        """p: dict name -> fp32 parameter tensor. video fp32 (B,F,3,H,W); objects fp32 (B,F,O,2054) or None.
+        Returns projected CLS embeddings fp32 (B, P)."""
+        bufs = self.bufs
+        B, Fr, C, Hh, Ww = video.shape
+        ps = self.patch
+        N = (Hh // ps) * (Ww // ps)
+        D = p[prefix + "cls_token"].shape[-1]
+        H = self.H
+        assert D == H * HEAD_DIM, "embed dim %d must be heads(%d) x 64" % (D, H)
+        assert Fr <= p[prefix + "temporal_embed"].shape[1]        # video_transformer.py:73
+        assert N + 1 == p[prefix + "pos_embed"].shape[1], "input resolution does not match pos_embed"
+        O = 0 if objects is None else objects.shape[2]
+        n = N + O
+        T = 1 + Fr * n
+        M = B * T
+        depth = 0
+        while (prefix + "blocks.%d.norm1.weight" % depth) in p:
+            depth += 1
+        video = video.contiguous()
+
+        # --- patch / object embedding + token assembly (video_transformer.py:71-76, 303-325)
+        K0 = C * ps * ps
+        cols = bufs.get("cols", (B * Fr * N, K0), BF)
+        ops.im2col_patches(video, cols, ps)
+        wp = _w16(bufs, "w.patch", p[prefix + "patch_embed.proj.weight"])
+        patch = bufs.get("patch", (B * Fr * N, D), F32)
+        ops.gemm(cols, wp, bias=p[prefix + "patch_embed.proj.bias"], out_f32=patch)
+        objemb = obj16 = None
+        if O > 0:
+            assert objects.shape[-1] == OBJ_DIM
+            obj16 = bufs.get("obj16", (B * Fr * O, OBJ_PITCH), BF)
+            ops.cast_bf16(objects.contiguous().reshape(-1, OBJ_DIM), obj16)
+            wo = _w16(bufs, "w.object", p[prefix + "object_embed.weight"], pitch=OBJ_PITCH)
+            objemb = bufs.get("objemb", (B * Fr * O, D), F32)
+            ops.gemm(obj16, wo, bias=p[prefix + "object_embed.bias"], out_f32=objemb)
+        type_embed = p.get(prefix + "token_type_embeddings.weight")
+        xs = [bufs.get("x.%d" % i, (M, D), F32) for i in range(depth + 1)]
+        ops.assemble_tokens(patch, objemb, p[prefix + "cls_token"], p[prefix + "pos_embed"],
+                            p[prefix + "temporal_embed"], type_embed, xs[0], B, Fr, N, O, D)
+
+        layers = []
+        for i in range(depth):
+            b = "%sblocks.%d." % (prefix, i)
+            L = {}
+            x = xs[i]
+
+            def ln(tag, src, wname):
+                h = bufs.get("h%s.%d" % (tag, i), (M, D), BF)
+                mean = bufs.get("mean%s.%d" % (tag, i), (M,), F32)
+                rstd = bufs.get("rstd%s.%d" % (tag, i), (M,), F32)
+                ops.layernorm_fwd(src, p[b + wname + ".weight"], p[b + wname + ".bias"], self.eps, y_bf16=h,
+                                  mean=mean, rstd=rstd)
+                return h, mean, rstd
+
+            def attention(tag, mode, h, aname, resid, out):
+                wqkv = _w16(bufs, "w.%s.qkv.%d" % (tag, i), p[b + aname + ".qkv.weight"])
+                qkv = bufs.get("qkv%s.%d" % (tag, i), (M, 3 * D), BF)
+                ops.gemm(h, wqkv, bias=p[b + aname + ".qkv.bias"], scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
+                a = bufs.get("a%s.%d" % (tag, i), (M, D), BF)
+                lse = bufs.get("lse%s.%d" % (tag, i), (B * H * T,), F32)
+                ops.attn_fwd(mode, B, T, H, Fr, n, qkv, a, lse)
+                wproj = _w16(bufs, "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"])
+                ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
+                return wqkv, wproj, qkv, a, lse
+
+            # time attention on norm3(x); residual from x                    (video_transformer.py:164-165)
+            L["h3"], L["m3"], L["r3"] = ln("3", x, "norm3")
+            tr = bufs.get("tr.%d" % i, (M, D), F32)
+            L["wqkv_t"], L["wproj_t"], L["qkv_t"], L["a_t"], L["lse_t"] = attention("t", ops.MODE_TIME, L["h3"],
+                                                                                    "timeattn", x, tr)
+            # space attention on norm1(time_residual); residual from x again  (:167-170)
+            L["h1"], L["m1"], L["r1"] = ln("1", tr, "norm1")
+            sr = bufs.get("sr.%d" % i, (M, D), F32)
+            L["wqkv_s"], L["wproj_s"], L["qkv_s"], L["a_s"], L["lse_s"] = attention("s", ops.MODE_SPACE, L["h1"],
+                                                                                    "attn", x, sr)
+            # MLP on norm2(space_residual)                                   (:174, Mlp :45-51)
+            L["h2"], L["m2"], L["r2"] = ln("2", sr, "norm2")
+            L["w1"] = _w16(bufs, "w.fc1.%d" % i, p[b + "mlp.fc1.weight"])
+            L["w2"] = _w16(bufs, "w.fc2.%d" % i, p[b + "mlp.fc2.weight"])
+            u = bufs.get("u.%d" % i, (M, 4 * D), BF)
+            g = bufs.get("g.%d" % i, (M, 4 * D), BF)
+            ops.gemm(L["h2"], L["w1"], bias=p[b + "mlp.fc1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
+            ops.gemm(g, L["w2"], bias=p[b + "mlp.fc2.bias"], residual=sr, out_f32=xs[i + 1])
+            L["tr"], L["sr"], L["u"], L["g"] = tr, sr, u, g
+            layers.append(L)
+
+        # final LayerNorm: only the CLS row is consumed (:346-351), then vid_proj (oa_model.py:131)
+        cls32 = bufs.get("cls32", (B, D), F32)
+        cls16 = bufs.get("cls16", (B, D), BF)
+        mf = bufs.get("meanf", (B,), F32)
+        rf = bufs.get("rstdf", (B,), F32)
+        ops.layernorm_fwd(xs[depth], p[prefix + "norm.weight"], p[prefix + "norm.bias"], self.eps, rows=B, ldx=T * D,
+                          y_bf16=cls16, y_f32=cls32, mean=mf, rstd=rf)
+        out = cls32.clone() if proj is None else None
+        wv = None
+        if proj is not None:
+            wv = _w16(bufs, "w.vid_proj", p[proj[0]])
+            P = p[proj[0]].shape[0]
+            out = torch.empty((B, P), dtype=F32, device=self.device)
+            ops.gemm(cls16, wv, bias=p[proj[1]], out_f32=out)
+        if save:
+            self.saved = dict(B=B, Fr=Fr, N=N, O=O, n=n, T=T, M=M, D=D, depth=depth, xs=xs, layers=layers, cols=cols,
+                              obj16=obj16, cls16=cls16, mf=mf, rf=rf, wv=wv, proj=proj, prefix=prefix,
+                              has_type=type_embed is not None)
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, p, grads, dout):
+        """dout: fp32 (B, P) gradient of the projected embeddings. Fills `grads` (GradBook-like: name -> fp32 view,
+        pre-zeroed) with every parameter gradient."""
+        S = self.saved
+        assert S is not None, "backward without a saved forward"
+        bufs = self.bufs
+        B, Fr, N, O, n, T, M, D, depth = (S[k] for k in ("B", "Fr", "N", "O", "n", "T", "M", "D", "depth"))
+        H = self.H
+        prefix = S["prefix"]
+        xs, layers = S["xs"], S["layers"]
+
+        def wgrad(dy16, act16, name):
+            ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
+                     accumulate=True)
+            ops.colsum_bf16(dy16, grads[name + ".bias"])
+
+        dy = bufs.get("dy.a", (M, D), F32, zero=True)         # d(block output), non-zero in the CLS rows only
+        dy16 = bufs.get("dy16.a", (M, D), BF, zero=True)
+        dcls16 = bufs.get("dcls16", (B, D), BF)
+        if S["proj"] is not None:
+            wname, bname = S["proj"]
+            P = dout.shape[1]
+            d16 = bufs.get("dout16", (B, P), BF)
+            ops.cast_bf16(dout.contiguous(), d16)
+            ops.gemm(d16, S["wv"], b_major=1, out_bf16=dcls16)
+            ops.gemm(d16, S["cls16"], a_major=1, b_major=1, out_f32=grads[wname], accumulate=True)
+            ops.colsum_bf16(d16, grads[bname])
+        else:
+            ops.cast_bf16(dout.contiguous(), dcls16)
+        ops.layernorm_bwd(xs[depth], S["mf"], S["rf"], p[prefix + "norm.weight"], dy_bf16=dcls16, rows=B, ldx=T * D,
+                          dx=dy, dx_bf16=dy16, lddx=T * D, lddxb=T * D, dgamma=grads[prefix + "norm.weight"],
+                          dbeta=grads[prefix + "norm.bias"])
+
+        du = bufs.get("du", (M, 4 * D), BF)
+        dh = bufs.get("dh", (M, D), BF)
+        da = bufs.get("da", (M, D), BF)
+        dqkv = bufs.get("dqkv", (M, 3 * D), BF)
+        dsr = bufs.get("dsr", (M, D), F32)
+        dsr16 = bufs.get("dsr16", (M, D), BF)
+        dtr = bufs.get("dtr", (M, D), F32)
+        dtr16 = bufs.get("dtr16", (M, D), BF)
+        acc = bufs.get("cls_acc", (B * H * 3 * HEAD_DIM,), F32)
+        dyb = bufs.get("dy.b", (M, D), F32)
+        dy16b = bufs.get("dy16.b", (M, D), BF)
+
+        for i in reversed(range(depth)):
+            b = "%sblocks.%d." % (prefix, i)
+            L = layers[i]
+            # ---- x_out = sr + fc2(gelu(fc1(norm2(sr))))
+            ops.gemm(dy16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
+            wgrad(dy16, L["g"], b + "mlp.fc2")
+            ops.gemm(du, L["w1"], b_major=1, out_bf16=dh)
+            wgrad(du, L["h2"], b + "mlp.fc1")
+            ops.layernorm_bwd(L["sr"], L["m2"], L["r2"], p[b + "norm2.weight"], dy_bf16=dh, add1=dy, dx=dsr,
+                              dx_bf16=dsr16, dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"])
+            # ---- sr = x + proj_s(space_attn(qkv_s(norm1(tr))))
+            ops.gemm(dsr16, L["wproj_s"], b_major=1, out_bf16=da)
+            wgrad(dsr16, L["a_s"], b + "attn.proj")
+            ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv, Q_SCALE, acc)
+            ops.gemm(dqkv, L["wqkv_s"], b_major=1, out_bf16=dh)
+            wgrad(dqkv, L["h1"], b + "attn.qkv")
+            ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16,
+                              dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"])
+            # ---- tr = x + proj_t(time_attn(qkv_t(norm3(x))))
+            ops.gemm(dtr16, L["wproj_t"], b_major=1, out_bf16=da)
+            wgrad(dtr16, L["a_t"], b + "timeattn.proj")
+            ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv, Q_SCALE, acc)
+            ops.gemm(dqkv, L["wqkv_t"], b_major=1, out_bf16=dh)
+            wgrad(dqkv, L["h3"], b + "timeattn.qkv")
+            # ---- dx = dsr (space skip) + dtr (time skip) + norm3'(dh)
+            ops.layernorm_bwd(xs[i], L["m3"], L["r3"], p[b + "norm3.weight"], dy_bf16=dh, add1=dsr, add2=dtr, dx=dyb,
+                              dx_bf16=dy16b, dgamma=grads[b + "norm3.weight"], dbeta=grads[b + "norm3.bias"])
+            dy, dyb = dyb, dy
+            dy16, dy16b = dy16b, dy16
+
+        # ---- token assembly / embeddings
+        dpatch = bufs.get("dpatch", (B * Fr * N, D), BF)
+        dobj = bufs.get("dobj", (B * Fr * O, D), BF) if O > 0 else None
+        ops.assemble_tokens_bwd(dy, dpatch, dobj, grads[prefix + "cls_token"], grads[prefix + "pos_embed"],
+                                grads[prefix + "temporal_embed"],
+                                grads[prefix + "token_type_embeddings.weight"] if S["has_type"] else None,
+                                B, Fr, N, O, D)
+        wgrad(dpatch, S["cols"], prefix + "patch_embed.proj")
+        if O > 0:
+            dwo = bufs.get("dw.object", (D, OBJ_PITCH), F32, zero=True)
+            ops.gemm(dobj, S["obj16"], a_major=1, b_major=1, out_f32=dwo, accumulate=True)
+            grads[prefix + "object_embed.weight"].copy_(dwo[:, :OBJ_DIM])
+            ops.colsum_bf16(dobj, grads[prefix + "object_embed.bias"])
+
+
+# ==================================================================================================== text tower
+class TextEngine:
+    """DistilBERT (post-LN, 6 layers) -> CLS -> ReLU -> Linear(768, P)."""
+
+    def __init__(self, device, heads=12, eps=1e-12):
+        self.device = device
+        self.H = heads
+        self.eps = eps
+        self.bufs = _Buffers(device)
+        self.saved = None
+
+    def forward(self, p, input_ids, attention_mask=None, proj=("txt_proj.1.weight", "txt_proj.1.bias"),
+                prefix="text_model.", save=True):
+        bufs = self.bufs
+        B, Lq = input_ids.shape
+        H = self.H
+        word = p[prefix + "embeddings.word_embeddings.weight"]
+        pos = p[prefix + "embeddings.position_embeddings.weight"]
+        D = word.shape[1]
+        assert D == H * HEAD_DIM
+        assert Lq <= pos.shape[0]
+        M = B * Lq
+        layers_n = 0
+        while (prefix + "transformer.layer.%d.sa_layer_norm.weight" % layers_n) in p:
+            layers_n += 1
+        ids = input_ids.contiguous().to(torch.int64)
+        key_mask = None
+        if attention_mask is not None:
+            key_mask = attention_mask.to(torch.int32).contiguous().view(-1)
+
+        emb = bufs.get("emb", (M, D), F32)
+        ops.text_embed(ids, word, pos, emb, Lq)
+
+        def ln(tag, src, wname):
+            y16 = bufs.get("y16." + tag, (M, D), BF)
+            y32 = bufs.get("y32." + tag, (M, D), F32)
+            mean = bufs.get("mean." + tag, (M,), F32)
+            rstd = bufs.get("rstd." + tag, (M,), F32)
+            ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_bf16=y16, y_f32=y32,
+                              mean=mean, rstd=rstd)
+            return y16, y32, mean, rstd
+
+        x16, x32, m0, r0 = ln("emb", emb, prefix + "embeddings.LayerNorm")
+        layers = []
+        for i in range(layers_n):
+            b = "%stransformer.layer.%d." % (prefix, i)
+            L = {"x16": x16, "x32": x32}
+            wqkv = bufs.get("w.qkv.%d" % i, (3 * D, D), BF)
+            bqkv = bufs.get("b.qkv.%d" % i, (3 * D,), F32)
+            for j, nm in enumerate(("q_lin", "k_lin", "v_lin")):
+                ops.cast_bf16(p[b + "attention.%s.weight" % nm].detach(), wqkv[j * D:(j + 1) * D])
+                bqkv[j * D:(j + 1) * D].copy_(p[b + "attention.%s.bias" % nm].detach())
+            qkv = bufs.get("qkv.%d" % i, (M, 3 * D), BF)
+            ops.gemm(x16, wqkv, bias=bqkv, scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
+            ctx = bufs.get("ctx.%d" % i, (M, D), BF)
+            lse = bufs.get("lse.%d" % i, (B * H * Lq,), F32)
+            ops.attn_fwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, qkv, ctx, lse, key_mask)
+            wo = _w16(bufs, "w.o.%d" % i, p[b + "attention.out_lin.weight"])
+            sa_sum = bufs.get("sa_sum.%d" % i, (M, D), F32)
+            ops.gemm(ctx, wo, bias=p[b + "attention.out_lin.bias"], residual=x32, out_f32=sa_sum)
+            y16, y32, m1, r1 = ln("sa.%d" % i, sa_sum, b + "sa_layer_norm")
+            w1 = _w16(bufs, "w.l1.%d" % i, p[b + "ffn.lin1.weight"])
+            w2 = _w16(bufs, "w.l2.%d" % i, p[b + "ffn.lin2.weight"])
+            Hd = w1.shape[0]
+            u = bufs.get("u.%d" % i, (M, Hd), BF)
+            g = bufs.get("g.%d" % i, (M, Hd), BF)
+            ops.gemm(y16, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
+            ffn_sum = bufs.get("ffn_sum.%d" % i, (M, D), F32)
+            ops.gemm(g, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
+            x16, x32, m2, r2 = ln("out.%d" % i, ffn_sum, b + "output_layer_norm")
+            L.update(wqkv=wqkv, qkv=qkv, ctx=ctx, lse=lse, wo=wo, sa_sum=sa_sum, y16=y16, m1=m1, r1=r1, w1=w1, w2=w2,
+                     u=u, g=g, ffn_sum=ffn_sum, m2=m2, r2=r2)
+            layers.append(L)
+
+        # last_hidden_state[:, 0] -> ReLU -> Linear (oa_model.py:113-121, 68-69)
+        out = x32.view(B, Lq, D)[:, 0].clone() if proj is None else None
+        r16 = wt = None
+        if proj is not None:
+            r16 = bufs.get("relu16", (B, D), BF)
+            ops.cast_bf16(x32, r16, rows=B, cols=D, lds=Lq * D, relu=True)
+            wt = _w16(bufs, "w.txt_proj", p[proj[0]])
+            out = torch.empty((B, p[proj[0]].shape[0]), dtype=F32, device=self.device)
+            ops.gemm(r16, wt, bias=p[proj[1]], out_f32=out)
+        if save:
+            self.saved = dict(B=B, Lq=Lq, M=M, D=D, ids=ids, key_mask=key_mask, emb=emb, m0=m0, r0=r0, layers=layers,
+                              last32=x32, r16=r16, wt=wt, proj=proj, prefix=prefix)
+        return out
+
+    def backward(self, p, grads, dout):
+        S = self.saved
+        assert S is not None, "backward without a saved forward"
+        bufs = self.bufs
+        B, Lq, M, D = S["B"], S["Lq"], S["M"], S["D"]
+        H = self.H
+        prefix = S["prefix"]
+        layers = S["layers"]
+
+        def wgrad_into(dy16, act16, wview, bview):
+            ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=wview, accumulate=True)
+            ops.colsum_bf16(dy16, bview)
+
+        dX = bufs.get("dX", (M, D), F32, zero=True)      # fp32 gradient w.r.t. the layer output (CLS rows only at first)
+        if S["proj"] is not None:
+            wname, bname = S["proj"]
+            d16 = bufs.get("dout16", (B, dout.shape[1]), BF)
+            ops.cast_bf16(dout.contiguous(), d16)
+            dr16 = bufs.get("dr16", (B, D), BF)
+            ops.gemm(d16, S["wt"], b_major=1, out_bf16=dr16)
+            wgrad_into(d16, S["r16"], grads[wname], grads[bname])
+            ops.relu_bwd(S["last32"], dr16, dX, rows=B, cols=D, ldx=Lq * D, lddx=Lq * D)   # straight onto the CLS rows
+        else:
+            dX.view(B, Lq, D)[:, 0].copy_(dout)
+        dX16 = None                                       # optional bf16 part of the same gradient
+
+        dffn = bufs.get("dffn", (M, D), F32)
+        dffn16 = bufs.get("dffn16", (M, D), BF)
+        dsa = bufs.get("dsa", (M, D), F32)
+        dsa16 = bufs.get("dsa16", (M, D), BF)
+        dya = bufs.get("dya16", (M, D), BF)
+        dxa = bufs.get("dxa16", (M, D), BF)
+        dctx = bufs.get("dctx", (M, D), BF)
+        dqkv = bufs.get("dqkv", (M, 3 * D), BF)
+        dwqkv = bufs.get("dwqkv", (3 * D, D), F32)
+        dbqkv = bufs.get("dbqkv", (3 * D,), F32)
+
+        for i in reversed(range(len(layers))):
+            b = "%stransformer.layer.%d." % (prefix, i)
+            L = layers[i]
+            Hd = L["u"].shape[1]
+            du = bufs.get("du", (M, Hd), BF)
+            # x_out = LN(ffn_sum),  ffn_sum = lin2(gelu(lin1(y))) + y
+            ops.layernorm_bwd(L["ffn_sum"], L["m2"], L["r2"], p[b + "output_layer_norm.weight"], dy_bf16=dX16,
+                              dy_f32=dX, dx=dffn, dx_bf16=dffn16, dgamma=grads[b + "output_layer_norm.weight"],
+                              dbeta=grads[b + "output_layer_norm.bias"])
+            ops.gemm(dffn16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
+            wgrad_into(dffn16, L["g"], grads[b + "ffn.lin2.weight"], grads[b + "ffn.lin2.bias"])
+            ops.gemm(du, L["w1"], b_major=1, out_bf16=dya)
+            wgrad_into(du, L["y16"], grads[b + "ffn.lin1.weight"], grads[b + "ffn.lin1.bias"])
+            # y = LN(sa_sum),  sa_sum = out_lin(attn) + x ; dy = dffn (skip) + dya (through lin1)
+            ops.layernorm_bwd(L["sa_sum"], L["m1"], L["r1"], p[b + "sa_layer_norm.weight"], dy_bf16=dya, dy_f32=dffn,
+                              dx=dsa, dx_bf16=dsa16, dgamma=grads[b + "sa_layer_norm.weight"],
+                              dbeta=grads[b + "sa_layer_norm.bias"])
+            ops.gemm(dsa16, L["wo"], b_major=1, out_bf16=dctx)
+            wgrad_into(dsa16, L["ctx"], grads[b + "attention.out_lin.weight"], grads[b + "attention.out_lin.bias"])
+            ops.attn_bwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, L["qkv"], L["ctx"], L["lse"], dctx, dqkv, Q_SCALE, None,
+                         S["key_mask"])
+            ops.gemm(dqkv, L["wqkv"], b_major=1, out_bf16=dxa)
+            dwqkv.zero_()
+            dbqkv.zero_()
+            wgrad_into(dqkv, L["x16"], dwqkv, dbqkv)
+            for j, nm in enumerate(("q_lin", "k_lin", "v_lin")):
+                grads[b + "attention.%s.weight" % nm].copy_(dwqkv[j * D:(j + 1) * D])
+                grads[b + "attention.%s.bias" % nm].copy_(dbqkv[j * D:(j + 1) * D])
+            # gradient w.r.t. the layer input x: dsa (skip, fp32) + dxa (through q/k/v, bf16)
+            dX, dsa = dsa, dX
+            dX16 = dxa      # consumed by the first LayerNorm backward of the next iteration, rewritten after it
+
+        demb = dffn
+        ops.layernorm_bwd(S["emb"], S["m0"], S["r0"], p[prefix + "embeddings.LayerNorm.weight"], dy_bf16=dX16,
+                          dy_f32=dX, dx=demb, dgamma=grads[prefix + "embeddings.LayerNorm.weight"],
+                          dbeta=grads[prefix + "embeddings.LayerNorm.bias"])
+        ops.text_embed_bwd(S["ids"], demb, grads[prefix + "embeddings.word_embeddings.weight"],
+                           grads[prefix + "embeddings.position_embeddings.weight"], Lq)

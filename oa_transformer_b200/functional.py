@@ -1,0 +1,133 @@
+"""autograd glue: each tower, the similarity matrix, the InfoNCE loss and the embedding all-gather are ONE
+torch.autograd.Function whose forward/backward are liboat launches (engine.py / ops.py). Nothing here computes.
+
+Reference semantics kept:
+  * AllGather_multi (OATrans/trainer/trainer_dist.py:29-45): forward all-gathers and concatenates in rank order;
+    backward returns the local slice of the incoming gradient with NO reduction.
+  * sim_matrix (OATrans/model/model.py:164-172) and NormSoftmaxLoss (OATrans/model/loss.py:7-25) stay separate
+    callables, as the trainer invokes them separately (trainer_dist.py:161-162).
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+from .engine import GradBook
+
+_i32, _f32, _sz = ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
+
+
+class _TowerFn(torch.autograd.Function):
+    """forward(runner, *params): runner.fwd() launches the tower forward; backward returns one fp32 gradient per
+    parameter, in order (views of the runner's flat gradient book)."""
+
+    @staticmethod
+    def forward(ctx, runner, *params):
+        ctx.runner = runner
+        return runner.fwd()
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.runner.bwd(dout)
+        return (None,) + tuple(grads)
+
+
+class TowerRunner:
+    def __init__(self, engine, named_params, fwd_kwargs):
+        self.engine = engine
+        self.named = named_params                      # list of (name, Parameter)
+        self.pdict = {n: p for n, p in named_params}
+        self.kw = fwd_kwargs
+        self._book = None
+
+    def fwd(self):
+        return self.engine.forward(self.pdict, **self.kw)
+
+    def bwd(self, dout):
+        eng = self.engine
+        key = tuple((n, tuple(p.shape)) for n, p in self.named)
+        book = getattr(eng, "_gradbook", None)
+        if book is None or getattr(eng, "_gradbook_key", None) != key:
+            book = GradBook(self.named, dout.device)
+            eng._gradbook, eng._gradbook_key = book, key
+        book.zero()
+        eng.backward(self.pdict, book, dout.contiguous().float())
+        return [book[n] if p.requires_grad else None for n, p in self.named]
+
+
+def run_tower(engine, named_params, **fwd_kwargs):
+    """Differentiable tower call. named_params: list of (name, Parameter) that the engine reads by name."""
+    runner = TowerRunner(engine, named_params, fwd_kwargs)
+    if not torch.is_grad_enabled() or not any(p.requires_grad for _, p in named_params):
+        return engine.forward(runner.pdict, save=False, **fwd_kwargs)
+    return _TowerFn.apply(runner, *[p for _, p in named_params])
+
+
+# ---------------------------------------------------------------------------------------------- similarity + loss
+class _SimMatrixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, eps):
+        a = a.contiguous().float()
+        b = b.contiguous().float()
+        n, P = a.shape
+        m = b.shape[0]
+        ws = torch.empty(ops.sim_workspace_bytes(n, m, P), dtype=torch.uint8, device=a.device)
+        sims = torch.empty(n, m, dtype=torch.float32, device=a.device)
+        ops.sim_matrix_fwd(a, b, eps, sims, ws)
+        ctx.ws, ctx.shape, ctx.eps = ws, (n, m, P), eps
+        return sims
+
+    @staticmethod
+    def backward(ctx, dsims):
+        n, m, P = ctx.shape
+        da = torch.empty(n, P, dtype=torch.float32, device=dsims.device)
+        db = torch.empty(m, P, dtype=torch.float32, device=dsims.device)
+        ops.sim_matrix_bwd(dsims.contiguous().float(), ctx.eps, da, db, ctx.ws, n, m, P)
+        return da, db, None
+
+
+def sim_matrix(a, b, eps=1e-8):
+    """Cosine-similarity matrix with eps-clamped norms (model/model.py:164-172). a: (n,P) text, b: (m,P) video."""
+    return _SimMatrixFn.apply(a, b, eps)
+
+
+class _NormSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, temperature):
+        x = x.contiguous().float()
+        assert x.shape[0] == x.shape[1], "NormSoftmaxLoss expects a square similarity matrix"
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        ops.norm_softmax_loss(x, temperature, loss, dx)
+        ctx.save_for_backward(dx)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None
+
+
+def norm_softmax_loss(x, temperature=0.05):
+    return _NormSoftmaxFn.apply(x, temperature)
+
+
+# ---------------------------------------------------------------------------------------------- all-gather
+class AllGatherSlice(torch.autograd.Function):
+    """all_gather_into_tensor forward; backward = the local row slice, unreduced (trainer_dist.py:40-45)."""
+
+    @staticmethod
+    def forward(ctx, tensor, rank, world_size):
+        import torch.distributed as dist
+        ctx.rank, ctx.bs = rank, tensor.shape[0]
+        t = tensor.contiguous()
+        if world_size == 1 or not (dist.is_available() and dist.is_initialized()):
+            return t.clone()
+        out = torch.empty((world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad[ctx.bs * ctx.rank: ctx.bs * (ctx.rank + 1)], None, None

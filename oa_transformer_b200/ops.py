@@ -155,8 +155,9 @@ def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
                               _i32(dst.shape[1]), _i32(1 if relu else 0), stream_ptr()), "oat_cast_bf16")
 
 
-def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx):
-    check(lib().oat_relu_bwd(ptr(x), _i64(ldx), ptr(dy_bf16), _i64(dy_bf16.stride(0)), ptr(dx), _i64(dx.stride(0)),
+def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx, lddx=None):
+    check(lib().oat_relu_bwd(ptr(x), _i64(ldx), ptr(dy_bf16), _i64(dy_bf16.stride(0)), ptr(dx),
+                             _i64(dx.stride(0) if lddx is None else lddx),
                              _i64(rows), _i32(cols), stream_ptr()), "oat_relu_bwd")
 
 
@@ -218,3 +219,28 @@ def infonce_fwd_bwd(text, video, temperature=0.05, eps=1e-8, want_sims=False, wa
                                     ptr(loss), ptr(dt), ptr(dv), ptr(workspace), _sz(nbytes), stream_ptr()),
           "oat_infonce_fwd_bwd")
     return loss, sims, dt, dv
+
+
+def sim_workspace_bytes(n, m, P):
+    f = lib().oat_sim_workspace_bytes
+    f.restype = _sz
+    return int(f(_i32(n), _i32(m), _i32(P)))
+
+
+def sim_matrix_fwd(a, b, eps, sims, ws):
+    n, P = a.shape
+    m = b.shape[0]
+    check(lib().oat_sim_matrix_fwd(ptr(a), ptr(b), _i32(n), _i32(m), _i32(P), _f32(eps), ptr(sims), ptr(ws),
+                                   _sz(ws.numel()), stream_ptr()), "oat_sim_matrix_fwd")
+
+
+def sim_matrix_bwd(dsims, eps, da, db, ws, n, m, P):
+    check(lib().oat_sim_matrix_bwd(ptr(dsims), _i32(n), _i32(m), _i32(P), _f32(eps), ptr(da), ptr(db), ptr(ws),
+                                   _sz(ws.numel()), stream_ptr()), "oat_sim_matrix_bwd")
+
+
+def norm_softmax_loss(sims, temperature, loss, dsims):
+    n = sims.shape[0]
+    scratch = torch.empty(2 * n, dtype=torch.float32, device=sims.device)
+    check(lib().oat_norm_softmax_loss(ptr(sims), _i32(n), _i64(sims.stride(0)), _f32(temperature), ptr(loss),
+                                      ptr(dsims), ptr(scratch), stream_ptr()), "oat_norm_softmax_loss")

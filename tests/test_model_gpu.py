@@ -1,0 +1,145 @@
+"""End-to-end parity of the CUDA dual encoder (towers + sim matrix + InfoNCE, forward and backward) on the GPU:
+  * against OUTPUTS OF THE REFERENCE (tests/golden/dual_small.pt, cfg1_full.pt: fp32 PyTorch) - looser, documented gate
+    because the CUDA path rounds matmul operands to bf16;
+  * against the pinned oracle in bf16-operand mode on the same inputs - the 1e-3 gate of BASELINE.json.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import oracle as O
+from oracle.weights import dual_encoder_spec, fill_seeded
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def rel(a, b, floor=1e-6):
+    d, n = float((a.double() - b.double()).norm()), float(b.double().norm())
+    return 0.0 if d <= floor else d / max(n, 1e-30)
+
+
+def cuda_dual(p_cpu, video, ids, mask, heads, objects=None, want_grads=True):
+    """Run the CUDA path through the public functional layer with leaf parameters built from a weight dict."""
+    from oa_transformer_b200.engine import TextEngine, VideoEngine
+    from oa_transformer_b200.functional import norm_softmax_loss, run_tower, sim_matrix
+    dev = torch.device("cuda")
+    params = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in p_cpu.items()}
+    vnamed = [(k, v) for k, v in params.items() if k.startswith("video_model.") or k.startswith("vid_proj.")]
+    tnamed = [(k, v) for k, v in params.items() if (k.startswith("text_model.") or k.startswith("txt_proj."))
+              and v.is_floating_point()]
+    ve = run_tower(VideoEngine(dev, heads=heads), vnamed, video=video.to(dev),
+                   objects=None if objects is None else objects.to(dev))
+    te = run_tower(TextEngine(dev, heads=heads), tnamed, input_ids=ids.to(dev),
+                   attention_mask=None if mask is None else mask.to(dev))
+    sims = sim_matrix(te, ve)
+    loss = norm_softmax_loss(sims, 0.05)
+    grads = {}
+    if want_grads:
+        loss.backward()
+        grads = {k: v.grad.detach().cpu() for k, v in params.items() if v.is_floating_point() and v.grad is not None}
+    torch.cuda.synchronize()
+    return te.detach().cpu(), ve.detach().cpu(), sims.detach().cpu(), float(loss), grads
+
+
+def oracle_dual(p_cpu, video, ids, mask, cfg, objects=None):
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in p_cpu.items()}
+    data = {"video": video, "text": {"input_ids": ids, "attention_mask": mask}}
+    if objects is not None:
+        data["object"] = objects
+    te, ve = O.dual_encoder(data, p, cfg)
+    sims = O.sim_matrix(te, ve)
+    loss = O.norm_softmax_loss(sims)
+    loss.backward()
+    grads = {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.is_floating_point() and v.grad is not None}
+    return te.detach(), ve.detach(), sims.detach(), float(loss), grads
+
+
+def summarize(tag, sims, sims_ref, loss, loss_ref, grads, grads_ref):
+    errs = {k: rel(grads[k], grads_ref[k]) for k in grads_ref if k in grads}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    rep = {"case": tag, "logit_max_abs_err": float((sims - sims_ref).abs().max()), "loss": loss, "loss_ref": loss_ref,
+           "grad_rel_err_max": max(errs.values()) if errs else None,
+           "grad_rel_err_median": sorted(errs.values())[len(errs) // 2] if errs else None, "worst": worst,
+           "missing": [k for k in grads_ref if k not in grads][:5]}
+    os.makedirs(REPORT, exist_ok=True)
+    with open(os.path.join(REPORT, "parity_%s.json" % tag), "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep))
+    return rep
+
+
+def test_small_dual_encoder_vs_reference_golden_and_bf16_oracle():
+    g = torch.load(os.path.join(GOLD, "dual_small.pt"), map_location="cpu", weights_only=False)
+    w = g["weights"]
+    te, ve, sims, loss, grads = cuda_dual(w, g["video"], g["input_ids"], g["attention_mask"], heads=2)
+    # (1) vs the reference's fp32 outputs
+    rep = summarize("small_vs_reference", sims, g["sims"], loss, float(g["loss"]), grads, g["grads"])
+    assert rep["logit_max_abs_err"] < 2e-2 and not rep["missing"]
+    assert abs(loss - float(g["loss"])) < 5e-2
+    assert rep["grad_rel_err_max"] < 0.15
+    # (2) vs the pinned oracle in bf16-operand mode
+    cfg = O.OracleCfg(heads=2, text_layers=2, bf16=True)
+    _, _, osims, oloss, ograds = oracle_dual(w, g["video"], g["input_ids"], g["attention_mask"], cfg)
+    rep = summarize("small_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep["logit_max_abs_err"] < 1e-3
+    assert rep["grad_rel_err_max"] < 2e-2 and rep["grad_rel_err_median"] < 5e-3
+
+
+def test_cfg1_full_size_vs_reference_golden_and_bf16_oracle():
+    """BASELINE.json configs[0]: 2-frame 64x64, 0 objects, 8-token text, batch 4, full ViT-B/16 + DistilBERT."""
+    g = torch.load(os.path.join(GOLD, "cfg1_full.pt"), map_location="cpu", weights_only=False)
+    w = fill_seeded(g["shapes"], g["weight_seed"], g["weight_scale"])
+    te, ve, sims, loss, grads = cuda_dual(w, g["video"], g["input_ids"], g["attention_mask"], heads=12)
+    rep = summarize("cfg1_vs_reference", sims, g["sims"], loss, float(g["loss"]), grads, g["grads_subset"])
+    assert rep["logit_max_abs_err"] < 2e-2
+    cfg = O.OracleCfg(bf16=True)
+    _, _, osims, oloss, ograds = oracle_dual(w, g["video"], g["input_ids"], g["attention_mask"], cfg)
+    rep = summarize("cfg1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep["logit_max_abs_err"] < 1e-3          # north-star gate: sim-matrix logits within 1e-3
+    assert abs(loss - oloss) < 1e-3 * max(1.0, abs(oloss))
+    assert rep["grad_rel_err_median"] < 5e-3 and rep["grad_rel_err_max"] < 3e-2
+
+
+def test_object_tokens_224_vs_bf16_oracle():
+    """Spec-by-extension rows X1-X3: 224x224, 2 frames, 4 object regions per frame, ragged text."""
+    spec = dual_encoder_spec(frames=2, objects=True)
+    w = fill_seeded(spec, 77, 0.02)
+    g = torch.Generator().manual_seed(78)
+    B, Fr, Oo, L = 2, 2, 4, 12
+    video = torch.randn(B, Fr, 3, 224, 224, generator=g)
+    objects = O.synth_objects(B, Fr, Oo, g)
+    text = O.synth_text(B, L, g, ragged=True)
+    te, ve, sims, loss, grads = cuda_dual(w, video, text["input_ids"], text["attention_mask"], heads=12,
+                                          objects=objects)
+    cfg = O.OracleCfg(bf16=True)
+    _, _, osims, oloss, ograds = oracle_dual(w, video, text["input_ids"], text["attention_mask"], cfg, objects=objects)
+    rep = summarize("objects_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep["logit_max_abs_err"] < 1e-3
+    assert rep["grad_rel_err_median"] < 5e-3 and rep["grad_rel_err_max"] < 3e-2
+    assert "video_model.object_embed.weight" in grads
+
+
+def test_frozen_in_time_module_surface():
+    """The nn.Module mirror: constructor, forward(data) -> (text, video) embeddings, backward into .grad."""
+    from oa_transformer_b200.model import FrozenInTime, NormSoftmaxLoss, sim_matrix
+    torch.manual_seed(0)
+    m = FrozenInTime({"model": "SpaceTimeTransformer", "arch_config": "base_patch16_224", "num_frames": 2,
+                      "pretrained": True, "time_init": "zeros", "allow_missing_vit": True},
+                     {"model": "", "input_objects": False},
+                     {"model": "distilbert-base-uncased", "pretrained": True, "random_init": True}).cuda()
+    g = torch.Generator().manual_seed(1)
+    data = {"video": torch.randn(2, 2, 3, 224, 224, generator=g).cuda(),
+            "text": {k: v.cuda() for k, v in O.synth_text(2, 8, g).items()}}
+    te, ve = m(data, aug=True)
+    assert te.shape == (2, 256) and ve.shape == (2, 256)
+    loss = NormSoftmaxLoss(0.05)(sim_matrix(te, ve))
+    loss.backward()
+    assert m.vid_proj[0].weight.grad is not None and m.text_model.embeddings.word_embeddings.weight.grad is not None
+    assert torch.isfinite(loss)
+    with torch.no_grad():
+        s = m(data, return_embeds=False)
+    assert s.shape == (2, 2)
