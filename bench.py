@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py - video-text pairs/s, forward + backward, of the OA-Transformer dual-encoder hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch-per-gpu B]
+  (N > 1: launched by torch.distributed.run, one rank per GPU, NCCL)
+
+Workload (BASELINE.json metric / configs[3]): 8-frame 224x224 video + 36 object regions per frame + 32-token text,
+per-GPU batch 32 (global 256 on 8 GPUs, weak scaling), ViT-B/16 space-time tower + DistilBERT-base, bf16 operands /
+fp32 accumulation, synthetic inputs, seeded random weights. One step = text tower fwd, video tower fwd, embedding
+all-gather, sim matrix + symmetric InfoNCE, backward of all of it, and (N > 1) the gradient all-reduce that the
+reference's DDP wrapper performs (base/base_trainer.py:23). No optimizer step (as BASELINE.md defines the metric).
+
+value  : device-timed (CUDA events, max over ranks) with inputs resident in HBM.
+e2e    : the same step through the public plugin API (model.FrozenInTime -> AllGather -> sim_matrix ->
+         NormSoftmaxLoss), inputs in pinned HOST memory, H2D copies and the loss read-back inside the timed region.
+roofline / roofline_attention: per-launch CUDA-event timings of one extra instrumented step (never the timed steps).
+cpu_baseline: the CPU oracle (a port of the reference algorithm, oracle/oracle.py) on the host cores, bounded sample.
+--impl reference: the same CPU oracle as its own arm (the reference is pure PyTorch; /root/reference is absent on the
+         GPU box, so the pinned port is what runs - `kind: "port"`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "video-text pairs/sec (8-frame 224^2, 36 obj, 32-tok) fwd+bwd"
+UNIT = "pairs/s"
+FRAMES, OBJECTS, TEXT_LEN, IMG = 8, 36, 32, 224
+
+
+def pair_flops(frames=FRAMES, objects=OBJECTS, text_len=TEXT_LEN, n_patches=196):
+    """Algorithmic fwd FLOPs per pair (SURVEY.md section 8d formulas)."""
+    n = n_patches + objects
+    T = 1 + frames * n
+    video = 12 * (T * 18874368 + 4 * 768 * (frames * n * (1 + n) + frames * n * (1 + frames) + 2 * T)) \
+        + 2 * frames * n_patches * 768 * 768 + 2 * frames * objects * 2054 * 768 + 2 * 768 * 256
+    text = 6 * (text_len * 14155776 + 4 * text_len * text_len * 768) + 393216
+    return video + text
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_oracle_step_fn(batch, threads=None):
+    """fwd+bwd of the pinned CPU oracle (fp32, what the reference computes) on `batch` synthetic pairs."""
+    import torch
+    from oracle import oracle as O
+    from oracle.weights import dual_encoder_spec, fill_seeded
+    if threads:
+        torch.set_num_threads(threads)
+    w = fill_seeded(dual_encoder_spec(frames=FRAMES, objects=True), 0, 0.02)
+    p = {k: v.requires_grad_(True) for k, v in w.items()}
+    g = torch.Generator().manual_seed(1234)
+    video = torch.randn(batch, FRAMES, 3, IMG, IMG, generator=g)
+    objects = O.synth_objects(batch, FRAMES, OBJECTS, g)
+    text = O.synth_text(batch, TEXT_LEN, g)
+    cfg = O.OracleCfg()
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        te, ve = O.dual_encoder({"video": video, "object": objects, "text": text}, p, cfg)
+        loss = O.norm_softmax_loss(O.sim_matrix(te, ve))
+        loss.backward()
+        return float(loss.detach())
+
+    return step
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 2
+    step = cpu_oracle_step_fn(batch, cores)
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        step()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = batch / dt
+    sample = "%d timed fwd+bwd steps of %d pairs each (8x224^2 frames, 36 objects, 32 tokens), fp32, %d threads; " \
+             "steps capped at 10 and warm-up at 2 to bound the run" % (steps, batch, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "8-frame 224^2 + 36 obj/frame + 32-token text, fwd+bwd, CPU oracle port of the "
+                                   "reference path, batch %d per step" % batch},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_model(device, seed=0):
+    import torch
+    from oa_transformer_b200.model import FrozenInTime
+    from oa_transformer_b200.synth import fill_seeded
+    torch.manual_seed(seed)
+    m = FrozenInTime(
+        video_params={"model": "SpaceTimeObjectTransformer", "arch_config": "base_patch16_224", "num_frames": FRAMES,
+                      "pretrained": True, "time_init": "rand", "allow_missing_vit": True},
+        object_params={"model": "", "input_objects": True},
+        text_params={"model": "distilbert-base-uncased", "pretrained": True, "random_init": True, "input": "text"},
+        projection_dim=256)
+    sd = m.state_dict()
+    new = fill_seeded({k: v for k, v in sd.items()}, seed, 0.02)
+    m.load_state_dict(new)
+    return m.to(device)
+
+
+def synth_batch(batch, rank, pinned):
+    import torch
+    from oa_transformer_b200.synth import synth_objects, synth_text
+    g = torch.Generator().manual_seed(1234 + rank)
+    video = torch.randn(batch, FRAMES, 3, IMG, IMG, generator=g)
+    objects = synth_objects(batch, FRAMES, OBJECTS, g)
+    text = synth_text(batch, TEXT_LEN, g)
+    if pinned:
+        video, objects = video.pin_memory(), objects.pin_memory()
+        text = {k: v.pin_memory() for k, v in text.items()}
+    return {"video": video, "object": objects, "text": text}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oa_transformer_b200 import ops
+    from oa_transformer_b200._lib import lib, check
+    from oa_transformer_b200.functional import AllGatherSlice
+    from oa_transformer_b200.model import NormSoftmaxLoss, sim_matrix
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    check(lib().oat_device_check(), "oat_device_check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch_per_gpu
+
+    model = build_model(device)
+    model.train()
+    loss_fn = NormSoftmaxLoss(0.05)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_grads():
+        # what DDP's reducer does (base/base_trainer.py:23): average parameter gradients across ranks
+        if world > 1:
+            for eng in (model.video_model._engine, model._text_engine):
+                book = getattr(eng, "_gradbook", None)
+                if book is not None:
+                    dist.all_reduce(book.flat, op=dist.ReduceOp.AVG)
+
+    def step(data):
+        for p in params:
+            p.grad = None
+        text_e, video_e = model(data, aug=True)
+        video_g = AllGatherSlice.apply(video_e, rank, world)
+        text_g = AllGatherSlice.apply(text_e, rank, world)
+        loss = loss_fn(sim_matrix(text_g, video_g))
+        loss.backward()
+        reduce_grads()
+        return loss
+
+    host = synth_batch(B, rank, pinned=True)
+    dev = {"video": host["video"].to(device), "object": host["object"].to(device),
+           "text": {k: v.to(device) for k, v in host["text"].items()}}
+
+    # ---------------- device-resident timing
+    for _ in range(W):
+        step(dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = step(dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    launches = (ops.LAUNCHES - launches0) // K
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(loss)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B / (ms / 1e3)
+
+    # ---------------- end-to-end through the plugin API with host inputs
+    e2e = None
+    if not args.no_e2e:
+        h2d = host["video"].numel() * 4 + host["object"].numel() * 4 + sum(v.numel() * 8 for v in host["text"].values())
+
+        def e2e_step():
+            data = {"video": host["video"].to(device, non_blocking=True),
+                    "object": host["object"].to(device, non_blocking=True),
+                    "text": {k: v.to(device, non_blocking=True) for k, v in host["text"].items()}}
+            return float(step(data).item())     # D2H read of the loss closes the step
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / K * 1e3
+        ems = max(e0.elapsed_time(e1) / K, wall)
+        t = torch.tensor([ems], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / (float(t) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 4, "ms_per_step": float(t)}
+
+    # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)
+    roofline = roofline_attn = None
+    peaks = load_peaks()
+    if rank == 0 and not args.no_profile:
+        ops.PROFILE = []
+        step(dev)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, work, a, b in prof:
+            d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+            if isinstance(work, tuple):
+                d["bytes"] += work[0]
+                d["flops"] += work[1]
+            else:
+                d["flops"] += work
+        gm = agg.get("gemm")
+        if gm and gm["ms"] > 0:
+            ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+            roofline = {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": ach,
+                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "launches": gm["n"],
+                        "ms_in_step": gm["ms"], "peak_source": peaks["source"] + ", sustained bf16",
+                        "note": "algorithmic 2*M*N*K summed over every GEMM launch of one step / summed CUDA-event "
+                                "durations of those launches (instrumented extra step)"}
+        sp = agg.get("attn_fwd_0")
+        if sp and sp["ms"] > 0:
+            gbs = sp["bytes"] / (sp["ms"] / 1e3) / 1e9
+            roofline_attn = {"kernel": "attn_fwd_kernel space (+cls)", "bound": "hbm", "achieved": gbs,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                             "tflops": sp["flops"] / (sp["ms"] / 1e3) / 1e12, "traffic": None, "launches": sp["n"],
+                             "ms_in_step": sp["ms"]}
+        breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"]} for k, v in agg.items()}
+    else:
+        breakdown = None
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            cb = 2
+            cstep = cpu_oracle_step_fn(cb, cores)
+            cstep()
+            t0 = time.perf_counter()
+            n_rep = 2
+            for _ in range(n_rep):
+                cstep()
+            cdt = (time.perf_counter() - t0) / n_rep
+            cpu = {"value": cb / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d fwd+bwd steps of %d pairs (same per-pair workload), fp32 oracle port of the reference "
+                             "path, after 1 warm-up" % (n_rep, cb)}
+        except Exception as ex:  # the baseline is informative; never lose the GPU line over it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        flops = 3.0 * pair_flops()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "WebVid+CC3M-synth (BASELINE configs[3] per-GPU shard): 8-frame 224^2, 36 "
+                                       "obj/frame, 32-token text, batch %d per GPU, fwd+bwd (+grad all-reduce when "
+                                       "N>1), ViT-B/16 space-time + DistilBERT-base" % B,
+                           "global_batch": world * B, "tokens_per_video": 1 + FRAMES * (196 + OBJECTS),
+                           "parallelism": "dp%d" % world,
+                           "l2": "per-step working set (activations ~%.0f GB) far exceeds the 126 MB L2; no flush "
+                                 "needed" % (B * 0.85)},
+                "loss": loss_val,
+                "model_tflops": value * flops / 1e12,
+                "mfu_vs_sustained_bf16": value * flops / 1e12 / world / peaks["bf16_tflops_sustained"],
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+                "roofline_attention": roofline_attn, "kernel_ms_breakdown": breakdown, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -237,11 +237,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (col < p.scale_cols) { x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale; }
             if (p.act == 1) {
-              // forward GELU: keep the bf16 pre-activation for backward, activate the rounded value
+              // forward GELU on the fp32 accumulator; the bf16 pre-activation is kept for the backward pass only
               __nv_bfloat16* pre = p.out2_bf16 + static_cast<long long>(row) * p.ld2 + col;
               st_bf16x4(pre, x);
-              x.x = gelu_erf(bf16_round(x.x)); x.y = gelu_erf(bf16_round(x.y));
-              x.z = gelu_erf(bf16_round(x.z)); x.w = gelu_erf(bf16_round(x.w));
+              x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
             } else if (p.act == 2) {
               const float4 u = ld_bf16x4(p.aux_bf16 + static_cast<long long>(row) * p.ld_aux + col);
               x.x *= gelu_erf_grad(u.x); x.y *= gelu_erf_grad(u.y);

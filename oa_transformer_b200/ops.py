@@ -12,6 +12,33 @@ from ._lib import GemmArgs, check, lib, ptr, stream_ptr
 
 ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
 
+# Kernel-launch accounting (bench.py reports it) and an optional per-launch CUDA-event profiler for the roofline lines.
+LAUNCHES = 0
+PROFILE = None      # when a list: (kind, work, start_event, end_event) is appended around every profiled launch
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Prof:
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.work, self.e0, self.e1))
+        return False
+
 
 def _ld(t):
     assert t.dim() == 2 and t.stride(1) == 1, "expected a 2-D tensor with unit inner stride"
@@ -61,7 +88,9 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
         a.out2_bf16, a.ld2 = ptr(out2_bf16), _ld(out2_bf16)
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
-    check(lib().oat_gemm_bf16(ctypes.byref(a), stream_ptr()), "oat_gemm_bf16")
+    _count(1)
+    with _Prof("gemm", 2.0 * M * N * K):
+        check(lib().oat_gemm_bf16(ctypes.byref(a), stream_ptr()), "oat_gemm_bf16")
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
@@ -73,6 +102,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f3
     D = gamma.numel()
     rows = x.shape[0] if rows is None else rows
     ldx = x.stride(0) if ldx is None else ldx
+    _count(1)
     check(lib().oat_layernorm_fwd(
         ptr(x), _i64(ldx), ptr(gamma), ptr(beta), _f32(eps), _i64(rows), _i32(D),
         ptr(y_bf16), _i64(y_bf16.stride(0) if y_bf16 is not None else 0),
@@ -88,6 +118,7 @@ def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None,
     ldadd = add1.stride(0) if add1 is not None else (add2.stride(0) if add2 is not None else 0)
     if add1 is not None and add2 is not None:
         assert add1.stride(0) == add2.stride(0)
+    _count(1)
     check(lib().oat_layernorm_bwd(
         ptr(dy_bf16), _i64(dy_bf16.stride(0) if dy_bf16 is not None else 0),
         ptr(dy_f32), _i64((dy_f32.stride(0) if lddyf is None else lddyf) if dy_f32 is not None else 0),
@@ -129,10 +160,24 @@ def _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask):
     return a
 
 
+def attn_core_work(mode, B, T, H, F, n):
+    """(algorithmic bf16 bytes, FLOPs) of one forward attention core over all groups:
+    per group bytes = 2 B * 64 * (q rows + k rows + v rows + out rows), flops = 4 * nq * nk * 64."""
+    if mode == MODE_SPACE:
+        groups, nq, nk = B * H * F, n, n + 1
+    elif mode == MODE_TIME:
+        groups, nq, nk = B * H * n, F, F + 1
+    else:
+        groups, nq, nk = B * H, T, T
+    return (groups * 128.0 * (2 * nq + 2 * nk), groups * 4.0 * nq * nk * 64)
+
+
 def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None):
     """qkv bf16 [B*T, 3*H*64] (q pre-scaled) -> out bf16 [B*T, H*64], lse fp32 [B*H*T]."""
     a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
-    check(lib().oat_attn_fwd(ctypes.byref(a), stream_ptr()), "oat_attn_fwd")
+    _count(1 if mode == MODE_PLAIN else 2)
+    with _Prof("attn_fwd_%d" % mode, attn_core_work(mode, B, T, H, F, n)):
+        check(lib().oat_attn_fwd(ctypes.byref(a), stream_ptr()), "oat_attn_fwd")
 
 
 def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None):
@@ -142,7 +187,9 @@ def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None
     a.dqkv, a.ld_dqkv = ptr(dqkv), dqkv.stride(0)
     a.scale = scale
     a.cls_acc = ptr(cls_acc)
-    check(lib().oat_attn_bwd(ctypes.byref(a), stream_ptr()), "oat_attn_bwd")
+    _count(1 if mode == MODE_PLAIN else 2)
+    with _Prof("attn_bwd_%d" % mode, attn_core_work(mode, B, T, H, F, n)):
+        check(lib().oat_attn_bwd(ctypes.byref(a), stream_ptr()), "oat_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------------ packing / tokens
@@ -151,11 +198,13 @@ def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
     rows = dst.shape[0] if rows is None else rows
     cols = src.shape[-1] if cols is None else cols
     lds = (src.stride(0) if src.dim() == 2 else cols) if lds is None else lds
+    _count(1)
     check(lib().oat_cast_bf16(ptr(src), _i64(lds), ptr(dst), _i64(dst.stride(0)), _i64(rows), _i32(cols),
                               _i32(dst.shape[1]), _i32(1 if relu else 0), stream_ptr()), "oat_cast_bf16")
 
 
 def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx, lddx=None):
+    _count(1)
     check(lib().oat_relu_bwd(ptr(x), _i64(ldx), ptr(dy_bf16), _i64(dy_bf16.stride(0)), ptr(dx),
                              _i64(dx.stride(0) if lddx is None else lddx),
                              _i64(rows), _i32(cols), stream_ptr()), "oat_relu_bwd")
@@ -164,17 +213,20 @@ def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx, lddx=None):
 def im2col_patches(video, out, P=16):
     B, Fr, C, H, W = video.shape
     assert video.is_contiguous() and video.dtype == torch.float32
+    _count(1)
     check(lib().oat_im2col_patches(ptr(video), ptr(out), _i64(B * Fr), _i32(C), _i32(H), _i32(W), _i32(P),
                                    stream_ptr()), "oat_im2col_patches")
 
 
 def assemble_tokens(patch, obj, cls_token, pos_embed, temporal, type_embed, x, B, Fr, N, O, D):
+    _count(1)
     check(lib().oat_assemble_tokens(ptr(patch), ptr(obj), ptr(cls_token), ptr(pos_embed), ptr(temporal),
                                     ptr(type_embed), ptr(x), _i32(B), _i32(Fr), _i32(N), _i32(O), _i32(D),
                                     stream_ptr()), "oat_assemble_tokens")
 
 
 def assemble_tokens_bwd(dx, dpatch, dobj, dcls, dpos, dtemporal, dtype_embed, B, Fr, N, O, D):
+    _count(1)
     check(lib().oat_assemble_tokens_bwd(ptr(dx), ptr(dpatch), ptr(dobj), ptr(dcls), ptr(dpos), ptr(dtemporal),
                                         ptr(dtype_embed), _i32(B), _i32(Fr), _i32(N), _i32(O), _i32(D),
                                         stream_ptr()), "oat_assemble_tokens_bwd")
@@ -182,17 +234,20 @@ def assemble_tokens_bwd(dx, dpatch, dobj, dcls, dpos, dtemporal, dtype_embed, B,
 
 def colsum_bf16(x, out):
     """out[c] += sum_r x[r, c] (x bf16 2-D, out fp32)."""
+    _count(1)
     check(lib().oat_colsum_bf16(ptr(x), _i64(x.stride(0)), _i64(x.shape[0]), _i32(x.shape[1]), ptr(out),
                                 stream_ptr()), "oat_colsum_bf16")
 
 
 def text_embed(ids, word, pos, out, L):
     assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _count(1)
     check(lib().oat_text_embed(ptr(ids), ptr(word), ptr(pos), ptr(out), _i64(ids.numel()), _i32(L),
                                _i32(word.shape[1]), stream_ptr()), "oat_text_embed")
 
 
 def text_embed_bwd(ids, dsum, dword, dpos, L):
+    _count(1)
     check(lib().oat_text_embed_bwd(ptr(ids), ptr(dsum), ptr(dword), ptr(dpos), _i64(ids.numel()), _i32(L),
                                    _i32(dsum.shape[1]), stream_ptr()), "oat_text_embed_bwd")
 
@@ -215,6 +270,7 @@ def infonce_fwd_bwd(text, video, temperature=0.05, eps=1e-8, want_sims=False, wa
     sims = torch.empty(n, n, dtype=torch.float32, device=text.device) if want_sims else None
     dt = torch.empty_like(text) if want_grad else None
     dv = torch.empty_like(video) if want_grad else None
+    _count(8)
     check(lib().oat_infonce_fwd_bwd(ptr(text), ptr(video), _i32(n), _i32(P), _f32(temperature), _f32(eps), ptr(sims),
                                     ptr(loss), ptr(dt), ptr(dv), ptr(workspace), _sz(nbytes), stream_ptr()),
           "oat_infonce_fwd_bwd")
@@ -230,11 +286,13 @@ def sim_workspace_bytes(n, m, P):
 def sim_matrix_fwd(a, b, eps, sims, ws):
     n, P = a.shape
     m = b.shape[0]
+    _count(3)
     check(lib().oat_sim_matrix_fwd(ptr(a), ptr(b), _i32(n), _i32(m), _i32(P), _f32(eps), ptr(sims), ptr(ws),
                                    _sz(ws.numel()), stream_ptr()), "oat_sim_matrix_fwd")
 
 
 def sim_matrix_bwd(dsims, eps, da, db, ws, n, m, P):
+    _count(2)
     check(lib().oat_sim_matrix_bwd(ptr(dsims), _i32(n), _i32(m), _i32(P), _f32(eps), ptr(da), ptr(db), ptr(ws),
                                    _sz(ws.numel()), stream_ptr()), "oat_sim_matrix_bwd")
 
@@ -242,5 +300,6 @@ def sim_matrix_bwd(dsims, eps, da, db, ws, n, m, P):
 def norm_softmax_loss(sims, temperature, loss, dsims):
     n = sims.shape[0]
     scratch = torch.empty(2 * n, dtype=torch.float32, device=sims.device)
+    _count(2)
     check(lib().oat_norm_softmax_loss(ptr(sims), _i32(n), _i64(sims.stride(0)), _f32(temperature), ptr(loss),
                                       ptr(dsims), ptr(scratch), stream_ptr()), "oat_norm_softmax_loss")

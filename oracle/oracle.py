@@ -96,9 +96,26 @@ def layer_norm(x, w, b, eps):
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
+class _GeluBF16(torch.autograd.Function):
+    """GELU of the fp32 pre-activation; the derivative is evaluated at the bf16-rounded pre-activation (the CUDA path
+    stores the pre-activation in bf16 for the backward pass)."""
+
+    @staticmethod
+    def forward(ctx, u):
+        ctx.save_for_backward(_r(u))
+        return F.gelu(u)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ur,) = ctx.saved_tensors
+        cdf = 0.5 * (1.0 + torch.erf(ur * 0.7071067811865476))
+        pdf = 0.3989422804014327 * torch.exp(-0.5 * ur * ur)
+        return g * (cdf + ur * pdf)
+
+
 def gelu(x, cfg):
     # exact erf GELU (nn.GELU default, video_transformer.py:35-49; DistilBERT activation "gelu")
-    return F.gelu(_ste(x, cfg))
+    return _GeluBF16.apply(x) if cfg.bf16 else F.gelu(x)
 
 
 def _softmax_attention(q, k, v, cfg, add_mask=None):
@@ -365,31 +382,4 @@ def v2t_metrics(sims):
     return _cols2metrics(ranks, nq)
 
 
-# ----------------------------------------------------------------------------------------------------------------
-# synthetic inputs
-# ----------------------------------------------------------------------------------------------------------------
-def synth_objects(B, Fr, O, gen):
-    """Region features in the format of base/base_dataset.py:593-650: [2048 ROI feats | x1,y1,x2,y2,w,h] with boxes
-    scaled to [0,1]; rows are already in confidence order."""
-    feat = torch.randn(B, Fr, O, 2048, generator=gen).abs()
-    x1 = torch.rand(B, Fr, O, 1, generator=gen) * 0.7
-    y1 = torch.rand(B, Fr, O, 1, generator=gen) * 0.7
-    w = 0.1 + torch.rand(B, Fr, O, 1, generator=gen) * 0.2
-    h = 0.1 + torch.rand(B, Fr, O, 1, generator=gen) * 0.2
-    return torch.cat([feat, x1, y1, x1 + w, y1 + h, w, h], dim=-1)
-
-
-def synth_text(B, L, gen, vocab=30522, ragged=False):
-    ids = torch.randint(1000, vocab, (B, L), generator=gen)
-    ids[:, 0] = 101
-    mask = torch.ones(B, L, dtype=torch.long)
-    if ragged:
-        lens = torch.randint(4, L + 1, (B,), generator=gen)
-        lens[0] = L
-        for b in range(B):
-            ids[b, lens[b] - 1] = 102
-            ids[b, lens[b]:] = 0
-            mask[b, lens[b]:] = 0
-    else:
-        ids[:, -1] = 102
-    return {"input_ids": ids, "attention_mask": mask}
+from oa_transformer_b200.synth import synth_objects, synth_text  # noqa: E402,F401  (shared input generators)
