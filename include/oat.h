@@ -41,8 +41,8 @@ int oat_device_check(void);
  *   a_major = 0: A stored [M][lda], K contiguous.   a_major = 1: A stored [K][lda], M contiguous.
  *   b_major = 0: B stored [N][ldb], K contiguous.   b_major = 1: B stored [K][ldb], N contiguous.
  * epilogue order: alpha, +bias[N], first scale_cols columns *= scale, activation, +residual[M][ldr] (fp32), store.
- *   act 0: none | 1: GELU(erf) forward - GELU of the fp32 accumulator goes to the outputs, the bf16 pre-activation
- *   to out2_bf16 (for backward) | 2: multiply by GELU'(aux_bf16[M][ld_aux]) | 3: ReLU.
+ *   act 0: none | 1: GELU(erf) forward - GELU of the fp32 accumulator goes to the outputs and its derivative
+ *   GELU'(x) (bf16) to out2_bf16, which is exactly the aux operand of the backward GEMM | 2: multiply by aux_bf16[M][ld_aux] (the stored GELU') | 3: ReLU.
  *   accumulate = 1: atomically add into out_f32 (gradient accumulation / split-K). split_k = 0 lets the library pick.
  * Replaces: nn.Linear at video_transformer.py:102,133,46-49; Conv2d-as-GEMM :69; oa_model.py:68-75; torch.mm in
  * model/model.py:171; DistilBERT linears; and the autograd dgrad/wgrad of each. */

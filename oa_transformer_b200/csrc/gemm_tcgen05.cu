@@ -2,8 +2,10 @@
 //
 //   warp 0      : TMEM allocation, then TMA producer (one elected lane)
 //   warp 1      : mbarrier init, then tcgen05.mma issuer (one elected lane)
-//   warps 2..5  : epilogue - tcgen05.ld accumulator rows -> per-warp smem transpose -> coalesced 128-bit
-//                 global traffic with fused bias / q-scale / GELU / GELU' / fp32 residual / atomic accumulate
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, alternating 16-column chunks) - tcgen05.ld accumulator
+//                 rows -> per-warp smem transpose (128-bit, conflict-free pitch) -> coalesced global traffic with
+//                 fused bias / q-scale / GELU (+ stored derivative) / fp32 residual / atomic accumulate; residual and
+//                 aux operands of the NEXT chunk are prefetched while the current one is processed
 //
 // Operand tiles are staged by TMA into 128B-swizzled shared memory, 4 stages of (128 x 64) + (BLOCK_N x 64) bf16.
 // Either operand may be K-major (contraction dim contiguous in global memory: activations x weights^T) or
@@ -27,9 +29,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
-constexpr int kEpiWarps = 4;
-constexpr int kStagingFloats = 32 * 33;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kChunk = 16;                       // accumulator columns per tcgen05.ld
+constexpr int kStgPitch = 20;                    // floats; 80-byte rows keep STS.128 / LDS.128 conflict-free
+constexpr int kStagingFloats = 32 * kStgPitch;
 
 struct GemmParams {
   int M, N, K;
@@ -194,8 +198,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may address
+    const int q = warp & 3;                 // TMEM lane quarter this warp may address
+    const int half = (warp - 2) >> 2;       // which of the two interleaved chunk streams of that quarter
     float* stg = staging + (warp - 2) * kStagingFloats;
+    const int rr = lane & 7;                // row within an 8-row group handled per read-back iteration
+    const int cc = (lane >> 3) * 4;         // 4-column group within the 16-column chunk
+    constexpr int kChunks = BLOCK_N / kChunk;
     int local_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
       const int split = tile / tiles_mn;
@@ -203,33 +211,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
       const uint32_t acc = local_iter & 1;
       const uint32_t acc_phase = (local_iter >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int row_base = m_blk * BLOCK_M + q * 32;
       const int col_base = n_blk * BLOCK_N;
       const bool first_split = (split == 0);
+      const bool use_res = p.residual != nullptr && first_split;
+      const bool use_aux = p.act == 2;
+
+      float4 res_cur[4], res_nxt[4];
+      uint2 aux_cur[4], aux_nxt[4];
+      auto prefetch = [&](int c, float4 (&res)[4], uint2 (&aux)[4]) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row_base + it * 8 + rr;
+          const int col = col_base + c * kChunk + cc;
+          const bool ok = row < p.M && col < p.N;
+          if (use_res) res[it] = ok ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + col)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (use_aux) aux[it] = ok ? *reinterpret_cast<const uint2*>(p.aux_bf16 + static_cast<long long>(row) * p.ld_aux + col)
+                                    : make_uint2(0u, 0u);
+        }
+      };
+      prefetch(half, res_cur, aux_cur);          // global loads may start before the accumulator is ready
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+      for (int c = half; c < kChunks; c += 2) {
+        const bool last = (c + 2 >= kChunks);
+        if (!last) prefetch(c + 2, res_nxt, aux_nxt);
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * kChunk, v);
         tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {
-          // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the MMA warp
+        if (last) {
+          // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * kStgPitch + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3);
-          const int cc = (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + rr;
           const int row = row_base + r;
-          const int col = col_base + c * 32 + cc;
+          const int col = col_base + c * kChunk + cc;
           if (row < p.M && col < p.N) {
-            float4 x = make_float4(stg[r * 33 + cc], stg[r * 33 + cc + 1], stg[r * 33 + cc + 2], stg[r * 33 + cc + 3]);
+            float4 x = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cc);
             x.x *= p.alpha; x.y *= p.alpha; x.z *= p.alpha; x.w *= p.alpha;
             if (p.bias != nullptr && first_split) {
               const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
@@ -237,21 +265,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (col < p.scale_cols) { x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale; }
             if (p.act == 1) {
-              // forward GELU on the fp32 accumulator; the bf16 pre-activation is kept for the backward pass only
-              __nv_bfloat16* pre = p.out2_bf16 + static_cast<long long>(row) * p.ld2 + col;
-              st_bf16x4(pre, x);
-              x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
-            } else if (p.act == 2) {
-              const float4 u = ld_bf16x4(p.aux_bf16 + static_cast<long long>(row) * p.ld_aux + col);
-              x.x *= gelu_erf_grad(u.x); x.y *= gelu_erf_grad(u.y);
-              x.z *= gelu_erf_grad(u.z); x.w *= gelu_erf_grad(u.w);
+              // GELU(erf) and its derivative from one shared exponential; the derivative (bf16) is what backward needs
+              float4 d;
+              gelu_fwd_grad(x.x, x.x, d.x); gelu_fwd_grad(x.y, x.y, d.y);
+              gelu_fwd_grad(x.z, x.z, d.z); gelu_fwd_grad(x.w, x.w, d.w);
+              st_bf16x4(p.out2_bf16 + static_cast<long long>(row) * p.ld2 + col, d);
+            } else if (use_aux) {
+              const float2 a0 = unpack_bf16x2(aux_cur[it].x), a1 = unpack_bf16x2(aux_cur[it].y);
+              x.x *= a0.x; x.y *= a0.y; x.z *= a1.x; x.w *= a1.y;
             } else if (p.act == 3) {
               x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
             }
-            if (p.residual != nullptr && first_split) {
-              const float4 rr = *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-            }
+            if (use_res) { x.x += res_cur[it].x; x.y += res_cur[it].y; x.z += res_cur[it].z; x.w += res_cur[it].w; }
             if (p.out_f32 != nullptr) {
               float* o = p.out_f32 + static_cast<long long>(row) * p.ld_f32 + col;
               if (p.accumulate) {
@@ -264,6 +289,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) { res_cur[it] = res_nxt[it]; aux_cur[it] = aux_nxt[it]; }
       }
     }
   }

@@ -124,6 +124,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
@@ -168,6 +177,19 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return __bfloat1622float2(t);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// GELU(erf) and d/dx GELU from ONE exponential: erf(|x|/sqrt2) by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), whose
+// exp(-x^2/2) factor is also the Gaussian pdf the derivative needs. ~20 instructions per element instead of
+// erff() + expf() (the epilogue of the K=768 GEMMs has ~6 k cycles per 128x256 tile to spend).
+__device__ __forceinline__ void gelu_fwd_grad(float x, float& g, float& dg) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float e = __expf(-z * z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float cdf = 0.5f * (1.0f + copysignf(1.0f - poly * e, x));
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143268f, e, cdf);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {

@@ -97,20 +97,19 @@ def layer_norm(x, w, b, eps):
 
 
 class _GeluBF16(torch.autograd.Function):
-    """GELU of the fp32 pre-activation; the derivative is evaluated at the bf16-rounded pre-activation (the CUDA path
-    stores the pre-activation in bf16 for the backward pass)."""
+    """GELU of the fp32 pre-activation; the CUDA path stores the derivative GELU'(u) in bf16 for the backward pass."""
 
     @staticmethod
     def forward(ctx, u):
-        ctx.save_for_backward(_r(u))
-        return F.gelu(u)
+        cdf = 0.5 * (1.0 + torch.erf(u * 0.7071067811865476))
+        pdf = 0.3989422804014327 * torch.exp(-0.5 * u * u)
+        ctx.save_for_backward(_r(cdf + u * pdf))
+        return u * cdf
 
     @staticmethod
     def backward(ctx, g):
-        (ur,) = ctx.saved_tensors
-        cdf = 0.5 * (1.0 + torch.erf(ur * 0.7071067811865476))
-        pdf = 0.3989422804014327 * torch.exp(-0.5 * ur * ur)
-        return g * (cdf + ur * pdf)
+        (d,) = ctx.saved_tensors
+        return g * d
 
 
 def gelu(x, cfg):

@@ -57,21 +57,21 @@ def test_gemm_gelu_forward_backward():
     A, B = _mk((M, K), 5), _mk((N, K), 6)
     B = (B.float() * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda") * 0.1
-    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    dact = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_bf16=act, out2_bf16=pre)
-    u = A.float() @ B.float().t() + bias
-    assert torch.allclose(pre.float(), u, rtol=1e-2, atol=1e-2)
-    g = torch.nn.functional.gelu(pre.float())
-    assert torch.allclose(act.float(), g, rtol=1e-2, atol=1e-2)
-    # backward: dU = (dG @ W) * gelu'(pre)   with W = [N_out, K_in] stored row-major -> MN-major B operand
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_bf16=act, out2_bf16=dact)
+    u = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    g = torch.nn.functional.gelu(u)
+    g.sum().backward()
+    assert torch.allclose(act.float(), g.detach(), rtol=1e-2, atol=1e-2)
+    assert torch.allclose(dact.float(), u.grad, rtol=1e-2, atol=1e-2)      # out2 holds GELU'(u)
+    # backward: dU = (dG @ W) * GELU'(u)   with W = [N_out, K_in] stored row-major -> MN-major B operand
     dG = _mk((M, 768), 7)
     W2 = (_mk((768, N), 8).float() * 0.05).to(torch.bfloat16)  # fc2.weight [768, 3072]
     dU = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(dG, W2, b_major=1, act=ops.ACT_GELU_BWD, aux=pre, out_bf16=dU)
-    x = pre.float().requires_grad_(True)
-    torch.nn.functional.gelu(x).backward(dG.float() @ W2.float())
-    assert torch.allclose(dU.float(), x.grad, rtol=2e-2, atol=2e-2)
+    ops.gemm(dG, W2, b_major=1, act=ops.ACT_GELU_BWD, aux=dact, out_bf16=dU)
+    ref = (dG.float() @ W2.float()) * dact.float()
+    assert torch.allclose(dU.float(), ref, rtol=2e-2, atol=2e-2)
 
 
 def test_gemm_wgrad_splitk_accumulate():

@@ -90,7 +90,7 @@ def noise_floor(w, video, ids, mask, cfg16, cfg32, objects=None, temperature=0.0
     """bf16-operand oracle vs fp32 oracle on the same inputs: the error that operand rounding alone introduces."""
     _, _, s16, l16, g16 = oracle_dual(w, video, ids, mask, cfg16, objects, temperature)
     _, _, s32, l32, g32 = oracle_dual(w, video, ids, mask, cfg32, objects, temperature)
-    rep = summarize("noise_floor", s16, s32, l16, l32, g16, g32)
+    rep = summarize("noise_floor_T%g" % temperature, s16, s32, l16, l32, g16, g32)
     return (s16, l16, g16), rep
 
 
@@ -131,16 +131,18 @@ def test_cfg1_full_size_vs_reference_golden_and_bf16_oracle():
 
 
 def test_cfg1_gradients_without_temperature_amplification():
-    """Same network and inputs with T = 1: the logit noise is no longer multiplied by 20 inside the loss, so the
-    backward kernels can be checked tightly against the bf16 oracle."""
+    """Same network and inputs with T = 1 (the logit noise is no longer multiplied by 20 inside the loss): the CUDA
+    gradients must sit within the operand-rounding noise floor measured the same way (bf16 oracle vs fp32 oracle).
+    Bias gradients are sums over the batch of nearly cancelling rows, which is where that floor is largest."""
     g = torch.load(os.path.join(GOLD, "cfg1_full.pt"), map_location="cpu", weights_only=False)
     w = fill_seeded(g["shapes"], g["weight_seed"], g["weight_scale"])
     te, ve, sims, loss, grads = cuda_dual(w, g["video"], g["input_ids"], g["attention_mask"], heads=12, temperature=1.0)
-    _, _, osims, oloss, ograds = oracle_dual(w, g["video"], g["input_ids"], g["attention_mask"], O.OracleCfg(bf16=True),
-                                             temperature=1.0)
+    (osims, oloss, ograds), floor = noise_floor(w, g["video"], g["input_ids"], g["attention_mask"],
+                                                O.OracleCfg(bf16=True), O.OracleCfg(), temperature=1.0)
     rep = summarize("cfg1_T1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
     assert abs(loss - oloss) < 1e-3 * max(1.0, abs(oloss))
-    assert rep["grad_rel_err_median"] < 4e-3 and rep["grad_rel_err_max"] < 1e-2
+    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
+    assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
 
 
 def test_object_tokens_224_vs_bf16_oracle():
