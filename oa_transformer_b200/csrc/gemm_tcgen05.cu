@@ -56,6 +56,15 @@ struct GemmParams {
   int accumulate;
 };
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <int BLOCK_N>
 struct GemmSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
@@ -78,7 +87,11 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// Epilogue specialisations (compile-time, so the per-element instruction count stays small - the K=768 GEMMs give the
+// epilogue only ~5 us per 128x256 tile): the generic one keeps every runtime switch of oat_gemm_args.
+enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI_MULAUX = 4, EPI_ATOMIC = 5 };
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -201,9 +214,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = warp & 3;                 // TMEM lane quarter this warp may address
     const int half = (warp - 2) >> 2;       // which of the two interleaved chunk streams of that quarter
     float* stg = staging + (warp - 2) * kStagingFloats;
+    const uint32_t stg_w = smem_u32(stg) + lane * (kStgPitch * 4);                      // this lane's row (write side)
+    const uint32_t stg_r = smem_u32(stg) + ((lane & 7) * kStgPitch + (lane >> 3) * 4) * 4;  // read side, +it*8 rows
     const int rr = lane & 7;                // row within an 8-row group handled per read-back iteration
     const int cc = (lane >> 3) * 4;         // 4-column group within the 16-column chunk
     constexpr int kChunks = BLOCK_N / kChunk;
+    constexpr bool kGeneric = EPI == EPI_GENERIC;
     int local_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
       const int split = tile / tiles_mn;
@@ -211,23 +227,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
       const uint32_t acc = local_iter & 1;
       const uint32_t acc_phase = (local_iter >> 1) & 1;
-      const int row_base = m_blk * BLOCK_M + q * 32;
-      const int col_base = n_blk * BLOCK_N;
+      const int row_base = m_blk * BLOCK_M + q * 32 + rr;
+      const int col_lane = n_blk * BLOCK_N + cc;          // + c * kChunk
       const bool first_split = (split == 0);
-      const bool use_res = p.residual != nullptr && first_split;
-      const bool use_aux = p.act == 2;
+      const bool use_bias = p.bias != nullptr && first_split;
+      const bool use_res = (kGeneric || EPI == EPI_F32_RES) && p.residual != nullptr && first_split;
+      const bool use_aux = EPI == EPI_MULAUX || (kGeneric && p.act == 2);
+      // per-row element offsets of the 4 rows this lane finishes per chunk (row = row_base + it*8)
+      bool row_ok[4];
+      long long off_f32[4], off_bf16[4], off_res[4], off_x2[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long row = row_base + it * 8;
+        row_ok[it] = row < p.M;
+        off_f32[it] = row * p.ld_f32 + col_lane;
+        off_bf16[it] = row * p.ld_bf16 + col_lane;
+        off_res[it] = row * p.ldr + col_lane;
+        off_x2[it] = (EPI == EPI_GELU || (kGeneric && p.act == 1)) ? row * p.ld2 + col_lane : row * p.ld_aux + col_lane;
+      }
 
       float4 res_cur[4], res_nxt[4];
       uint2 aux_cur[4], aux_nxt[4];
       auto prefetch = [&](int c, float4 (&res)[4], uint2 (&aux)[4]) {
+        const bool col_ok = col_lane + c * kChunk < p.N;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int row = row_base + it * 8 + rr;
-          const int col = col_base + c * kChunk + cc;
-          const bool ok = row < p.M && col < p.N;
-          if (use_res) res[it] = ok ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + col)
+          const bool ok = row_ok[it] && col_ok;
+          if (use_res) res[it] = ok ? *reinterpret_cast<const float4*>(p.residual + off_res[it] + c * kChunk)
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (use_aux) aux[it] = ok ? *reinterpret_cast<const uint2*>(p.aux_bf16 + static_cast<long long>(row) * p.ld_aux + col)
+          if (use_aux) aux[it] = ok ? *reinterpret_cast<const uint2*>(p.aux_bf16 + off_x2[it] + c * kChunk)
                                     : make_uint2(0u, 0u);
         }
       };
@@ -248,44 +276,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * kStgPitch + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) sts128(stg_w + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
+        const int col = col_lane + c * kChunk;
+        if (col < p.N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI != EPI_ATOMIC && EPI != EPI_MULAUX && use_bias) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+          const bool scaled = (kGeneric || EPI == EPI_BF16) && col < p.scale_cols;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 8 + rr;
-          const int row = row_base + r;
-          const int col = col_base + c * kChunk + cc;
-          if (row < p.M && col < p.N) {
-            float4 x = *reinterpret_cast<const float4*>(stg + r * kStgPitch + cc);
-            x.x *= p.alpha; x.y *= p.alpha; x.z *= p.alpha; x.w *= p.alpha;
-            if (p.bias != nullptr && first_split) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-            }
-            if (col < p.scale_cols) { x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale; }
-            if (p.act == 1) {
+          for (int it = 0; it < 4; ++it) {
+            if (!row_ok[it]) continue;
+            float4 x = lds128(stg_r + it * (8 * kStgPitch * 4));
+            if (kGeneric) { x.x *= p.alpha; x.y *= p.alpha; x.z *= p.alpha; x.w *= p.alpha; }
+            x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+            if (scaled) { x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale; }
+            if (EPI == EPI_GELU || (kGeneric && p.act == 1)) {
               // GELU(erf) and its derivative from one shared exponential; the derivative (bf16) is what backward needs
               float4 d;
               gelu_fwd_grad(x.x, x.x, d.x); gelu_fwd_grad(x.y, x.y, d.y);
               gelu_fwd_grad(x.z, x.z, d.z); gelu_fwd_grad(x.w, x.w, d.w);
-              st_bf16x4(p.out2_bf16 + static_cast<long long>(row) * p.ld2 + col, d);
+              st_bf16x4(p.out2_bf16 + off_x2[it] + c * kChunk, d);
             } else if (use_aux) {
               const float2 a0 = unpack_bf16x2(aux_cur[it].x), a1 = unpack_bf16x2(aux_cur[it].y);
               x.x *= a0.x; x.y *= a0.y; x.z *= a1.x; x.w *= a1.y;
-            } else if (p.act == 3) {
+            } else if (kGeneric && p.act == 3) {
               x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
             }
             if (use_res) { x.x += res_cur[it].x; x.y += res_cur[it].y; x.z += res_cur[it].z; x.w += res_cur[it].w; }
-            if (p.out_f32 != nullptr) {
-              float* o = p.out_f32 + static_cast<long long>(row) * p.ld_f32 + col;
-              if (p.accumulate) {
-                atomicAdd(o + 0, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
-              } else {
-                *reinterpret_cast<float4*>(o) = x;
-              }
+            if (EPI == EPI_ATOMIC || (kGeneric && p.accumulate && p.out_f32 != nullptr)) {
+              float* o = p.out_f32 + off_f32[it] + c * kChunk;
+              atomicAdd(o + 0, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+            } else if (EPI == EPI_F32_RES || (kGeneric && p.out_f32 != nullptr)) {
+              *reinterpret_cast<float4*>(p.out_f32 + off_f32[it] + c * kChunk) = x;
             }
-            if (p.out_bf16 != nullptr) st_bf16x4(p.out_bf16 + static_cast<long long>(row) * p.ld_bf16 + col, x);
+            if (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_MULAUX || (kGeneric && p.out_bf16 != nullptr))
+              st_bf16x4(p.out_bf16 + off_bf16[it] + c * kChunk, x);
           }
         }
         __syncwarp();
@@ -355,7 +380,19 @@ static int pick_split_k(int tiles_mn, int k_blocks, int sms, int requested) {
   return best;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+static int pick_epi(const oat_gemm_args* a) {
+  if (a->alpha != 1.0f) return EPI_GENERIC;
+  const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
+  if (a->accumulate) return (f32 && !b16 && a->act == 0 && a->bias == nullptr && a->residual == nullptr && a->scale_cols == 0) ? EPI_ATOMIC : EPI_GENERIC;
+  if (a->act == 1) return (b16 && !f32 && a->residual == nullptr && a->scale_cols == 0) ? EPI_GELU : EPI_GENERIC;
+  if (a->act == 2) return (b16 && !f32 && a->residual == nullptr && a->bias == nullptr && a->scale_cols == 0) ? EPI_MULAUX : EPI_GENERIC;
+  if (a->act != 0) return EPI_GENERIC;
+  if (b16 && !f32 && a->residual == nullptr) return EPI_BF16;
+  if (f32 && !b16 && a->scale_cols == 0) return EPI_F32_RES;
+  return EPI_GENERIC;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -389,7 +426,7 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
   p.accumulate = a->accumulate;
 
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -417,15 +454,30 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
   const bool amn = a->a_major != 0, bmn = a->b_major != 0;
   // 256-wide tiles unless the problem is narrow
   const bool wide = (a->N % 256 == 0) || a->N > 512;
-  if (wide) {
-    if (!amn && !bmn) return launch_gemm<256, false, false>(a, s);
-    if (!amn && bmn) return launch_gemm<256, false, true>(a, s);
-    if (amn && bmn) return launch_gemm<256, true, true>(a, s);
-    return launch_gemm<256, true, false>(a, s);
-  } else {
-    if (!amn && !bmn) return launch_gemm<128, false, false>(a, s);
-    if (!amn && bmn) return launch_gemm<128, false, true>(a, s);
-    if (amn && bmn) return launch_gemm<128, true, true>(a, s);
-    return launch_gemm<128, true, false>(a, s);
+  const int code = (amn ? 2 : 0) | (bmn ? 1 : 0);
+  if (!wide) {
+    switch (code) {
+      case 0: return launch_gemm<128, false, false, EPI_GENERIC>(a, s);
+      case 1: return launch_gemm<128, false, true, EPI_GENERIC>(a, s);
+      case 2: return launch_gemm<128, true, false, EPI_GENERIC>(a, s);
+      default: return launch_gemm<128, true, true, EPI_GENERIC>(a, s);
+    }
   }
+  const int epi = pick_epi(a);
+#define OAT_GEMM_CASE(AM, BM)                                                         \
+  switch (epi) {                                                                      \
+    case EPI_BF16: return launch_gemm<256, AM, BM, EPI_BF16>(a, s);                   \
+    case EPI_F32_RES: return launch_gemm<256, AM, BM, EPI_F32_RES>(a, s);             \
+    case EPI_GELU: return launch_gemm<256, AM, BM, EPI_GELU>(a, s);                   \
+    case EPI_MULAUX: return launch_gemm<256, AM, BM, EPI_MULAUX>(a, s);               \
+    case EPI_ATOMIC: return launch_gemm<256, AM, BM, EPI_ATOMIC>(a, s);               \
+    default: return launch_gemm<256, AM, BM, EPI_GENERIC>(a, s);                      \
+  }
+  switch (code) {
+    case 0: OAT_GEMM_CASE(false, false)
+    case 1: OAT_GEMM_CASE(false, true)
+    case 2: OAT_GEMM_CASE(true, false)
+    default: OAT_GEMM_CASE(true, true)
+  }
+#undef OAT_GEMM_CASE
 }
