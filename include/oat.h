@@ -68,14 +68,15 @@ int oat_gemm_bf16(const oat_gemm_args* args, oat_stream_t stream);
  * Forward: y = (x - mean) * rstd * gamma + beta per row; writes bf16 (GEMM operand) and/or fp32 outputs and the
  * row statistics needed by backward. Replaces nn.LayerNorm(eps=1e-6) at video_transformer.py:164,167,174,346 and
  * DistilBERT's LayerNorm(eps=1e-12). Rows may be strided (ldx) so that only the CLS rows are normalised for :351.
- * Backward: dy = dy_bf16 (+ dy_f32); dx = add1 + add2 + LN'(dy); dgamma/dbeta are ACCUMULATED (atomics). */
+ * Backward: dy = dy_bf16 (+ dy_f32); dx = add1 + add2 + LN'(dy); dgamma/dbeta are ACCUMULATED (atomics), and so is
+ * dxsum[c] += sum_rows dx[row, c] (optional: the bias gradient of the GEMM that produced the LayerNorm input). */
 int oat_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t rows,
                       int32_t D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
                       oat_stream_t stream);
 int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float* dy_f32, int64_t lddyf, const float* x,
                       int64_t ldx, const float* mean, const float* rstd, const float* gamma, int64_t rows, int32_t D,
                       const float* add1, const float* add2, int64_t ldadd, float* dx, int64_t lddx, void* dx_bf16,
-                      int64_t lddxb, float* dgamma, float* dbeta, oat_stream_t stream);
+                      int64_t lddxb, float* dgamma, float* dbeta, float* dxsum, oat_stream_t stream);
 
 /* ---- attention ------------------------------------------------------------------------------------------------
  * qkv: bf16 [B*T, 3*H*64] as produced by the qkv GEMM (q already scaled by 64^-0.5, columns q | k | v, head-major).

@@ -166,21 +166,44 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a slab of rows for all columns.
+// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a 256-row slab; a thread owns 8 adjacent columns
+// (one 16-byte load per row) and keeps 8 independent loads in flight.
 constexpr int kColsumRowsPerCta = 256;
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int cols,
-                                   float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                          long long rows, int cols, float* __restrict__ out) {
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c >= cols) return;
   const long long r0 = static_cast<long long>(blockIdx.x) * kColsumRowsPerCta;
   const long long r1 = min(rows, r0 + kColsumRowsPerCta);
-  for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
-    float s0 = 0.f, s1 = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
-      s0 += v.x; s1 += v.y;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  long long r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (r + u) * ld + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+      }
     }
-    atomicAdd(out + c, s0);
-    atomicAdd(out + c + 1, s1);
   }
+  for (; r < r1; ++r) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(out + c + k, acc[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ text embeddings
@@ -278,11 +301,13 @@ extern "C" int oat_assemble_tokens_bwd(const float* dx, void* dpatch_bf16, void*
 
 extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int32_t cols, float* out,
                                oat_stream_t stream) {
-  OAT_REQUIRE(cols % 2 == 0 && ld % 2 == 0, "oat_colsum_bf16: cols and ld must be even");
+  OAT_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "oat_colsum_bf16: cols and ld must be multiples of 8");
   if (rows <= 0) return OAT_OK;
-  const unsigned grid = static_cast<unsigned>((rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta);
-  colsum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows,
-                                                          cols, out);
+  const int threads = cols / 8 < 256 ? ((cols / 8 + 31) / 32) * 32 : 256;
+  dim3 grid(static_cast<unsigned>((rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta),
+            static_cast<unsigned>((cols / 8 + threads - 1) / threads));
+  colsum_bf16_kernel<<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows,
+                                                             cols, out);
   return check_launch("colsum_bf16_kernel");
 }
 

@@ -59,6 +59,11 @@ struct GemmParams {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// one 128-bit reduction instead of four scalar atomics (split-K / gradient accumulation epilogue)
+__device__ __forceinline__ void red_add_v4(float* gptr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(gptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -304,8 +309,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (use_res) { x.x += res_cur[it].x; x.y += res_cur[it].y; x.z += res_cur[it].z; x.w += res_cur[it].w; }
             if (EPI == EPI_ATOMIC || (kGeneric && p.accumulate && p.out_f32 != nullptr)) {
-              float* o = p.out_f32 + off_f32[it] + c * kChunk;
-              atomicAdd(o + 0, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+              red_add_v4(p.out_f32 + off_f32[it] + c * kChunk, x);
             } else if (EPI == EPI_F32_RES || (kGeneric && p.out_f32 != nullptr)) {
               *reinterpret_cast<float4*>(p.out_f32 + off_f32[it] + c * kChunk) = x;
             }

@@ -70,17 +70,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows,
                      const float* __restrict__ add1, const float* __restrict__ add2, long long ldadd,
                      float* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = NV * 128;
   __shared__ float red[kLnWarps][D];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float4 gm[NV], dg[NV], db[NV];
+  float4 gm[NV], dg[NV], db[NV], ds[NV];   // ds: column sums of dx (the bias gradient of the producer GEMM)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     gm[i] = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long row = static_cast<long long>(blockIdx.x) * kLnWarps + warp; row < rows;
        row += static_cast<long long>(gridDim.x) * kLnWarps) {
@@ -124,6 +125,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb,
         const float4 a = reinterpret_cast<const float4*>(add2 + row * ldadd)[i * 32 + lane];
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
       }
+      ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
       if (dx != nullptr) reinterpret_cast<float4*>(dx + row * lddx)[i * 32 + lane] = o;
       if (dx_bf16 != nullptr) {
         uint2 pk;
@@ -133,11 +135,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb,
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr) return;
+  if (dgamma == nullptr && dbeta == nullptr && dxsum == nullptr) return;
   // cross-warp reduction of the per-lane column partials, then one atomic per column per CTA
-  for (int pass = 0; pass < 2; ++pass) {
-    float4* src = pass == 0 ? dg : db;
-    float* dst = pass == 0 ? dgamma : dbeta;
+  for (int pass = 0; pass < 3; ++pass) {
+    float4* src = pass == 0 ? dg : (pass == 1 ? db : ds);
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(red[warp])[i * 32 + lane] = src[i];
@@ -168,13 +170,13 @@ template <int NV>
 static int launch_ln_bwd(const void* dyb, long long lddyb, const float* dyf, long long lddyf, const float* x,
                          long long ldx, const float* mean, const float* rstd, const float* gamma, long long rows,
                          const float* add1, const float* add2, long long ldadd, float* dx, long long lddx,
-                         void* dxb, long long lddxb, float* dgamma, float* dbeta, cudaStream_t s) {
+                         void* dxb, long long lddxb, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
   long long want = (rows + kLnWarps - 1) / kLnWarps;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dyb), lddyb, dyf, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2,
-      ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta);
+      ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, dxsum);
   return check_launch("layernorm_bwd_kernel");
 }
 
@@ -202,7 +204,7 @@ extern "C" int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float
                                  const float* x, int64_t ldx, const float* mean, const float* rstd,
                                  const float* gamma, int64_t rows, int32_t D, const float* add1, const float* add2,
                                  int64_t ldadd, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb, float* dgamma,
-                                 float* dbeta, oat_stream_t stream) {
+                                 float* dbeta, float* dxsum, oat_stream_t stream) {
   using namespace oat;
   OAT_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024, "oat_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
   OAT_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "oat_layernorm_bwd: no incoming gradient");
@@ -210,7 +212,7 @@ extern "C" int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float
   cudaStream_t s = as_stream(stream);
 #define OAT_LN_BWD(NV)                                                                                              \
   return launch_ln_bwd<NV>(dy_bf16, lddyb, dy_f32, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2, ldadd, dx, \
-                           lddx, dx_bf16, lddxb, dgamma, dbeta, s)
+                           lddx, dx_bf16, lddxb, dgamma, dbeta, dxsum, s)
   switch (D / 128) {
     case 1: OAT_LN_BWD(1);
     case 2: OAT_LN_BWD(2);

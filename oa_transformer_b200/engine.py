@@ -205,10 +205,12 @@ class VideoEngine:
         prefix = S["prefix"]
         xs, layers = S["xs"], S["layers"]
 
-        def wgrad(dy16, act16, name):
+        def wgrad(dy16, act16, name, bias=True):
+            # bias=False: the bias gradient was already reduced (fp32) by the LayerNorm-backward kernel that produced dy
             ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
                      accumulate=True)
-            ops.colsum_bf16(dy16, grads[name + ".bias"])
+            if bias:
+                ops.colsum_bf16(dy16, grads[name + ".bias"])
 
         dy = bufs.get("dy.a", (M, D), F32, zero=True)         # d(block output), non-zero in the CLS rows only
         dy16 = bufs.get("dy16.a", (M, D), BF, zero=True)
@@ -225,7 +227,8 @@ class VideoEngine:
             ops.cast_bf16(dout.contiguous(), dcls16)
         ops.layernorm_bwd(xs[depth], S["mf"], S["rf"], p[prefix + "norm.weight"], dy_bf16=dcls16, rows=B, ldx=T * D,
                           dx=dy, dx_bf16=dy16, lddx=T * D, lddxb=T * D, dgamma=grads[prefix + "norm.weight"],
-                          dbeta=grads[prefix + "norm.bias"])
+                          dbeta=grads[prefix + "norm.bias"],
+                          dxsum=grads["%sblocks.%d.mlp.fc2.bias" % (prefix, depth - 1)] if depth > 0 else None)
 
         du = bufs.get("du", (M, 4 * D), BF)
         dh = bufs.get("dh", (M, D), BF)
@@ -244,28 +247,31 @@ class VideoEngine:
             L = layers[i]
             # ---- x_out = sr + fc2(gelu(fc1(norm2(sr))))
             ops.gemm(dy16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
-            wgrad(dy16, L["g"], b + "mlp.fc2")
+            wgrad(dy16, L["g"], b + "mlp.fc2", bias=False)
             ops.gemm(du, L["w1"], b_major=1, out_bf16=dh)
             wgrad(du, L["h2"], b + "mlp.fc1")
             ops.layernorm_bwd(L["sr"], L["m2"], L["r2"], p[b + "norm2.weight"], dy_bf16=dh, add1=dy, dx=dsr,
-                              dx_bf16=dsr16, dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"])
+                              dx_bf16=dsr16, dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"],
+                              dxsum=grads[b + "attn.proj.bias"])
             # ---- sr = x + proj_s(space_attn(qkv_s(norm1(tr))))
             ops.gemm(dsr16, L["wproj_s"], b_major=1, out_bf16=da)
-            wgrad(dsr16, L["a_s"], b + "attn.proj")
+            wgrad(dsr16, L["a_s"], b + "attn.proj", bias=False)
             ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv, Q_SCALE, acc)
             ops.gemm(dqkv, L["wqkv_s"], b_major=1, out_bf16=dh)
             wgrad(dqkv, L["h1"], b + "attn.qkv")
             ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16,
-                              dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"])
+                              dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"],
+                              dxsum=grads[b + "timeattn.proj.bias"])
             # ---- tr = x + proj_t(time_attn(qkv_t(norm3(x))))
             ops.gemm(dtr16, L["wproj_t"], b_major=1, out_bf16=da)
-            wgrad(dtr16, L["a_t"], b + "timeattn.proj")
+            wgrad(dtr16, L["a_t"], b + "timeattn.proj", bias=False)
             ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv, Q_SCALE, acc)
             ops.gemm(dqkv, L["wqkv_t"], b_major=1, out_bf16=dh)
             wgrad(dqkv, L["h3"], b + "timeattn.qkv")
             # ---- dx = dsr (space skip) + dtr (time skip) + norm3'(dh)
             ops.layernorm_bwd(xs[i], L["m3"], L["r3"], p[b + "norm3.weight"], dy_bf16=dh, add1=dsr, add2=dtr, dx=dyb,
-                              dx_bf16=dy16b, dgamma=grads[b + "norm3.weight"], dbeta=grads[b + "norm3.bias"])
+                              dx_bf16=dy16b, dgamma=grads[b + "norm3.weight"], dbeta=grads[b + "norm3.bias"],
+                              dxsum=grads["%sblocks.%d.mlp.fc2.bias" % (prefix, i - 1)] if i > 0 else None)
             dy, dyb = dyb, dy
             dy16, dy16b = dy16b, dy16
 
@@ -383,7 +389,8 @@ class TextEngine:
 
         def wgrad_into(dy16, act16, wview, bview):
             ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=wview, accumulate=True)
-            ops.colsum_bf16(dy16, bview)
+            if bview is not None:       # None: already reduced in fp32 by the producing LayerNorm-backward kernel
+                ops.colsum_bf16(dy16, bview)
 
         dX = bufs.get("dX", (M, D), F32, zero=True)      # fp32 gradient w.r.t. the layer output (CLS rows only at first)
         if S["proj"] is not None:
@@ -417,17 +424,17 @@ class TextEngine:
             # x_out = LN(ffn_sum),  ffn_sum = lin2(gelu(lin1(y))) + y
             ops.layernorm_bwd(L["ffn_sum"], L["m2"], L["r2"], p[b + "output_layer_norm.weight"], dy_bf16=dX16,
                               dy_f32=dX, dx=dffn, dx_bf16=dffn16, dgamma=grads[b + "output_layer_norm.weight"],
-                              dbeta=grads[b + "output_layer_norm.bias"])
+                              dbeta=grads[b + "output_layer_norm.bias"], dxsum=grads[b + "ffn.lin2.bias"])
             ops.gemm(dffn16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
-            wgrad_into(dffn16, L["g"], grads[b + "ffn.lin2.weight"], grads[b + "ffn.lin2.bias"])
+            wgrad_into(dffn16, L["g"], grads[b + "ffn.lin2.weight"], None)
             ops.gemm(du, L["w1"], b_major=1, out_bf16=dya)
             wgrad_into(du, L["y16"], grads[b + "ffn.lin1.weight"], grads[b + "ffn.lin1.bias"])
             # y = LN(sa_sum),  sa_sum = out_lin(attn) + x ; dy = dffn (skip) + dya (through lin1)
             ops.layernorm_bwd(L["sa_sum"], L["m1"], L["r1"], p[b + "sa_layer_norm.weight"], dy_bf16=dya, dy_f32=dffn,
                               dx=dsa, dx_bf16=dsa16, dgamma=grads[b + "sa_layer_norm.weight"],
-                              dbeta=grads[b + "sa_layer_norm.bias"])
+                              dbeta=grads[b + "sa_layer_norm.bias"], dxsum=grads[b + "attention.out_lin.bias"])
             ops.gemm(dsa16, L["wo"], b_major=1, out_bf16=dctx)
-            wgrad_into(dsa16, L["ctx"], grads[b + "attention.out_lin.weight"], grads[b + "attention.out_lin.bias"])
+            wgrad_into(dsa16, L["ctx"], grads[b + "attention.out_lin.weight"], None)
             ops.attn_bwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, L["qkv"], L["ctx"], L["lse"], dctx, dqkv, Q_SCALE, None,
                          S["key_mask"])
             ops.gemm(dqkv, L["wqkv"], b_major=1, out_bf16=dxa)

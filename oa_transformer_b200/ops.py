@@ -111,7 +111,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f3
 
 
 def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None, ldx=None, lddyf=None, add1=None,
-                  add2=None, dx=None, dx_bf16=None, lddx=None, lddxb=None, dgamma=None, dbeta=None):
+                  add2=None, dx=None, dx_bf16=None, lddx=None, lddxb=None, dgamma=None, dbeta=None, dxsum=None):
     D = gamma.numel()
     rows = x.shape[0] if rows is None else rows
     ldx = x.stride(0) if ldx is None else ldx
@@ -126,7 +126,7 @@ def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None,
         ptr(add1), ptr(add2), _i64(ldadd),
         ptr(dx), _i64((dx.stride(0) if lddx is None else lddx) if dx is not None else 0),
         ptr(dx_bf16), _i64((dx_bf16.stride(0) if lddxb is None else lddxb) if dx_bf16 is not None else 0),
-        ptr(dgamma), ptr(dbeta), stream_ptr()), "oat_layernorm_bwd")
+        ptr(dgamma), ptr(dbeta), ptr(dxsum), stream_ptr()), "oat_layernorm_bwd")
 
 
 # ------------------------------------------------------------------------------------------------ attention

@@ -47,12 +47,14 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     dx16 = torch.empty(rows, D, device="cuda", dtype=BF)
     dgamma = torch.zeros(D, device="cuda")
     dbeta = torch.zeros(D, device="cuda")
+    dxsum = torch.zeros(D, device="cuda")
     ops.layernorm_bwd(x, mean, rstd, gamma, dy_bf16=dy16, dy_f32=dy32, add1=add1, add2=add2, dx=dx, dx_bf16=dx16,
-                      dgamma=dgamma, dbeta=dbeta)
+                      dgamma=dgamma, dbeta=dbeta, dxsum=dxsum)
     ref.backward(dy16.float() + dy32)
     assert rel(dx, xr.grad + add1 + add2) < 1e-5
     assert rel(dx16.float(), xr.grad + add1 + add2) < 5e-3
     assert rel(dgamma, gr.grad) < 1e-4 and rel(dbeta, br.grad) < 1e-4
+    assert rel(dxsum, dx.sum(0)) < 1e-4
 
 
 def test_layernorm_strided_cls_rows():
