@@ -224,7 +224,8 @@ def main():
     device = torch.device("cuda", local_rank)
     check(lib().oat_device_check(), "oat_device_check")
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     W = max(args.warmup, 3)
     K = args.steps
     B = args.batch_per_gpu
@@ -318,11 +319,14 @@ def main():
     # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)
     roofline = roofline_attn = None
     peaks = load_peaks()
-    if rank == 0 and not args.no_profile:
+    breakdown = None
+    if not args.no_profile:
+        # every rank runs the instrumented step (it contains collectives); only rank 0 keeps the numbers
         ops.PROFILE = []
         step(dev)
-        torch.cuda.synchronize()
+        barrier()
         prof, ops.PROFILE = ops.PROFILE, None
+    if rank == 0 and not args.no_profile:
         agg = {}
         for kind, work, a, b in prof:
             d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
@@ -350,8 +354,6 @@ def main():
                              "tflops": sp["flops"] / (sp["ms"] / 1e3) / 1e12, "traffic": None, "launches": sp["n"],
                              "ms_in_step": sp["ms"]}
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"]} for k, v in agg.items()}
-    else:
-        breakdown = None
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None

@@ -58,6 +58,8 @@ def check(rc, what=""):
 
 def stream_ptr():
     import torch
+    if not torch.cuda.is_available():
+        raise OatError("no CUDA device: the liboat kernels are the only implementation of this path (no CPU fallback)")
     return c_vp(torch.cuda.current_stream().cuda_stream)
 
 

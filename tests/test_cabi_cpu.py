@@ -1,0 +1,107 @@
+"""No-GPU checks of the drop-in boundary: liboat.so builds for sm_100a, loads, exports every symbol that
+include/oat.h declares, reports errors through oat_last_error(), and the product path refuses to run without a GPU
+(no CPU fallback). Also the host-side mirrors of the reference plugin surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from oa_transformer_b200._lib import lib
+    return lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "oat.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oat_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20, names
+    for n in names:
+        assert hasattr(lib, n), "include/oat.h declares %s but liboat.so does not export it" % n
+
+
+def test_version_and_error_channel(lib):
+    assert lib.oat_version() >= 100
+    rc = lib.oat_gemm_bf16(None, None)
+    assert rc == -1
+    assert b"null args" in lib.oat_last_error()
+
+
+def test_no_cpu_fallback(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.oat_device_check() != 0          # no device -> error code, never a silent CPU path
+    from oa_transformer_b200 import ops
+    from oa_transformer_b200._lib import OatError
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    out = torch.zeros(128, 128)
+    with pytest.raises(OatError):
+        ops.gemm(a, a, out_f32=out)
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "oa_transformer_b200", "liboat.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass      # tcgen05.mma, TMA, tcgen05.ld
+    assert "sm_100a" in sass or "sm_100" in sass
+
+
+def test_metrics_match_reference_fixture():
+    from oa_transformer_b200.model.metric import t2v_metrics, v2t_metrics
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "metrics.pt"), map_location="cpu", weights_only=False)
+    for name, c in g.items():
+        t2v, v2t = t2v_metrics(c["sims"].numpy()), v2t_metrics(c["sims"].numpy())
+        for k, v in c["t2v"].items():
+            assert abs(float(t2v[k]) - v) < 1e-9, (name, k)
+        for k, v in c["v2t"].items():
+            assert abs(float(v2t[k]) - v) < 1e-9, (name, k)
+
+
+def test_frozen_in_time_state_dict_contract():
+    """state_dict keys / shapes of SURVEY.md section 8b and the reference's error behaviour."""
+    from oa_transformer_b200.model import FrozenInTime
+    vp = {"model": "SpaceTimeTransformer", "arch_config": "base_patch16_224", "num_frames": 4, "pretrained": True,
+          "time_init": "zeros", "allow_missing_vit": True}
+    tp = {"model": "distilbert-base-uncased", "pretrained": True, "random_init": True}
+    m = FrozenInTime(vp, {"model": "", "input_objects": False}, tp)
+    sd = m.state_dict()
+    assert len(sd) == 327
+    assert tuple(sd["video_model.cls_token"].shape) == (1, 1, 768)
+    assert tuple(sd["video_model.pos_embed"].shape) == (1, 197, 768)
+    assert tuple(sd["video_model.temporal_embed"].shape) == (1, 4, 768)
+    assert tuple(sd["video_model.patch_embed.proj.weight"].shape) == (768, 3, 16, 16)
+    assert tuple(sd["video_model.blocks.11.timeattn.qkv.weight"].shape) == (2304, 768)
+    assert tuple(sd["video_model.blocks.0.mlp.fc1.weight"].shape) == (3072, 768)
+    assert tuple(sd["txt_proj.1.weight"].shape) == (256, 768) and tuple(sd["vid_proj.0.weight"].shape) == (256, 768)
+    # time_init='zeros' (video_transformer.py:89-95)
+    assert float(sd["video_model.blocks.3.timeattn.qkv.weight"].abs().max()) == 0.0
+    assert float(sd["video_model.blocks.3.timeattn.proj.weight"].min()) == 1.0
+    with pytest.raises(NotImplementedError):
+        FrozenInTime(vp, {"model": ""}, dict(tp, pretrained=False))
+    with pytest.raises(NotImplementedError):
+        FrozenInTime(dict(vp, model="resnet"), {"model": ""}, tp)
+    # temporal-embedding inflation on checkpoint load (oa_model.py:148-189)
+    ck = {"video_model.temporal_embed": torch.ones(1, 2, 768), "video_model.pos_embed": sd["video_model.pos_embed"]}
+    out = m._inflate_positional_embeds(dict(ck))
+    assert tuple(out["video_model.temporal_embed"].shape) == (1, 4, 768)
+    assert float(out["video_model.temporal_embed"][:, 2:].abs().max()) == 0.0
+    # object-token variant adds the region embedding of oa_video_transformer_region.py:250
+    mo = FrozenInTime(dict(vp, model="SpaceTimeObjectTransformer"), {"model": "", "input_objects": True}, tp)
+    assert tuple(mo.state_dict()["video_model.object_embed.weight"].shape) == (768, 2054)
