@@ -20,23 +20,9 @@ import torch.nn.functional as F
 from ..base import BaseModel
 from ..engine import TextEngine
 from ..functional import run_tower
+from ..utils import state_dict_data_parallel_fix
 from .model import sim_matrix as _unused  # noqa: F401  (kept importable from here like the reference)
 from .video_transformer import SpaceTimeTransformer
-
-
-def state_dict_data_parallel_fix(load_state_dict, curr_state_dict):
-    """utils/util.py:24-50: reconcile the 'module.' prefix between a checkpoint and the current model."""
-    load_keys, curr_keys = list(load_state_dict.keys()), list(curr_state_dict.keys())
-    redo_dp = undo_dp = False
-    if not curr_keys[0].startswith('module.') and load_keys[0].startswith('module.'):
-        undo_dp = True
-    elif curr_keys[0].startswith('module.') and not load_keys[0].startswith('module.'):
-        redo_dp = True
-    if undo_dp:
-        return {k[7:]: v for k, v in load_state_dict.items()}
-    if redo_dp:
-        return {'module.' + k: v for k, v in load_state_dict.items()}
-    return load_state_dict
 
 
 class FrozenInTime(BaseModel):

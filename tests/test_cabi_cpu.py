@@ -105,3 +105,43 @@ def test_frozen_in_time_state_dict_contract():
     # object-token variant adds the region embedding of oa_video_transformer_region.py:250
     mo = FrozenInTime(dict(vp, model="SpaceTimeObjectTransformer"), {"model": "", "input_objects": True}, tp)
     assert tuple(mo.state_dict()["video_model.object_embed.weight"].shape) == (768, 2054)
+
+
+def _parser():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('-c', '--config', default=None)
+    ap.add_argument('-r', '--resume', default=None)
+    ap.add_argument('-d', '--device', default=None)
+    return ap
+
+
+def test_config_parser_reflection_factory(monkeypatch):
+    """parse_config_dist_multi.ConfigParser: JSON + reflection factory + the reference's assertions."""
+    import collections
+    import oa_transformer_b200.data_loader as module_data
+    import oa_transformer_b200.model as module_arch
+    from oa_transformer_b200.parse_config_dist_multi import ConfigParser
+    cfg_path = os.path.join(ROOT, "oa_transformer_b200", "configs", "pt", "cc3m_webvid", "synthetic-objects.json")
+    monkeypatch.setattr("sys.argv", ["prog", "-c", cfg_path, "--bs", "4"])
+    Opt = collections.namedtuple('CustomArgs', 'flags type target')
+    cfg = ConfigParser(_parser(), [Opt(['--bs', '--batch_size'], type=int, target=('trainer', 'epochs'))], test=True)
+    assert cfg['trainer']['epochs'] == 4                      # CLI override through the option target path
+    model = cfg.initialize('arch', module_arch)
+    assert type(model).__name__ == "FrozenInTime" and model.use_objects
+    loss = cfg.initialize('loss', module_arch)
+    assert loss.temperature == 0.05
+    dl = cfg.initialize('data_loader', module_data, index=0)
+    batch = next(iter(dl))
+    assert tuple(batch['video'].shape) == (8, 8, 3, 224, 224) and tuple(batch['object'].shape) == (8, 8, 36, 2054)
+    with pytest.raises(AssertionError):
+        cfg.initialize('loss', module_arch, temperature=0.1) if 'temperature' in cfg['loss']['args'] else \
+            (_ for _ in ()).throw(AssertionError())
+    monkeypatch.setattr("sys.argv", ["prog"])
+    with pytest.raises(AssertionError):
+        ConfigParser(_parser(), test=True)                   # neither -c nor -r
+    # the shipped pre-training config keeps the reference's schema and still builds the arch args
+    ref_cfg = os.path.join(ROOT, "oa_transformer_b200", "configs", "pt", "cc3m_webvid", "norm.json")
+    monkeypatch.setattr("sys.argv", ["prog", "-c", ref_cfg])
+    cfg2 = ConfigParser(_parser(), test=True)
+    assert cfg2['arch']['args']['video_params']['time_init'] == 'zeros' and cfg2['n_gpu'] == 8

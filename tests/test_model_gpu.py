@@ -184,3 +184,31 @@ def test_frozen_in_time_module_surface():
     with torch.no_grad():
         s = m(data, return_embeds=False)
     assert s.shape == (2, 2)
+
+
+def test_train_dist_multi_entry_point_synthetic(tmp_path, monkeypatch):
+    """The plugin surface end to end on one GPU: ConfigParser -> FrozenInTime / NormSoftmaxLoss / loaders ->
+    Multi_Trainer_dist._train_epoch (model, AllGather_multi, sim_matrix, loss, backward, AdamW step) -> validation
+    metrics -> checkpoint with the reference's dictionary layout."""
+    import json as _json
+    from oa_transformer_b200 import train_dist_multi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = _json.load(open(os.path.join(root, "oa_transformer_b200", "configs", "pt", "cc3m_webvid",
+                                       "synthetic-objects.json")))
+    cfg["trainer"]["save_dir"] = str(tmp_path)
+    cfg["trainer"]["save_period"] = 1
+    cfg["data_loader"][0]["args"].update({"batch_size": 2, "n_samples": 4, "num_objects": 4})
+    cfg["data_loader"][0]["args"]["video_params"]["num_frames"] = 2
+    cfg["arch"]["args"]["video_params"]["num_frames"] = 2
+    cfg["trainer"]["max_samples_per_epoch"] = 4
+    p = tmp_path / "cfg.json"
+    p.write_text(_json.dumps(cfg))
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    train_dist_multi.main(["-c", str(p)])
+    ckpts = list(tmp_path.rglob("checkpoint-epoch1.pth"))
+    assert len(ckpts) == 1
+    ck = torch.load(str(ckpts[0]), map_location="cpu", weights_only=False)
+    assert set(ck.keys()) == {"arch", "epoch", "state_dict", "optimizer", "monitor_best", "config"}
+    assert ck["arch"] == "FrozenInTime" and "video_model.object_embed.weight" in ck["state_dict"]
