@@ -562,6 +562,11 @@ static int launch_bwd(const AttnGeom& G, int groups, cudaStream_t s) {
   return check_launch("attn_bwd_kernel");
 }
 
+// SIMT gather kernels for time attention (attention_time.cu): sequence length F + 1 <= 17
+int launch_time_fwd(const oat_attn_args* a, cudaStream_t s);
+int launch_time_bwd(const oat_attn_args* a, cudaStream_t s);
+constexpr int kTimeSimtMaxF = 16;
+
 }  // namespace oat
 
 extern "C" int oat_attn_fwd(const oat_attn_args* a, oat_stream_t stream) {
@@ -572,10 +577,11 @@ extern "C" int oat_attn_fwd(const oat_attn_args* a, oat_stream_t stream) {
   OAT_REQUIRE(a->qkv != nullptr && a->out != nullptr, "oat_attn_fwd: null qkv/out");
   const AttnGeom G = to_geom(a);
   cudaStream_t s = as_stream(stream);
-  if (rows <= 32) rc = launch_fwd<32, 2>(G, groups, s);
+  if (a->mode == 1 && a->F <= kTimeSimtMaxF) rc = launch_time_fwd(a, s);
+  else if (rows <= 32) rc = launch_fwd<32, 2>(G, groups, s);
   else if (rows <= 64) rc = launch_fwd<64, 4>(G, groups, s);
   else if (rows <= 128) rc = launch_fwd<128, 4>(G, groups, s);
-  else rc = launch_fwd<256, 4>(G, groups, s);
+  else rc = launch_fwd<256, 8>(G, groups, s);
   if (rc != OAT_OK) return rc;
   if (a->mode != 2) {
     const int smem = (((a->T + 3) & ~3) + kClsWarps * 64 + 2 * kClsWarps) * 4;
@@ -605,6 +611,7 @@ extern "C" int oat_attn_bwd(const oat_attn_args* a, oat_stream_t stream) {
   if (a->mode != 2) {
     cudaError_t e = cudaMemsetAsync(a->cls_acc, 0, sizeof(float) * a->B * a->H * 3 * HD, s);
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    if (a->mode == 1 && a->F <= kTimeSimtMaxF) return launch_time_bwd(a, s);
     rows += 1;  // the CLS query row
     if (rows > 256) return set_error(OAT_ERR_ARG, "oat_attn_bwd: group too large for the 256-row tile");
   }
