@@ -149,6 +149,19 @@ int oat_infonce_fwd_bwd(const float* text, const float* video, int32_t n, int32_
                         float* sims_out, float* loss, float* dtext, float* dvideo, void* workspace,
                         size_t workspace_bytes, oat_stream_t stream);
 
+/* ---- object -> patch attention (three score->weight modes) and bbox -> patch masks ---------------------------------
+ * mode 0: weights = masks (B,O,L), out = masks @ v            (oa_model_global_local.py:178)
+ * mode 1: weights = sigmoid(q . k^T)                          (oa_model_region_mem.py:147-151)
+ * mode 2: weights = softmax(q . k^T * C^-0.5)                 (Visualization/.../visualize.py:155-168)
+ * q (B,O,C), k (B,L,C), v (B,L,Cv) fp32; weights (B,O,L) and/or out (B,O,Cv) fp32 (either may be NULL).
+ * oat_patch_masks_from_bbox: boxes fp64 [n, stride] (x1,y1,x2,y2 in [0,1]) -> masks fp32 [n, grid*grid], exactly
+ * mask[int(y1*g):ceil(y2*g), int(x1*g):ceil(x2*g)] = 1 of base/base_dataset_global_local.py:348-356 (bit-exact). */
+int oat_object_patch_attn(const float* q, const float* k, const float* v, const float* masks, float* weights,
+                          float* out, int32_t B, int32_t O, int32_t L, int32_t C, int32_t Cv, int32_t mode,
+                          oat_stream_t stream);
+int oat_patch_masks_from_bbox(const double* boxes, int32_t stride, float* masks, int32_t n, int32_t grid,
+                              oat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,8 +5,8 @@
 // A group (b, slot i, head h) has F queries and F + 1 keys of 64 dims: 2-8 FLOP per byte, far too small for 128-row
 // tensor-core tiles, so the goal is to touch every 128-byte head slice once and keep the SM busy:
 //   lane = group_in_warp * Fp + frame   (Fp = F rounded up to a power of two; 32 / Fp groups per warp)
-//   every lane owns one token row (its q / k / v / dO slices live in registers); the other rows of its group are
-//   streamed through L1 (all lanes of a group read the same addresses -> broadcast).
+//   every lane owns one token row and stages that token's head slices into shared memory with cp.async (all loads
+//   of a CTA are in flight at once); the other rows of its group are then read from shared memory (broadcast).
 // Backward computes the (F x (F+1)) probability / dS rows once on the query side, hands them to the key side through
 // shared memory, and reduces the three CLS-row vectors (dQ of the CLS query, dK / dV of the CLS key) with a warp
 // transpose-reduce -> shared memory -> one global atomic per component per CTA.
@@ -16,7 +16,8 @@
 namespace oat {
 
 constexpr int TD = 64;            // head dim
-constexpr int kTimeWarps = 8;
+constexpr int kTimeWarps = 4;     // 128 threads = 128 token rows staged per CTA
+constexpr int TP = 72;            // smem row pitch (bf16): 144 B keeps the per-group broadcast reads conflict-free
 
 struct TimeGeom {
   int B, T, H, F, n, Fp, gpc, chunks;   // gpc: groups per CTA, chunks: CTAs per (b, h)
@@ -123,25 +124,44 @@ __device__ __forceinline__ TimeLane decode_lane(const TimeGeom& G, int lane, int
   return L;
 }
 
+__device__ __forceinline__ void cp_async16_t(void* smem, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_t() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void stage_row(__nv_bfloat16* dst, const __nv_bfloat16* src) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) cp_async16_t(dst + c * 8, src + c * 8);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int KMAX>   // F + 1 <= KMAX
 __global__ void __launch_bounds__(kTimeWarps * 32) attn_time_fwd_kernel(const TimeGeom G) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[kTimeWarps * 32 * TP];
+  __shared__ __align__(16) __nv_bfloat16 Vs[kTimeWarps * 32 * TP];
+  __shared__ __align__(16) __nv_bfloat16 Cs[2 * TP];           // CLS key / value rows of this (b, h)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TimeLane L = decode_lane(G, lane, warp);
-  if (!L.valid) return;
   const int HD3 = G.H * TD;
   const __nv_bfloat16* base = G.qkv + L.row0 * G.ld_qkv + L.h * TD;
+  const long long own = static_cast<long long>(L.valid ? L.tok : 0);
+  stage_row(Ks + threadIdx.x * TP, base + own * G.ld_qkv + HD3);
+  stage_row(Vs + threadIdx.x * TP, base + own * G.ld_qkv + 2 * HD3);
+  if (threadIdx.x < 16) cp_async16_t(Cs + (threadIdx.x >> 3) * TP + (threadIdx.x & 7) * 8,
+                                     base + (1 + (threadIdx.x >> 3)) * HD3 + (threadIdx.x & 7) * 8);
   uint4 raw[8];
   float q[TD];
-  load_row(base + static_cast<long long>(L.tok) * G.ld_qkv, raw);
+  load_row(base + own * G.ld_qkv, raw);
   unpack_row(raw, q);
+  cp_async_wait_all_t();
+  __syncthreads();
+  if (!L.valid) return;
+  const int g0 = threadIdx.x - L.i;          // smem row of frame 0 of this lane's group
   float s[KMAX];
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     if (j <= G.F) {
-      const long long kt = (j == 0) ? 0 : 1 + static_cast<long long>(j - 1) * G.n + L.pos;
-      load_row(base + kt * G.ld_qkv + HD3, raw);
+      load_row(j == 0 ? Cs : Ks + (g0 + j - 1) * TP, raw);
       s[j] = dot_row(q, raw);
       m = fmaxf(m, s[j]);
     } else {
@@ -161,8 +181,7 @@ __global__ void __launch_bounds__(kTimeWarps * 32) attn_time_fwd_kernel(const Ti
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     if (j <= G.F) {
-      const long long kt = (j == 0) ? 0 : 1 + static_cast<long long>(j - 1) * G.n + L.pos;
-      load_row(base + kt * G.ld_qkv + 2 * HD3, raw);
+      load_row(j == 0 ? Cs + TP : Vs + (g0 + j - 1) * TP, raw);
       axpy_row(bf16_round(s[j] * inv), raw, o);
     }
   }
@@ -188,13 +207,17 @@ __device__ __forceinline__ float dot_packed(const uint4 (&x)[8], const uint4 (&y
 
 template <int KMAX>
 __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const TimeGeom G) {
-  extern __shared__ float sm_time[];
-  // per warp: P[lane = query row][key] and dS likewise
-  float* sP = sm_time + (threadIdx.x >> 5) * (2 * 32 * KMAX);
+  extern __shared__ __align__(16) uint8_t sm_time_raw[];
+  constexpr int kRows = kTimeWarps * 32;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_time_raw);     // [kRows][TP] each
+  __nv_bfloat16* Ks = Qs + kRows * TP;
+  __nv_bfloat16* Vs = Ks + kRows * TP;
+  __nv_bfloat16* Ds = Vs + kRows * TP;                                     // dO
+  __nv_bfloat16* Cs = Ds + kRows * TP;                                     // CLS rows: q, k, v, dO, O  [5][TP]
+  float* sm_f = reinterpret_cast<float*>(Cs + 5 * TP);
+  float* sP = sm_f + (threadIdx.x >> 5) * (2 * 32 * KMAX);                 // per warp: P[lane][key], dS likewise
   float* sDS = sP + 32 * KMAX;
-  float* sAcc = sm_time + kTimeWarps * (2 * 32 * KMAX);   // [3][64] CTA-level accumulators for the CLS rows
-  for (int t = threadIdx.x; t < 3 * TD; t += blockDim.x) sAcc[t] = 0.f;
-  __syncthreads();
+  float* sAcc = sm_f + kTimeWarps * (2 * 32 * KMAX);                       // [3][64] CTA accumulators for the CLS rows
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TimeLane L = decode_lane(G, lane, warp);
@@ -205,67 +228,76 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
   const float* lrow = G.lse + (static_cast<long long>(L.b) * G.H + L.h) * G.T;
   const long long own = static_cast<long long>(L.valid ? L.tok : 0);
 
+  // stage this lane's token (q, k, v, dO) and the CLS rows; every load of the CTA is in flight at once
+  stage_row(Qs + threadIdx.x * TP, base + own * G.ld_qkv);
+  stage_row(Ks + threadIdx.x * TP, base + own * G.ld_qkv + HD3);
+  stage_row(Vs + threadIdx.x * TP, base + own * G.ld_qkv + 2 * HD3);
+  stage_row(Ds + threadIdx.x * TP, dbase + own * G.ld_dout);
+  if (threadIdx.x < 40) {
+    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+    const __nv_bfloat16* src = r < 3 ? base + r * HD3 : (r == 3 ? dbase : obase);
+    cp_async16_t(Cs + r * TP + c * 8, src + c * 8);
+  }
+  for (int t = threadIdx.x; t < 3 * TD; t += blockDim.x) sAcc[t] = 0.f;
   uint4 raw[8];
   float a[TD];                 // fp32 row whose role changes per phase
-  float p[KMAX], ds[KMAX];     // row i of P and (first) dP, then dS
+  float p[KMAX], ds[KMAX];
+  load_row(obase + own * G.ld_out, raw);                   // own O row (only needed for delta): straight from HBM
+  const float lse = lrow[own];
+  cp_async_wait_all_t();
+  __syncthreads();
+  const int g0 = threadIdx.x - L.i;                        // smem row of frame 0 of this lane's group
 
   // ================= query side: row i of P / dS, dQ_i, shares of dK_cls / dV_cls =================
-  // phase 1a: s_ij = q_i . k_j
-  load_row(base + own * G.ld_qkv, raw);
-  unpack_row(raw, a);                                      // a = q_i
-  const float lse = lrow[own];
+  {
+    uint4 dor[8];
+    load_row(Ds + threadIdx.x * TP, dor);
+    unpack_row(dor, a);                                    // a = dO_i
+  }
+  const float delta = dot_row(a, raw);
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) {
-    p[j] = 0.f;
+  for (int j = 0; j < KMAX; ++j) {                         // dP_ij - delta_i = dO_i . v_j - delta_i
+    ds[j] = 0.f;
     if (j <= G.F) {
-      const long long kt = (j == 0) ? 0 : 1 + static_cast<long long>(j - 1) * G.n + L.pos;
-      load_row(base + (L.valid ? kt : 0) * G.ld_qkv + HD3, raw);
-      p[j] = L.valid ? __expf(dot_row(a, raw) - lse) : 0.f;
+      load_row(j == 0 ? Cs + 2 * TP : Vs + (g0 + j - 1) * TP, raw);
+      ds[j] = dot_row(a, raw) - delta;
     }
   }
   {
-    // dK_cls += dS_i0 * q_i needs dS first; keep q_i's contribution for later by computing P_i0-independent part now:
-    // (done after phase 1b, q_i is reloaded there)
-  }
-  // phase 1b: dP_ij = dO_i . v_j, delta_i = dO_i . O_i, dS = P (dP - delta)
-  load_row(dbase + own * G.ld_dout, raw);
-  unpack_row(raw, a);                                      // a = dO_i
-  load_row(obase + own * G.ld_out, raw);
-  const float delta = dot_row(a, raw);
+    // P_i0 first (q_i . k_cls), so that dO_i can be consumed in place: dV_cls share = P_i0 * dO_i
+    uint4 qr[8];
+    load_row(Qs + threadIdx.x * TP, qr);
+    load_row(Cs + TP, raw);
+    const float p0 = L.valid ? bf16_round(__expf(dot_packed(qr, raw) - lse)) : 0.f;
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) {
-    ds[j] = 0.f;
+    for (int d = 0; d < TD; ++d) a[d] *= p0;
+    warp_transpose_reduce(a, lane);
+    atomicAdd(&sAcc[2 * TD + 2 * lane], a[0]); atomicAdd(&sAcc[2 * TD + 2 * lane + 1], a[1]);
+  }
+  load_row(Qs + threadIdx.x * TP, raw);
+  unpack_row(raw, a);                                      // a = q_i
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {                         // P_ij = exp(q_i . k_j - lse_i), dS = P (dP - delta)
+    p[j] = 0.f;
     if (j <= G.F) {
-      const long long kt = (j == 0) ? 0 : 1 + static_cast<long long>(j - 1) * G.n + L.pos;
-      load_row(base + (L.valid ? kt : 0) * G.ld_qkv + 2 * HD3, raw);
-      ds[j] = p[j] * (dot_row(a, raw) - delta);
+      load_row(j == 0 ? Cs + TP : Ks + (g0 + j - 1) * TP, raw);
+      p[j] = L.valid ? __expf(dot_row(a, raw) - lse) : 0.f;
     }
+    ds[j] *= p[j];
     sP[lane * KMAX + j] = p[j];
     sDS[lane * KMAX + j] = ds[j];
   }
-  {
-    // CLS key (j = 0): dV_cls += P_i0 * dO_i (a = dO_i), then dK_cls += dS_i0 * q_i (q_i reloaded)
-    float v[TD];
-    const float p0 = bf16_round(p[0]);
 #pragma unroll
-    for (int d = 0; d < TD; ++d) v[d] = p0 * a[d];
-    warp_transpose_reduce(v, lane);
-    atomicAdd(&sAcc[2 * TD + 2 * lane], v[0]); atomicAdd(&sAcc[2 * TD + 2 * lane + 1], v[1]);
-    load_row(base + own * G.ld_qkv, raw);
-    unpack_row(raw, v);
-#pragma unroll
-    for (int d = 0; d < TD; ++d) v[d] *= ds[0];
-    warp_transpose_reduce(v, lane);
-    atomicAdd(&sAcc[TD + 2 * lane], v[0]); atomicAdd(&sAcc[TD + 2 * lane + 1], v[1]);
-  }
-  // phase 2: dQ_i = sum_j dS_ij k_j
+  for (int d = 0; d < TD; ++d) a[d] *= ds[0];              // dK_cls share = dS_i0 * q_i (in place)
+  warp_transpose_reduce(a, lane);
+  atomicAdd(&sAcc[TD + 2 * lane], a[0]); atomicAdd(&sAcc[TD + 2 * lane + 1], a[1]);
+  // dQ_i = sum_j dS_ij k_j
 #pragma unroll
   for (int d = 0; d < TD; ++d) a[d] = 0.f;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     if (j <= G.F) {
-      const long long kt = (j == 0) ? 0 : 1 + static_cast<long long>(j - 1) * G.n + L.pos;
-      load_row(base + (L.valid ? kt : 0) * G.ld_qkv + HD3, raw);
+      load_row(j == 0 ? Cs + TP : Ks + (g0 + j - 1) * TP, raw);
       axpy_row(ds[j], raw, a);
     }
   }
@@ -273,17 +305,16 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
   __syncwarp();
 
   // ================= key side: this lane's token as key j = i + 1 =================
-  // CLS query against this key: scalars first
   float pc = 0.f, dsc = 0.f;
   {
     uint4 kv[8];
-    load_row(base + own * G.ld_qkv + HD3, kv);             // k_own
-    load_row(base, raw);                                   // q_cls
+    load_row(Ks + threadIdx.x * TP, kv);                   // k_own
+    load_row(Cs, raw);                                     // q_cls
     const float sc = dot_packed(kv, raw);
-    load_row(base + own * G.ld_qkv + 2 * HD3, kv);         // v_own
-    load_row(dbase, raw);                                  // dO_cls
+    load_row(Vs + threadIdx.x * TP, kv);                   // v_own
+    load_row(Cs + 3 * TP, raw);                            // dO_cls
     const float dp = dot_packed(kv, raw);
-    load_row(obase, kv);                                   // O_cls
+    load_row(Cs + 4 * TP, kv);                             // O_cls
     const float delta_c = dot_packed(raw, kv);
     if (L.valid) {
       pc = __expf(sc - lrow[0]);
@@ -297,12 +328,11 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
 #pragma unroll
   for (int i = 0; i < KMAX - 1; ++i) {
     if (i < G.F) {
-      const long long qt = 1 + static_cast<long long>(i) * G.n + L.pos;
-      load_row(base + (L.valid ? qt : 0) * G.ld_qkv, raw);
-      axpy_row(L.valid ? sDS[(L.gl * G.Fp + i) * KMAX + jk] : 0.f, raw, a);
+      load_row(Qs + (g0 + i) * TP, raw);
+      axpy_row(L.valid ? sDS[(lane - L.i + i) * KMAX + jk] : 0.f, raw, a);
     }
   }
-  load_row(base, raw);
+  load_row(Cs, raw);
   axpy_row(dsc, raw, a);
   if (L.valid) store_row_bf16(G.dqkv + (L.row0 + L.tok) * G.ld_dqkv + HD3 + L.h * TD, a, 1.f);
   // dV_j = sum_i P_ij dO_i + P_cj dO_cls   (P rounded to bf16 like the forward's P.V operand)
@@ -311,16 +341,15 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
 #pragma unroll
   for (int i = 0; i < KMAX - 1; ++i) {
     if (i < G.F) {
-      const long long qt = 1 + static_cast<long long>(i) * G.n + L.pos;
-      load_row(dbase + (L.valid ? qt : 0) * G.ld_dout, raw);
-      axpy_row(L.valid ? bf16_round(sP[(L.gl * G.Fp + i) * KMAX + jk]) : 0.f, raw, a);
+      load_row(Ds + (g0 + i) * TP, raw);
+      axpy_row(L.valid ? bf16_round(sP[(lane - L.i + i) * KMAX + jk]) : 0.f, raw, a);
     }
   }
-  load_row(dbase, raw);
+  load_row(Cs + 3 * TP, raw);
   axpy_row(bf16_round(pc), raw, a);
   if (L.valid) store_row_bf16(G.dqkv + (L.row0 + L.tok) * G.ld_dqkv + 2 * HD3 + L.h * TD, a, 1.f);
   // dQ_cls share = dS_cj * k_j
-  load_row(base + own * G.ld_qkv + HD3, raw);
+  load_row(Ks + threadIdx.x * TP, raw);
   unpack_row(raw, a);
 #pragma unroll
   for (int d = 0; d < TD; ++d) a[d] *= dsc;
@@ -385,7 +414,16 @@ int launch_time_fwd(const oat_attn_args* a, cudaStream_t s) {
 int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   const TimeGeom G = make_time_geom(a);
   const int grid = a->B * a->H * G.chunks;
-  auto smem_for = [](int kmax) { return static_cast<int>((kTimeWarps * 2 * 32 * kmax + 3 * TD) * sizeof(float)); };
+  auto smem_for = [](int kmax) {
+    return static_cast<int>((4 * kTimeWarps * 32 + 5) * TP * 2 + (kTimeWarps * 2 * 32 * kmax + 3 * TD) * sizeof(float));
+  };
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(attn_time_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(5));
+    cudaFuncSetAttribute(attn_time_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(9));
+    cudaFuncSetAttribute(attn_time_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(17));
+    attr_done = true;
+  }
   if (a->F + 1 <= 5) attn_time_bwd_kernel<5><<<grid, kTimeWarps * 32, smem_for(5), s>>>(G);
   else if (a->F + 1 <= 9) attn_time_bwd_kernel<9><<<grid, kTimeWarps * 32, smem_for(9), s>>>(G);
   else attn_time_bwd_kernel<17><<<grid, kTimeWarps * 32, smem_for(17), s>>>(G);

@@ -303,3 +303,39 @@ def norm_softmax_loss(sims, temperature, loss, dsims):
     _count(2)
     check(lib().oat_norm_softmax_loss(ptr(sims), _i32(n), _i64(sims.stride(0)), _f32(temperature), ptr(loss),
                                       ptr(dsims), ptr(scratch), stream_ptr()), "oat_norm_softmax_loss")
+
+
+# ------------------------------------------------------------------------------------------------ object -> patch
+XATTN_MASK, XATTN_SIGMOID, XATTN_SOFTMAX = 0, 1, 2
+
+
+def object_patch_attention(q, k, v=None, mode="softmax", masks=None, want_weights=True):
+    """One op, three score->weight modes. q (B,O,C), k (B,L,C), v (B,L,Cv), masks (B,O,L): fp32 CUDA.
+    Returns (weights (B,O,L) or None, out (B,O,Cv) or None)."""
+    m = {"mask": XATTN_MASK, "sigmoid": XATTN_SIGMOID, "softmax": XATTN_SOFTMAX}[mode]
+    ref = masks if m == XATTN_MASK else q
+    B, O = ref.shape[0], ref.shape[1]
+    L = masks.shape[2] if m == XATTN_MASK else k.shape[1]
+    C = 0 if m == XATTN_MASK else q.shape[2]
+    dev = ref.device
+    for t in (q, k, v, masks):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    weights = torch.empty(B, O, L, dtype=torch.float32, device=dev) if want_weights else None
+    out = torch.empty(B, O, v.shape[2], dtype=torch.float32, device=dev) if v is not None else None
+    _count(1)
+    check(lib().oat_object_patch_attn(ptr(q), ptr(k), ptr(v), ptr(masks), ptr(weights), ptr(out), _i32(B), _i32(O),
+                                      _i32(L), _i32(C), _i32(v.shape[2] if v is not None else 0), _i32(m),
+                                      stream_ptr()), "oat_object_patch_attn")
+    return weights, out
+
+
+def patch_masks_from_bbox(boxes, patch_rows=14):
+    """boxes: fp64 CUDA tensor [n, >=4] with (x1, y1, x2, y2) in [0,1] -> fp32 masks [n, patch_rows^2] (bit-exact
+    with base/base_dataset_global_local.py:348-356)."""
+    assert boxes.dtype == torch.float64 and boxes.dim() == 2 and boxes.is_contiguous()
+    n = boxes.shape[0]
+    masks = torch.empty(n, patch_rows * patch_rows, dtype=torch.float32, device=boxes.device)
+    _count(1)
+    check(lib().oat_patch_masks_from_bbox(ptr(boxes), _i32(boxes.shape[1]), ptr(masks), _i32(n), _i32(patch_rows),
+                                          stream_ptr()), "oat_patch_masks_from_bbox")
+    return masks

@@ -224,3 +224,30 @@ def test_infonce_against_reference_golden():
         assert float((sims.cpu() - c["sims"]).abs().max()) < 2e-5, name     # what the split-bf16 GEMM actually gives
         assert abs(float(loss) - float(c["loss"])) < 1e-4 * max(1.0, abs(float(c["loss"]))), name
         assert rel(dt.cpu(), c["ga"]) < 1e-3 and rel(dv.cpu(), c["gb"]) < 1e-3, (name, rel(dt.cpu(), c["ga"]))
+
+
+# ------------------------------------------------------------------------------------------------ object -> patch (X4)
+def test_patch_masks_bit_exact_vs_reference_fixture():
+    from oa_transformer_b200 import ops
+    g = torch.load(os.path.join(GOLD, "patch_masks.pt"), map_location="cpu", weights_only=False)
+    masks = ops.patch_masks_from_bbox(g["boxes"].cuda().contiguous())
+    assert torch.equal(masks.cpu().double(), g["masks"])
+
+
+@pytest.mark.parametrize("mode,C,Ob", [("softmax", 256, 5), ("sigmoid", 256, 5), ("softmax", 768, 36), ("mask", 768, 20)])
+def test_object_patch_attention_modes(mode, C, Ob):
+    from oa_transformer_b200 import ops
+    g = gen(11)
+    B, L = 3, 196
+    q = torch.randn(B, Ob, C, generator=g) * 0.3
+    k = torch.randn(B, L, C, generator=g) * 0.3
+    v = torch.randn(B, L, C, generator=g)
+    masks = None
+    if mode == "mask":
+        boxes = O.synth_objects(B, 1, Ob, g)[:, 0, :, 2048:2052].reshape(-1, 4).double()
+        masks = torch.from_numpy(O.patch_masks_from_bbox(boxes.numpy())).float().view(B, Ob, L)
+    w_ref, o_ref = O.object_patch_attention(q, k, v, mode, masks)
+    w, o = ops.object_patch_attention(None if mode == "mask" else q.cuda(), None if mode == "mask" else k.cuda(),
+                                      v.cuda(), mode, None if masks is None else masks.cuda().contiguous())
+    assert rel(w.cpu(), w_ref) < 1e-5
+    assert rel(o.cpu(), o_ref) < 1e-5
