@@ -206,14 +206,13 @@ __device__ __forceinline__ float dot_packed(const uint4 (&x)[8], const uint4 (&y
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const TimeGeom G) {
+__global__ void __launch_bounds__(kTimeWarps * 32, 4) attn_time_bwd_kernel(const TimeGeom G) {
   extern __shared__ __align__(16) uint8_t sm_time_raw[];
   constexpr int kRows = kTimeWarps * 32;
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_time_raw);     // [kRows][TP] each
-  __nv_bfloat16* Ks = Qs + kRows * TP;
-  __nv_bfloat16* Vs = Ks + kRows * TP;
-  __nv_bfloat16* Ds = Vs + kRows * TP;                                     // dO
-  __nv_bfloat16* Cs = Ds + kRows * TP;                                     // CLS rows: q, k, v, dO, O  [5][TP]
+  // two row buffers, used twice: (K, V) for the query side, then (Q, dO) for the key side
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(sm_time_raw);     // [kRows][TP]
+  __nv_bfloat16* Ys = Xs + kRows * TP;
+  __nv_bfloat16* Cs = Ys + kRows * TP;                                     // CLS rows: q, k, v, dO, O  [5][TP]
   float* sm_f = reinterpret_cast<float*>(Cs + 5 * TP);
   float* sP = sm_f + (threadIdx.x >> 5) * (2 * 32 * KMAX);                 // per warp: P[lane][key], dS likewise
   float* sDS = sP + 32 * KMAX;
@@ -228,11 +227,9 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
   const float* lrow = G.lse + (static_cast<long long>(L.b) * G.H + L.h) * G.T;
   const long long own = static_cast<long long>(L.valid ? L.tok : 0);
 
-  // stage this lane's token (q, k, v, dO) and the CLS rows; every load of the CTA is in flight at once
-  stage_row(Qs + threadIdx.x * TP, base + own * G.ld_qkv);
-  stage_row(Ks + threadIdx.x * TP, base + own * G.ld_qkv + HD3);
-  stage_row(Vs + threadIdx.x * TP, base + own * G.ld_qkv + 2 * HD3);
-  stage_row(Ds + threadIdx.x * TP, dbase + own * G.ld_dout);
+  // stage K, V rows of this CTA's 128 tokens and the CLS rows; every load of the CTA is in flight at once
+  stage_row(Xs + threadIdx.x * TP, base + own * G.ld_qkv + HD3);
+  stage_row(Ys + threadIdx.x * TP, base + own * G.ld_qkv + 2 * HD3);
   if (threadIdx.x < 40) {
     const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
     const __nv_bfloat16* src = r < 3 ? base + r * HD3 : (r == 3 ? dbase : obase);
@@ -242,31 +239,28 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
   uint4 raw[8];
   float a[TD];                 // fp32 row whose role changes per phase
   float p[KMAX], ds[KMAX];
-  load_row(obase + own * G.ld_out, raw);                   // own O row (only needed for delta): straight from HBM
+  load_row(dbase + own * G.ld_dout, raw);                  // own dO row
+  unpack_row(raw, a);                                      // a = dO_i
+  load_row(obase + own * G.ld_out, raw);                   // own O row (only needed for delta)
+  const float delta = dot_row(a, raw);
   const float lse = lrow[own];
   cp_async_wait_all_t();
   __syncthreads();
   const int g0 = threadIdx.x - L.i;                        // smem row of frame 0 of this lane's group
 
   // ================= query side: row i of P / dS, dQ_i, shares of dK_cls / dV_cls =================
-  {
-    uint4 dor[8];
-    load_row(Ds + threadIdx.x * TP, dor);
-    unpack_row(dor, a);                                    // a = dO_i
-  }
-  const float delta = dot_row(a, raw);
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {                         // dP_ij - delta_i = dO_i . v_j - delta_i
     ds[j] = 0.f;
     if (j <= G.F) {
-      load_row(j == 0 ? Cs + 2 * TP : Vs + (g0 + j - 1) * TP, raw);
+      load_row(j == 0 ? Cs + 2 * TP : Ys + (g0 + j - 1) * TP, raw);
       ds[j] = dot_row(a, raw) - delta;
     }
   }
+  uint4 qr[8];
+  load_row(base + own * G.ld_qkv, qr);                     // own q row
   {
     // P_i0 first (q_i . k_cls), so that dO_i can be consumed in place: dV_cls share = P_i0 * dO_i
-    uint4 qr[8];
-    load_row(Qs + threadIdx.x * TP, qr);
     load_row(Cs + TP, raw);
     const float p0 = L.valid ? bf16_round(__expf(dot_packed(qr, raw) - lse)) : 0.f;
 #pragma unroll
@@ -274,13 +268,12 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
     warp_transpose_reduce(a, lane);
     atomicAdd(&sAcc[2 * TD + 2 * lane], a[0]); atomicAdd(&sAcc[2 * TD + 2 * lane + 1], a[1]);
   }
-  load_row(Qs + threadIdx.x * TP, raw);
-  unpack_row(raw, a);                                      // a = q_i
+  unpack_row(qr, a);                                       // a = q_i
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {                         // P_ij = exp(q_i . k_j - lse_i), dS = P (dP - delta)
     p[j] = 0.f;
     if (j <= G.F) {
-      load_row(j == 0 ? Cs + TP : Ks + (g0 + j - 1) * TP, raw);
+      load_row(j == 0 ? Cs + TP : Xs + (g0 + j - 1) * TP, raw);
       p[j] = L.valid ? __expf(dot_row(a, raw) - lse) : 0.f;
     }
     ds[j] *= p[j];
@@ -297,21 +290,23 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     if (j <= G.F) {
-      load_row(j == 0 ? Cs + TP : Ks + (g0 + j - 1) * TP, raw);
+      load_row(j == 0 ? Cs + TP : Xs + (g0 + j - 1) * TP, raw);
       axpy_row(ds[j], raw, a);
     }
   }
   if (L.valid) store_row_bf16(G.dqkv + (L.row0 + L.tok) * G.ld_dqkv + L.h * TD, a, G.scale);
-  __syncwarp();
+  __syncthreads();                                         // everyone is done with K / V: restage Q and dO
+  stage_row(Xs + threadIdx.x * TP, base + own * G.ld_qkv);
+  stage_row(Ys + threadIdx.x * TP, dbase + own * G.ld_dout);
 
   // ================= key side: this lane's token as key j = i + 1 =================
   float pc = 0.f, dsc = 0.f;
   {
     uint4 kv[8];
-    load_row(Ks + threadIdx.x * TP, kv);                   // k_own
+    load_row(base + own * G.ld_qkv + HD3, kv);             // k_own (L1/L2 hit: staged a moment ago)
     load_row(Cs, raw);                                     // q_cls
     const float sc = dot_packed(kv, raw);
-    load_row(Vs + threadIdx.x * TP, kv);                   // v_own
+    load_row(base + own * G.ld_qkv + 2 * HD3, kv);         // v_own
     load_row(Cs + 3 * TP, raw);                            // dO_cls
     const float dp = dot_packed(kv, raw);
     load_row(Cs + 4 * TP, kv);                             // O_cls
@@ -321,6 +316,8 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
       dsc = pc * (dp - delta_c);
     }
   }
+  cp_async_wait_all_t();
+  __syncthreads();
   const int jk = L.i + 1;
   // dK_j = sum_i dS_ij q_i + dS_cj q_cls
 #pragma unroll
@@ -328,7 +325,7 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
 #pragma unroll
   for (int i = 0; i < KMAX - 1; ++i) {
     if (i < G.F) {
-      load_row(Qs + (g0 + i) * TP, raw);
+      load_row(Xs + (g0 + i) * TP, raw);
       axpy_row(L.valid ? sDS[(lane - L.i + i) * KMAX + jk] : 0.f, raw, a);
     }
   }
@@ -341,7 +338,7 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
 #pragma unroll
   for (int i = 0; i < KMAX - 1; ++i) {
     if (i < G.F) {
-      load_row(Ds + (g0 + i) * TP, raw);
+      load_row(Ys + (g0 + i) * TP, raw);
       axpy_row(L.valid ? bf16_round(sP[(lane - L.i + i) * KMAX + jk]) : 0.f, raw, a);
     }
   }
@@ -349,7 +346,7 @@ __global__ void __launch_bounds__(kTimeWarps * 32, 2) attn_time_bwd_kernel(const
   axpy_row(bf16_round(pc), raw, a);
   if (L.valid) store_row_bf16(G.dqkv + (L.row0 + L.tok) * G.ld_dqkv + 2 * HD3 + L.h * TD, a, 1.f);
   // dQ_cls share = dS_cj * k_j
-  load_row(Ks + threadIdx.x * TP, raw);
+  load_row(base + own * G.ld_qkv + HD3, raw);
   unpack_row(raw, a);
 #pragma unroll
   for (int d = 0; d < TD; ++d) a[d] *= dsc;
@@ -415,7 +412,7 @@ int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   const TimeGeom G = make_time_geom(a);
   const int grid = a->B * a->H * G.chunks;
   auto smem_for = [](int kmax) {
-    return static_cast<int>((4 * kTimeWarps * 32 + 5) * TP * 2 + (kTimeWarps * 2 * 32 * kmax + 3 * TD) * sizeof(float));
+    return static_cast<int>((2 * kTimeWarps * 32 + 5) * TP * 2 + (kTimeWarps * 2 * 32 * kmax + 3 * TD) * sizeof(float));
   };
   static bool attr_done = false;
   if (!attr_done) {
