@@ -566,6 +566,9 @@ static int launch_bwd(const AttnGeom& G, int groups, cudaStream_t s) {
 int launch_time_fwd(const oat_attn_args* a, cudaStream_t s);
 int launch_time_bwd(const oat_attn_args* a, cudaStream_t s);
 constexpr int kTimeSimtMaxF = 16;
+// tcgen05 / TMEM space attention with the CLS query fused (attention_space_tc.cu): 128 <= n <= 255
+bool space_tc_fwd_supported(const oat_attn_args* a);
+int launch_space_tc_fwd(const oat_attn_args* a, cudaStream_t s);
 
 }  // namespace oat
 
@@ -577,6 +580,7 @@ extern "C" int oat_attn_fwd(const oat_attn_args* a, oat_stream_t stream) {
   OAT_REQUIRE(a->qkv != nullptr && a->out != nullptr, "oat_attn_fwd: null qkv/out");
   const AttnGeom G = to_geom(a);
   cudaStream_t s = as_stream(stream);
+  if (space_tc_fwd_supported(a)) return launch_space_tc_fwd(a, s);
   if (a->mode == 1 && a->F <= kTimeSimtMaxF) rc = launch_time_fwd(a, s);
   else if (rows <= 32) rc = launch_fwd<32, 2>(G, groups, s);
   else if (rows <= 64) rc = launch_fwd<64, 4>(G, groups, s);

@@ -1,0 +1,373 @@
+// Space attention forward on the 5th-generation tensor cores (tcgen05 + TMEM), with the global CLS query fused in.
+//
+// Reference: VarAttention.forward, OATrans/model/video_transformer.py:99-135, '(b f) n d' grouping (:112, pattern
+// :275-278): every token of frame f attends to [CLS] + the n tokens of its own frame; the CLS query attends to
+// every key (:108-110). One attention group = (batch b, frame f, head h): n queries, n + 1 keys, head dim 64.
+//
+// Persistent kernel, one CTA per SM, 10 warps:
+//   warp 0      TMA producer: Q / K / V head slices of the group (n rows x 128 B each, straight out of the qkv GEMM
+//               output, 128B-swizzled) into a 2-stage shared-memory ring; the CLS token's q / k / v rows are appended
+//               as row n of each matrix (so the CLS query rides along as one more query row and the CLS key as one
+//               more key - nothing is materialised n times as the reference does at :115-119)
+//   warp 1      tcgen05.mma issuer: S = Q K^T per 128-query tile into TMEM (fp32, N = keys rounded up to 16), then
+//               O = P V with the A operand (P, bf16) read straight from TMEM where the softmax warps left it
+//   warps 2-5   softmax + epilogue of query tile 0 (one thread per query row, TMEM lane = row)
+//   warps 6-9   softmax + epilogue of query tile 1
+// TMEM (512 columns): per tile a 256-column region; S occupies [0, nkp), P overwrites S in place as packed bf16 in
+// [0, nkp/2), O accumulates in [128, 192) once S is dead. The whole key row of a query lives in TMEM, so the softmax is
+// exact two-pass (row max, then exp / sum) - no online rescaling. While one tile is in softmax the tensor core works on
+// the other tile / the next group.
+//
+// The CLS query (row n of tile 1) produces one partial (max, sum, unnormalised O) per (b, h, f); a small combine
+// kernel merges the F partials (the CLS key is counted by frame 0 only).
+#include <cuda.h>
+
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box1);
+
+namespace {
+
+constexpr int SD = 64;                         // head dim
+constexpr int kSpThreads = 320;
+constexpr int kTileBytes = 128 * 128;          // 128 rows x 128 B
+constexpr int kMatBytes = 256 * 128;           // up to 256 rows of one operand
+constexpr int kStageBytes = 3 * kMatBytes;     // Q | K | V
+constexpr int kSpSmem = 2 * kStageBytes + 1024 + 256;
+constexpr int kClsPart = 2 + SD;               // (max2, sum, o[64]) per (b, h, f)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct SpaceGeom {
+  int B, T, H, F, n, nk, nkp, groups;
+  long long ld_qkv, ld_out;
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* out;
+  float* lse;
+  float* cls_part;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ld32_wait(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld_32x32b_x32(taddr, v);
+  tmem_ld_wait();
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kSpThreads, 1)
+attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGeom G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
+  uint64_t* full = bars;           // [2] producer -> MMA
+  uint64_t* empty = bars + 2;      // [2] MMA + 8 softmax warps -> producer
+  uint64_t* s_full = bars + 4;     // [2] MMA -> softmax (S tile ready)
+  uint64_t* p_full = bars + 6;     // [2] softmax -> MMA (P in TMEM)
+  uint64_t* o_full = bars + 8;     // [2] MMA -> softmax (O ready)
+  uint64_t* buf_free = bars + 10;  // [2] softmax -> MMA (TMEM region drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HDIM = G.H * SD;
+
+  // operand rows that no load ever writes (key rows nk..nkp, query rows n+1..255) must be finite: zero everything once
+  for (int i = tid; i < 2 * kStageBytes / 16; i += kSpThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) tma_prefetch_desc(&tmap);
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 2);
+      mbar_init(&empty[i], 9);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&buf_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const int row0 = b * G.T + 1 + f * G.n;
+      uint8_t* qs = smem + s * kStageBytes;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[s], 3u * G.n * 128u);
+        tma_load_2d(qs, &tmap, &full[s], h * SD, row0);
+        tma_load_2d(qs + kMatBytes, &tmap, &full[s], HDIM + h * SD, row0);
+        tma_load_2d(qs + 2 * kMatBytes, &tmap, &full[s], 2 * HDIM + h * SD, row0);
+      }
+      if (lane < 24) {
+        // the CLS token's q / k / v head slices become row n of each operand (same 128B swizzle as the TMA rows)
+        const int m = lane >> 3, c = lane & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv +
+                                                          m * HDIM + h * SD + c * 8);
+        *reinterpret_cast<uint4*>(qs + m * kMatBytes + G.n * 128 + ((c ^ (G.n & 7)) << 4)) = val;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (lane 0 issues everything)
+    const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(G.nkp), 0u, 0u);
+    const uint32_t idesc_o = make_idesc_bf16(128, SD, 0u, 1u);   // B = V is MN-major ([key][d], d contiguous)
+    const int ksteps = G.nkp >> 4;
+    auto issue_pv = [&](int j, uint32_t v_addr, uint32_t par, int release_stage) {
+      mbar_wait(&p_full[j], par);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + j * 256 + 128;
+        const uint32_t a_tmem = tmem_base + j * 256;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t bdesc = make_smem_desc_sw128(v_addr + ks * 2048, kMatBytes, 1024);
+          tc_mma_bf16_ts(d_tmem, a_tmem + ks * 8, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&o_full[j]);
+        if (release_stage >= 0) tc_commit(&empty[release_stage]);
+      }
+      __syncwarp();
+    };
+    uint32_t prev_v = 0;
+    int prev_stage = -1;
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1, par = i & 1;
+      const uint32_t q_addr = smem_u32(smem + s * kStageBytes);
+      const uint32_t k_addr = q_addr + kMatBytes, v_addr = k_addr + kMatBytes;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        mbar_wait(&buf_free[j], par ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(q_addr + j * kTileBytes + k * 32, 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(k_addr + k * 32, 0, 1024);
+            tc_mma_bf16(tmem_base + j * 256, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&s_full[j]);
+        }
+        __syncwarp();
+        if (j == 0) {
+          if (i > 0) issue_pv(1, prev_v, (i - 1) & 1, prev_stage);
+        } else {
+          issue_pv(0, v_addr, par, -1);
+        }
+      }
+      prev_v = v_addr;
+      prev_stage = s;
+    }
+    if (i > 0) issue_pv(1, prev_v, (i - 1) & 1, prev_stage);
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue, one thread per query row
+    const int j = (warp - 2) >> 2;             // query tile = TMEM region
+    const int q = warp & 3;                    // TMEM lane quarter this warp may address
+    const int r_tile = q * 32 + lane;
+    const int r = j * 128 + r_tile;            // query index inside the group; r == n is the CLS query
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 256;
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int s = i & 1;
+      const uint32_t par = i & 1;
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      // keys: [frame tokens 0..n-1, CLS]; the CLS query counts the CLS key in frame 0 only
+      const int limit = (r == G.n && f != 0) ? G.n : G.nk;
+      mbar_wait(&s_full[j], par);
+      tc_fence_after();
+      uint32_t v[32];
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        ld32_wait(t_row + c * 32, v);
+        if (c < NCH - 1) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c * 32 + e < limit) ? __uint_as_float(v[e]) : -INFINITY);
+        }
+      }
+      const float m2 = mx * kLog2e;
+      // pass 2: p = 2^(s*log2e - m2), row sum, P (bf16) back into TMEM over the S columns already consumed
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        ld32_wait(t_row + c * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), kLog2e, -m2));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), kLog2e, -m2));
+          if (c == NCH - 1) {
+            if (c * 32 + e >= limit) p0 = 0.f;
+            if (c * 32 + e + 1 >= limit) p1 = 0.f;
+          }
+          sum += p0 + p1;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(t_row + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j]);
+
+      // epilogue: O (unnormalised) out of TMEM, then hand the region back to the MMA warp
+      mbar_wait(&o_full[j], par);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      ld32_wait(t_row + 128, o0);
+      ld32_wait(t_row + 160, o1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_free[j]);
+
+      if (r == G.n) {
+        float* pp = G.cls_part + ((static_cast<long long>(b) * G.H + h) * G.F + f) * kClsPart;
+        pp[0] = m2;
+        pp[1] = sum;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          pp[2 + d] = __uint_as_float(o0[d]);
+          pp[34 + d] = __uint_as_float(o1[d]);
+        }
+      }
+      const float inv = 1.0f / sum;
+      // stage this row as bf16 in the (dead) Q tile of the stage, then write whole 128-byte rows coalesced
+      uint8_t* stg = smem + s * kStageBytes + j * kTileBytes;
+      {
+        uint8_t* rowp = stg + r_tile * 128;
+        const int sw = r_tile & 7;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o0[8 * c + 0]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = w;
+          w.x = pack_bf16x2(__uint_as_float(o1[8 * c + 0]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ sw) << 4)) = w;
+        }
+      }
+      __syncwarp();
+      const long long tok0 = static_cast<long long>(b) * G.T + 1 + f * G.n;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
+        if (j * 128 + rr < G.n) {
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+          *reinterpret_cast<uint4*>(G.out + (tok0 + j * 128 + rr) * G.ld_out + h * SD + ch * 8) = w;
+        }
+      }
+      if (r < G.n && G.lse != nullptr)
+        G.lse[(static_cast<long long>(b) * G.H + h) * G.T + 1 + f * G.n + r] = (m2 + log2f(sum)) * kLn2;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// merge the F per-frame partials of the CLS query: out row 0 of every (b, h)
+__global__ void __launch_bounds__(SD) attn_cls_combine_kernel(const SpaceGeom G) {
+  const int bh = blockIdx.x, b = bh / G.H, h = bh % G.H, d = threadIdx.x;
+  const float* part = G.cls_part + static_cast<long long>(bh) * G.F * kClsPart;
+  float M = -INFINITY;
+  for (int f = 0; f < G.F; ++f) M = fmaxf(M, part[f * kClsPart]);
+  float L = 0.f, o = 0.f;
+  for (int f = 0; f < G.F; ++f) {
+    const float w = exp2f(part[f * kClsPart] - M);
+    L = fmaf(part[f * kClsPart + 1], w, L);
+    o = fmaf(part[f * kClsPart + 2 + d], w, o);
+  }
+  G.out[static_cast<long long>(b) * G.T * G.ld_out + h * SD + d] = __float2bfloat16_rn(o / L);
+  if (d == 0 && G.lse != nullptr) G.lse[static_cast<long long>(bh) * G.T] = (M + log2f(L)) * kLn2;
+}
+
+template <int NCH>
+int launch_space_tc(const CUtensorMap& tm, const SpaceGeom& G, cudaStream_t s) {
+  auto kern = attn_space_tc_fwd_kernel<NCH>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc smem attr: %s", cudaGetErrorString(e));
+    done = true;
+  }
+  const int sms = num_sms();
+  const int grid = G.groups < sms ? G.groups : sms;
+  kern<<<grid, kSpThreads, kSpSmem, s>>>(tm, G);
+  return check_launch("attn_space_tc_fwd_kernel");
+}
+
+}  // namespace
+
+bool space_tc_fwd_supported(const oat_attn_args* a) {
+  return a->mode == 0 && a->key_mask == nullptr && a->cls_acc != nullptr && a->n >= 128 && a->n + 1 <= 256 &&
+         a->ld_qkv % 8 == 0 && a->ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
+}
+
+// cls_acc must hold B*H*F*66 floats (forward workspace for the CLS-query partials)
+int launch_space_tc_fwd(const oat_attn_args* a, cudaStream_t s) {
+  SpaceGeom G;
+  G.B = a->B; G.T = a->T; G.H = a->H; G.F = a->F; G.n = a->n;
+  G.nk = a->n + 1;
+  G.nkp = (G.nk + 15) & ~15;
+  G.groups = a->B * a->F * a->H;
+  G.ld_qkv = a->ld_qkv; G.ld_out = a->ld_out;
+  G.qkv = reinterpret_cast<const __nv_bfloat16*>(a->qkv);
+  G.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  G.lse = a->lse;
+  G.cls_part = a->cls_acc;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, a->n);
+  if (rc != OAT_OK) return rc;
+  const int nch = (G.nkp + 31) / 32;
+  switch (nch) {
+    case 5: rc = launch_space_tc<5>(tm, G, s); break;
+    case 6: rc = launch_space_tc<6>(tm, G, s); break;
+    case 7: rc = launch_space_tc<7>(tm, G, s); break;
+    case 8: rc = launch_space_tc<8>(tm, G, s); break;
+    default: return set_error(OAT_ERR_ARG, "attn_space_tc: unsupported key count %d", G.nk);
+  }
+  if (rc != OAT_OK) return rc;
+  attn_cls_combine_kernel<<<a->B * a->H, SD, 0, s>>>(G);
+  return check_launch("attn_cls_combine_kernel");
+}
+
+}  // namespace oat

@@ -75,14 +75,15 @@ def _qkv(B, T, H, seed, scale=1.0):
     return q.to(BF)
 
 
-def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None):
+def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None, fwd_ws=True):
     from oa_transformer_b200 import ops
     T = qkv16.shape[1]
     qkv = qkv16.reshape(B * T, 3 * H * 64).cuda()
     out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
     lse = torch.zeros(B * H * T, device="cuda")
     km = key_mask.to(torch.int32).cuda().contiguous() if key_mask is not None else None
-    ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse, km)
+    ws = torch.empty(max(1, ops.attn_fwd_workspace_floats(mode, B, H, F)), device="cuda") if fwd_ws else None
+    ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse, km, cls_ws=ws)
     dqkv = torch.zeros_like(qkv)
     acc = torch.empty(B * H * 3 * 64, device="cuda") if mode != ops.MODE_PLAIN else None
     ops.attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout16.reshape(B * T, H * 64).cuda(), dqkv, 0.125, acc, km)
@@ -113,6 +114,33 @@ def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     # the CLS row on its own (cross-group atomics path)
     assert rel(dqkv[:, 0], gref[:, 0]) < 6e-3, rel(dqkv[:, 0], gref[:, 0])
     assert rel(out[:, 0], ref.detach()[:, 0]) < 4e-3
+
+
+@pytest.mark.parametrize("B,F,n,H", [(1, 1, 232, 1), (4, 4, 232, 12), (2, 3, 196, 5), (1, 2, 128, 2), (1, 2, 255, 3),
+                                     (1, 3, 160, 2)])
+def test_space_attention_tcgen05_fwd(B, F, n, H):
+    """tcgen05/TMEM space kernel (CLS query fused) vs the oracle and vs the mma.sync kernel it replaces; more groups than
+    SMs in one case so the persistent 2-stage ring wraps."""
+    from oa_transformer_b200 import ops
+    T = 1 + F * n
+    qkv16 = _qkv(B, T, H, 11, scale=1.5)
+    qkv = qkv16.reshape(B * T, 3 * H * 64).cuda()
+    outs = []
+    for use_ws in (True, False):
+        out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
+        lse = torch.zeros(B * H * T, device="cuda")
+        ws = torch.empty(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda") if use_ws else None
+        ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
+        torch.cuda.synchronize()
+        outs.append((out.cpu().float().view(B, T, H * 64), lse.cpu().view(B, H, T)))
+    cfg = O.OracleCfg(heads=H, bf16=True)
+    q, k, v = (qkv16.float()[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = O.divided_attention_core(q, k, v, "space", F, n, cfg)
+    (o_tc, l_tc), (o_old, l_old) = outs
+    assert rel(o_tc, ref) < 4e-3, rel(o_tc, ref)
+    assert rel(o_tc[:, 0], ref[:, 0]) < 4e-3, rel(o_tc[:, 0], ref[:, 0])
+    assert rel(o_tc, o_old) < 4e-3
+    assert (l_tc - l_old).abs().max() < 2e-3, (l_tc - l_old).abs().max()
 
 
 @pytest.mark.parametrize("B,L,H", [(3, 32, 12), (2, 8, 2), (2, 50, 2)])
