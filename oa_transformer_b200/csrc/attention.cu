@@ -15,6 +15,8 @@
 //
 // The per-group work is HBM/latency-bound for time attention (sequence length F+1) and small-tile tensor work for
 // space attention; the tcgen05/TMEM variant of the space kernel is the next step.
+#include <stdlib.h>
+
 #include "oat_host.h"
 #include "oat_ptx.cuh"
 
@@ -569,6 +571,8 @@ constexpr int kTimeSimtMaxF = 16;
 // tcgen05 / TMEM space attention with the CLS query fused (attention_space_tc.cu): 128 <= n <= 255
 bool space_tc_fwd_supported(const oat_attn_args* a);
 int launch_space_tc_fwd(const oat_attn_args* a, cudaStream_t s);
+bool space_tc_bwd_supported(const oat_attn_args* a);
+int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s);
 
 }  // namespace oat
 
@@ -616,6 +620,12 @@ extern "C" int oat_attn_bwd(const oat_attn_args* a, oat_stream_t stream) {
     cudaError_t e = cudaMemsetAsync(a->cls_acc, 0, sizeof(float) * a->B * a->H * 3 * HD, s);
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     if (a->mode == 1 && a->F <= kTimeSimtMaxF) return launch_time_bwd(a, s);
+    if (space_tc_bwd_supported(a) && !a->key_mask && getenv("OAT_SPACE_BWD_LEGACY") == nullptr) {
+      rc = launch_space_tc_bwd(a, s);
+      if (rc != OAT_OK) return rc;
+      attn_cls_finalize_kernel<<<a->B * a->H, 3 * HD, 0, s>>>(G);
+      return check_launch("attn_cls_finalize_kernel");
+    }
     rows += 1;  // the CLS query row
     if (rows > 256) return set_error(OAT_ERR_ARG, "oat_attn_bwd: group too large for the 256-row tile");
   }

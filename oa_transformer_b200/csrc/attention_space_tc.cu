@@ -334,6 +334,390 @@ int launch_space_tc(const CUtensorMap& tm, const SpaceGeom& G, cudaStream_t s) {
   return check_launch("attn_space_tc_fwd_kernel");
 }
 
+
+// =============================================================================================== backward
+// Key-major ("transposed") formulation so that the three gradient contractions whose M dimension is the key index read
+// their A operand without a transpose: per key tile kt (128 keys, TMEM lane = key) and query half qh (128 queries)
+//   S^T  = K[kt] Q[qh]^T            TMEM cols [  0,128)      dP^T = V[kt] dO[qh]^T      TMEM cols [128,256)
+//   math (8 warps, thread = key row, 64 query columns each):  P^T = 2^(S^T log2e - lse2[q]),  dS^T = P^T (dP^T - delta[q])
+//        P^T  -> TMEM (bf16, in place over the S^T columns already consumed)
+//        dS^T -> shared memory, [key][query] rows of 64 queries (128 B), 128B-swizzled: read by the tensor core both as a
+//                K-major A operand (dK) and as an MN-major A operand (dQ)
+//   dV[kt]  += P^T  dO[qh]     (A from TMEM, B = dO rows MN-major)     TMEM cols [256,320)
+//   dK[kt]  += dS^T Q[qh]      (A K-major smem, B = Q rows MN-major)   TMEM cols [320,384)
+//   dQ[qh]  += dS   K[kt]      (A MN-major smem, B = K rows MN-major)  TMEM cols [384,448) / [448,512)
+// The CLS query is query row n, the CLS key is key row n; their gradients are reduced across the F groups of a (b, h)
+// with fp32 atomics into cls_acc (same contract as the mma.sync kernel: dq already scaled). Rows beyond the valid ones
+// are zero in shared memory, so they contribute nothing and need no masking; the only masked cell is the
+// (CLS query, CLS key) pair, which frame 0 alone accounts for.
+struct SpaceBwdGeom {
+  int B, T, H, F, n, groups;
+  long long ld_qkv, ld_out, ld_dout, ld_dqkv;
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  float* cls_acc;
+  float scale;
+};
+
+constexpr int kBwdDsBytes = 2 * kTileBytes;                       // dS^T of one unit: 2 blocks of [128 keys x 64 queries]
+constexpr int kBwdOperandBytes = 4 * kMatBytes;                   // Q | K | V | dO
+constexpr int kBwdSmem = kBwdOperandBytes + kBwdDsBytes + 2 * 256 * 4 + 1024 + 256;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kSpThreads, 1)
+attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                         const SpaceBwdGeom G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + kMatBytes;
+  uint8_t* Vs = smem + 2 * kMatBytes;
+  uint8_t* Ds = smem + 3 * kMatBytes;                 // dO
+  uint8_t* dSs = smem + kBwdOperandBytes;             // dS^T unit buffer / epilogue staging
+  float* lse2_s = reinterpret_cast<float*>(dSs + kBwdDsBytes);   // [256]
+  float* del_s = lse2_s + 256;                                   // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(del_s + 256);
+  uint64_t* full = bars;           // producer -> MMA + math        (per group)
+  uint64_t* empty = bars + 1;      // MMA -> producer               (per group)
+  uint64_t* st_full = bars + 2;    // MMA -> math: S^T, dP^T ready  (per unit)
+  uint64_t* math_done = bars + 3;  // math -> MMA: P^T, dS^T ready  (per unit)
+  uint64_t* acc_full = bars + 4;   // MMA -> math: dV, dK complete  (per key tile)
+  uint64_t* acc_free = bars + 5;   // math -> MMA: dV, dK drained   (per key tile)
+  uint64_t* dq_full = bars + 6;    // MMA -> math: dQ complete      (per group)
+  uint64_t* dq_free = bars + 7;    // math -> MMA: dQ drained       (per group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HDIM = G.H * SD;
+  const int n = G.n;
+
+  for (int i = tid; i < (kBwdOperandBytes + kBwdDsBytes) / 16; i += kSpThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do); }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else if (warp == 1 && lane == 0) {
+    mbar_init(full, 2);
+    mbar_init(empty, 1);
+    mbar_init(st_full, 1);
+    mbar_init(math_done, 8);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 8);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 8);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const int row0 = b * G.T + 1 + f * n;
+      mbar_wait(empty, (i & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full, 4u * n * 128u);
+        tma_load_2d(Qs, &tmap_qkv, full, h * SD, row0);
+        tma_load_2d(Ks, &tmap_qkv, full, HDIM + h * SD, row0);
+        tma_load_2d(Vs, &tmap_qkv, full, 2 * HDIM + h * SD, row0);
+        tma_load_2d(Ds, &tmap_do, full, h * SD, row0);
+      }
+      {
+        // CLS token rows (q, k, v, dO) -> row n of each operand
+        const int m = lane >> 3, c = lane & 7;
+        const __nv_bfloat16* src = (m < 3)
+            ? G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + m * HDIM + h * SD + c * 8
+            : G.dout + static_cast<long long>(b) * G.T * G.ld_dout + h * SD + c * 8;
+        const uint4 val = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>(smem + m * kMatBytes + n * 128 + ((c ^ (n & 7)) << 4)) = val;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_st = make_idesc_bf16(128, 128, 0u, 0u);   // S^T, dP^T: both operands K-major
+    const uint32_t idesc_kn = make_idesc_bf16(128, SD, 0u, 1u);    // dV, dK: A K-major (TMEM / smem), B MN-major
+    const uint32_t idesc_mn = make_idesc_bf16(128, SD, 1u, 1u);    // dQ: A MN-major smem, B MN-major
+    const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), d_addr = smem_u32(Ds);
+    const uint32_t ds_addr = smem_u32(dSs);
+    const uint32_t t_st = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
+                   t_dq = tmem_base + 384;
+    int i = 0;
+    uint32_t unit = 0, ktile = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      mbar_wait(full, i & 1);
+      tc_fence_after();
+      for (int kt = 0; kt < 2; ++kt, ++ktile) {
+        for (int qh = 0; qh < 2; ++qh, ++unit) {
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(t_st, make_smem_desc_sw128(k_addr + kt * kTileBytes + k * 32, 0, 1024),
+                          make_smem_desc_sw128(q_addr + qh * kTileBytes + k * 32, 0, 1024), idesc_st, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(t_dp, make_smem_desc_sw128(v_addr + kt * kTileBytes + k * 32, 0, 1024),
+                          make_smem_desc_sw128(d_addr + qh * kTileBytes + k * 32, 0, 1024), idesc_st, k > 0 ? 1u : 0u);
+            tc_commit(st_full);
+          }
+          __syncwarp();
+          if (qh == 0) {                       // first accumulation into dV / dK of this key tile overwrites them
+            mbar_wait(acc_free, (ktile & 1) ^ 1);
+            if (kt == 0) mbar_wait(dq_free, (i & 1) ^ 1);
+          }
+          mbar_wait(math_done, unit & 1);
+          tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {   // dV += P^T dO : k = 16 queries per step
+              const uint32_t a_t = t_st + (ks < 4 ? ks * 8 : 64 + (ks - 4) * 8);
+              tc_mma_bf16_ts(t_dv, a_t, make_smem_desc_sw128(d_addr + (qh * 128 + ks * 16) * 128, kMatBytes, 1024),
+                             idesc_kn, (qh > 0 || ks > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {   // dK += dS^T Q
+              const uint64_t adesc = make_smem_desc_sw128(ds_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32, 0, 1024);
+              tc_mma_bf16(t_dk, adesc, make_smem_desc_sw128(q_addr + (qh * 128 + ks * 16) * 128, kMatBytes, 1024),
+                          idesc_kn, (qh > 0 || ks > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {   // dQ += dS K : k = 16 keys per step, A = dS^T read MN-major
+              const uint64_t adesc = make_smem_desc_sw128(ds_addr + ks * 2048, kTileBytes, 1024);
+              tc_mma_bf16(t_dq + qh * SD, adesc,
+                          make_smem_desc_sw128(k_addr + (kt * 128 + ks * 16) * 128, kMatBytes, 1024), idesc_mn,
+                          (kt > 0 || ks > 0) ? 1u : 0u);
+            }
+            if (qh == 1) {
+              tc_commit(acc_full);
+              if (kt == 1) { tc_commit(dq_full); tc_commit(empty); }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ math warps
+    const int mw = warp - 2;                  // 0..7
+    const int q4 = warp & 3;                  // TMEM lane quarter
+    const int hh = mw >> 2;                   // which 64-query half of a unit / which accumulator in the epilogues
+    const int r_tile = q4 * 32 + lane;        // key row inside the key tile (math) / row inside the tile (epilogues)
+    const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint32_t t_st = tmem_base + lane_off + hh * 64, t_dp = tmem_base + lane_off + 128 + hh * 64;
+    uint8_t* ds_row = dSs + hh * kTileBytes + r_tile * 128;
+    const int sw = r_tile & 7;
+    uint8_t* stg = dSs + mw * 4096;           // this warp's 32 x 128 B staging rows
+    const int mt = mw * 32 + lane;            // 0..255: query row this thread prepares lse / delta for
+    int i = 0;
+    uint32_t unit = 0, ktile = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const long long tok_base = static_cast<long long>(b) * G.T;
+      const long long tok0 = tok_base + 1 + f * n;
+      mbar_wait(full, i & 1);
+      // ---- delta[q] = dO[q] . O[q], lse2[q] = lse[q] * log2e for the 256 query rows (row n = CLS query)
+      {
+        float dl = 0.f, l2 = 0.f;
+        if (mt <= n) {
+          const long long tok = (mt == n) ? tok_base : tok0 + mt;
+          const __nv_bfloat16* op = G.out + tok * G.ld_out + h * SD;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 o = *reinterpret_cast<const uint4*>(op + c * 8);
+            const uint4 d = *reinterpret_cast<const uint4*>(Ds + mt * 128 + ((c ^ (mt & 7)) << 4));
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 x = unpack_bf16x2(ow[k]), y = unpack_bf16x2(dw[k]);
+              dl = fmaf(x.x, y.x, dl);
+              dl = fmaf(x.y, y.y, dl);
+            }
+          }
+          l2 = G.lse[(static_cast<long long>(b) * G.H + h) * G.T + (tok - tok_base)] * kLog2e;
+        }
+        del_s[mt] = dl;
+        lse2_s[mt] = l2;
+      }
+      named_bar_sync(1, 256);
+
+      for (int kt = 0; kt < 2; ++kt, ++ktile) {
+        const int key = kt * 128 + r_tile;
+        // the (CLS query, CLS key) cell is counted by frame 0 only
+        const int kill = (key == n && f != 0) ? n : -1;
+        for (int qh = 0; qh < 2; ++qh, ++unit) {
+          mbar_wait(st_full, unit & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32b_x32(t_st + cc * 32, sv);
+            tmem_ld_32x32b_x32(t_dp + cc * 32, dv);
+            tmem_ld_wait();
+            const int qa0 = qh * 128 + hh * 64 + cc * 32;
+            float pv[32], dsv[32];
+#pragma unroll
+            for (int e4 = 0; e4 < 32; e4 += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + qa0 + e4);
+              const float4 d4 = *reinterpret_cast<const float4*>(del_s + qa0 + e4);
+              const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float p = ex2_approx(fmaf(__uint_as_float(sv[e4 + k]), kLog2e, -ls[k]));
+                pv[e4 + k] = p;
+                dsv[e4 + k] = p * (__uint_as_float(dv[e4 + k]) - dl[k]);
+              }
+            }
+            if (kill >= qa0 && kill < qa0 + 32) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (qa0 + e == kill) { pv[e] = 0.f; dsv[e] = 0.f; }
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
+            tmem_st_32x32b_x16(t_st + cc * 16, pk);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint4 w;
+              w.x = pack_bf16x2(dsv[8 * c4 + 0], dsv[8 * c4 + 1]);
+              w.y = pack_bf16x2(dsv[8 * c4 + 2], dsv[8 * c4 + 3]);
+              w.z = pack_bf16x2(dsv[8 * c4 + 4], dsv[8 * c4 + 5]);
+              w.w = pack_bf16x2(dsv[8 * c4 + 6], dsv[8 * c4 + 7]);
+              *reinterpret_cast<uint4*>(ds_row + (((cc * 4 + c4) ^ sw) << 4)) = w;
+            }
+          }
+          tmem_st_wait();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(math_done);
+        }
+        // ---- dV (hh == 0) / dK (hh == 1) of this key tile: TMEM -> bf16 rows -> global, CLS key row -> atomics
+        mbar_wait(acc_full, ktile & 1);
+        tc_fence_after();
+        {
+          uint32_t a0[32], a1[32];
+          const uint32_t t_acc = tmem_base + lane_off + 256 + hh * 64;
+          tmem_ld_32x32b_x32(t_acc, a0);
+          tmem_ld_32x32b_x32(t_acc + 32, a1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_free);
+          if (key == n && G.cls_acc != nullptr) {
+            float* acc = G.cls_acc + (static_cast<long long>(b) * G.H + h) * 3 * SD + (hh == 0 ? 2 * SD : SD);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+              atomicAdd(acc + d, __uint_as_float(a0[d]));
+              atomicAdd(acc + 32 + d, __uint_as_float(a1[d]));
+            }
+          }
+          uint8_t* rowp = stg + lane * 128;
+          const int s7 = lane & 7;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(a0[8 * c + 0]), __uint_as_float(a0[8 * c + 1]));
+            w.y = pack_bf16x2(__uint_as_float(a0[8 * c + 2]), __uint_as_float(a0[8 * c + 3]));
+            w.z = pack_bf16x2(__uint_as_float(a0[8 * c + 4]), __uint_as_float(a0[8 * c + 5]));
+            w.w = pack_bf16x2(__uint_as_float(a0[8 * c + 6]), __uint_as_float(a0[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + ((c ^ s7) << 4)) = w;
+            w.x = pack_bf16x2(__uint_as_float(a1[8 * c + 0]), __uint_as_float(a1[8 * c + 1]));
+            w.y = pack_bf16x2(__uint_as_float(a1[8 * c + 2]), __uint_as_float(a1[8 * c + 3]));
+            w.z = pack_bf16x2(__uint_as_float(a1[8 * c + 4]), __uint_as_float(a1[8 * c + 5]));
+            w.w = pack_bf16x2(__uint_as_float(a1[8 * c + 6]), __uint_as_float(a1[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ s7) << 4)) = w;
+          }
+          __syncwarp();
+          __nv_bfloat16* dst = G.dqkv + (hh == 0 ? 2 * HDIM : HDIM) + h * SD;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+            const int kj = kt * 128 + q4 * 32 + rr;
+            if (kj < n) {
+              const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              *reinterpret_cast<uint4*>(dst + (tok0 + kj) * G.ld_dqkv + ch * 8) = w;
+            }
+          }
+        }
+        named_bar_sync(1, 256);   // staging rows drained before the next unit's dS^T lands on them
+      }
+      // ---- dQ: tile hh (queries hh*128 ..), scaled; CLS query row -> atomics
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      {
+        uint32_t a0[32], a1[32];
+        const uint32_t t_acc = tmem_base + lane_off + 384 + hh * 64;
+        tmem_ld_32x32b_x32(t_acc, a0);
+        tmem_ld_32x32b_x32(t_acc + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free);
+        const int qrow = hh * 128 + r_tile;
+        if (qrow == n && G.cls_acc != nullptr) {
+          float* acc = G.cls_acc + (static_cast<long long>(b) * G.H + h) * 3 * SD;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) {
+            atomicAdd(acc + d, __uint_as_float(a0[d]) * G.scale);
+            atomicAdd(acc + 32 + d, __uint_as_float(a1[d]) * G.scale);
+          }
+        }
+        uint8_t* rowp = stg + lane * 128;
+        const int s7 = lane & 7;
+        const float sc = G.scale;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(a0[8 * c + 0]) * sc, __uint_as_float(a0[8 * c + 1]) * sc);
+          w.y = pack_bf16x2(__uint_as_float(a0[8 * c + 2]) * sc, __uint_as_float(a0[8 * c + 3]) * sc);
+          w.z = pack_bf16x2(__uint_as_float(a0[8 * c + 4]) * sc, __uint_as_float(a0[8 * c + 5]) * sc);
+          w.w = pack_bf16x2(__uint_as_float(a0[8 * c + 6]) * sc, __uint_as_float(a0[8 * c + 7]) * sc);
+          *reinterpret_cast<uint4*>(rowp + ((c ^ s7) << 4)) = w;
+          w.x = pack_bf16x2(__uint_as_float(a1[8 * c + 0]) * sc, __uint_as_float(a1[8 * c + 1]) * sc);
+          w.y = pack_bf16x2(__uint_as_float(a1[8 * c + 2]) * sc, __uint_as_float(a1[8 * c + 3]) * sc);
+          w.z = pack_bf16x2(__uint_as_float(a1[8 * c + 4]) * sc, __uint_as_float(a1[8 * c + 5]) * sc);
+          w.w = pack_bf16x2(__uint_as_float(a1[8 * c + 6]) * sc, __uint_as_float(a1[8 * c + 7]) * sc);
+          *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ s7) << 4)) = w;
+        }
+        __syncwarp();
+        __nv_bfloat16* dst = G.dqkv + h * SD;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+          const int qj = hh * 128 + q4 * 32 + rr;
+          if (qj < n) {
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            *reinterpret_cast<uint4*>(dst + (tok0 + qj) * G.ld_dqkv + ch * 8) = w;
+          }
+        }
+      }
+      named_bar_sync(1, 256);   // staging drained; also orders this group's lse/delta reads before the next group's writes
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 bool space_tc_fwd_supported(const oat_attn_args* a) {
@@ -368,6 +752,43 @@ int launch_space_tc_fwd(const oat_attn_args* a, cudaStream_t s) {
   if (rc != OAT_OK) return rc;
   attn_cls_combine_kernel<<<a->B * a->H, SD, 0, s>>>(G);
   return check_launch("attn_cls_combine_kernel");
+}
+
+bool space_tc_bwd_supported(const oat_attn_args* a) {
+  return a->mode == 0 && a->key_mask == nullptr && a->cls_acc != nullptr && a->n >= 128 && a->n + 1 <= 256 &&
+         a->ld_qkv % 8 == 0 && a->ld_out % 8 == 0 && a->ld_dout % 8 == 0 && a->ld_dqkv % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a->dout) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dqkv) & 15) == 0;
+}
+
+// cls_acc ([B*H][3][64] fp32) must be zeroed by the caller; the caller also runs the finalize kernel afterwards
+int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
+  SpaceBwdGeom G;
+  G.B = a->B; G.T = a->T; G.H = a->H; G.F = a->F; G.n = a->n;
+  G.groups = a->B * a->F * a->H;
+  G.ld_qkv = a->ld_qkv; G.ld_out = a->ld_out; G.ld_dout = a->ld_dout; G.ld_dqkv = a->ld_dqkv;
+  G.qkv = reinterpret_cast<const __nv_bfloat16*>(a->qkv);
+  G.out = reinterpret_cast<const __nv_bfloat16*>(a->out);
+  G.dout = reinterpret_cast<const __nv_bfloat16*>(a->dout);
+  G.lse = a->lse;
+  G.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
+  G.cls_acc = a->cls_acc;
+  G.scale = a->scale;
+  CUtensorMap tq, td;
+  int rc = make_tmap_bf16_2d(&tq, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, a->n);
+  if (rc != OAT_OK) return rc;
+  rc = make_tmap_bf16_2d(&td, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, a->n);
+  if (rc != OAT_OK) return rc;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_space_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd smem attr: %s", cudaGetErrorString(e));
+    done = true;
+  }
+  const int sms = num_sms();
+  const int grid = G.groups < sms ? G.groups : sms;
+  attn_space_tc_bwd_kernel<<<grid, kSpThreads, kBwdSmem, s>>>(tq, td, G);
+  return check_launch("attn_space_tc_bwd_kernel");
 }
 
 }  // namespace oat

@@ -40,3 +40,34 @@ if os.environ.get("ATT_TIME"):
     t_tc = timeit(lambda: ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws))
     by, fl = ops.attn_core_work(ops.MODE_SPACE, B, T, H, F, n)
     print(json.dumps({"old_ms": t_old, "tc_ms": t_tc, "tc_TFLOPs": fl / t_tc / 1e9, "tc_GBps": by / t_tc / 1e6}))
+
+# ---- backward: tcgen05 kernel vs the mma.sync kernel (OAT_SPACE_BWD_LEGACY=1)
+out = torch.zeros(M, H * 64, device="cuda", dtype=BF); lse = torch.zeros(B * H * T, device="cuda")
+ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda")
+ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
+dout = torch.randn(M, H * 64, device="cuda").to(BF)
+acc = torch.empty(B * H * 192, device="cuda")
+gr = {}
+for name in ("old", "tc"):
+    if name == "old":
+        os.environ["OAT_SPACE_BWD_LEGACY"] = "1"
+    else:
+        os.environ.pop("OAT_SPACE_BWD_LEGACY", None)
+    dqkv = torch.zeros_like(qkv)
+    ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc)
+    torch.cuda.synchronize()
+    gr[name] = dqkv.float().view(B, T, 3, H * 64)
+d = (gr["old"] - gr["tc"]).abs()
+rep = {"nan": bool(torch.isnan(gr["tc"]).any())}
+for i, nm in enumerate("qkv"):
+    rep["d%s_max_err" % nm] = float(d[:, 1:, i].max()); rep["d%s_ref_max" % nm] = float(gr["old"][:, 1:, i].abs().max())
+    rep["d%s_cls_err" % nm] = float(d[:, 0, i].max()); rep["d%s_cls_ref" % nm] = float(gr["old"][:, 0, i].abs().max())
+    rep["d%s_rel" % nm] = float((gr["old"][:, :, i] - gr["tc"][:, :, i]).norm() / gr["old"][:, :, i].norm())
+print(json.dumps(rep))
+if os.environ.get("ATT_TIME"):
+    dqkv = torch.zeros_like(qkv)
+    os.environ["OAT_SPACE_BWD_LEGACY"] = "1"
+    t_old = timeit(lambda: ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc))
+    os.environ.pop("OAT_SPACE_BWD_LEGACY", None)
+    t_tc = timeit(lambda: ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc))
+    print(json.dumps({"bwd_old_ms": t_old, "bwd_tc_ms": t_tc, "bwd_tc_TFLOPs_5mm": 2.5 * fl / t_tc / 1e9}))

@@ -93,7 +93,8 @@ def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None, fwd_ws=True):
 
 @pytest.mark.parametrize("mode,B,F,n,H", [("space", 2, 2, 16, 2), ("time", 2, 2, 16, 2), ("space", 2, 3, 232, 3),
                                           ("time", 1, 8, 40, 2), ("time", 1, 16, 9, 1), ("space", 1, 2, 196, 12),
-                                          ("time", 1, 4, 232, 12)])
+                                          ("time", 1, 4, 232, 12), ("space", 4, 4, 232, 12), ("space", 1, 2, 128, 2),
+                                          ("space", 1, 3, 255, 2)])
 def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     from oa_transformer_b200 import ops
     T = 1 + F * n
