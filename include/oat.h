@@ -86,7 +86,10 @@ int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float* dy_f32, i
  * mode 2 "plain": every token attends to every key with key_mask[b*T+j] != 0 (DistilBERT self-attention).
  * out: bf16 [B*T, H*64]; lse: fp32 [B*H*T] log-sum-exp per query (saved for backward).
  * Backward consumes dout (bf16, same layout as out) and writes dqkv (bf16, same layout as qkv; the q part is the
- * gradient w.r.t. the UNSCALED projection, i.e. multiplied by `scale`). cls_acc: fp32 [B*H*3*64] scratch. */
+ * gradient w.r.t. the UNSCALED projection, i.e. multiplied by `scale`). cls_acc: fp32 [B*H*3*64] scratch.
+ * Forward, modes 0/1: cls_acc may instead point to oat_attn_fwd_workspace_floats() fp32 words of scratch; the CLS
+ * query is then fused into the space / time kernel (per-CTA partials + a combine kernel) instead of a separate pass
+ * over all T keys. */
 typedef struct oat_attn_args {
   int32_t mode, B, T, H, F, n;
   const void* qkv; int64_t ld_qkv;
@@ -98,6 +101,7 @@ typedef struct oat_attn_args {
   float scale;
   float* cls_acc;
 } oat_attn_args;
+size_t oat_attn_fwd_workspace_floats(int32_t mode, int32_t B, int32_t H, int32_t F, int32_t n);
 int oat_attn_fwd(const oat_attn_args* args, oat_stream_t stream);
 int oat_attn_bwd(const oat_attn_args* args, oat_stream_t stream);
 

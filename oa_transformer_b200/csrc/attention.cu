@@ -565,7 +565,8 @@ static int launch_bwd(const AttnGeom& G, int groups, cudaStream_t s) {
 }
 
 // SIMT gather kernels for time attention (attention_time.cu): sequence length F + 1 <= 17
-int launch_time_fwd(const oat_attn_args* a, cudaStream_t s);
+int launch_time_fwd(const oat_attn_args* a, cudaStream_t s, bool* cls_done);
+long long time_fwd_workspace_floats(int B, int H, int F, int n);
 int launch_time_bwd(const oat_attn_args* a, cudaStream_t s);
 constexpr int kTimeSimtMaxF = 16;
 // tcgen05 / TMEM space attention with the CLS query fused (attention_space_tc.cu): 128 <= n <= 255
@@ -576,6 +577,13 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s);
 
 }  // namespace oat
 
+extern "C" size_t oat_attn_fwd_workspace_floats(int32_t mode, int32_t B, int32_t H, int32_t F, int32_t n) {
+  if (B <= 0 || H <= 0 || F <= 0 || n <= 0) return 0;
+  if (mode == 0) return static_cast<size_t>(B) * H * F * 66;
+  if (mode == 1 && F <= oat::kTimeSimtMaxF) return static_cast<size_t>(oat::time_fwd_workspace_floats(B, H, F, n));
+  return 0;
+}
+
 extern "C" int oat_attn_fwd(const oat_attn_args* a, oat_stream_t stream) {
   using namespace oat;
   int rows = 0, groups = 0;
@@ -585,8 +593,11 @@ extern "C" int oat_attn_fwd(const oat_attn_args* a, oat_stream_t stream) {
   const AttnGeom G = to_geom(a);
   cudaStream_t s = as_stream(stream);
   if (space_tc_fwd_supported(a)) return launch_space_tc_fwd(a, s);
-  if (a->mode == 1 && a->F <= kTimeSimtMaxF) rc = launch_time_fwd(a, s);
-  else if (rows <= 32) rc = launch_fwd<32, 2>(G, groups, s);
+  if (a->mode == 1 && a->F <= kTimeSimtMaxF) {
+    bool cls_done = false;
+    rc = launch_time_fwd(a, s, &cls_done);
+    if (rc != OAT_OK || cls_done) return rc;
+  } else if (rows <= 32) rc = launch_fwd<32, 2>(G, groups, s);
   else if (rows <= 64) rc = launch_fwd<64, 4>(G, groups, s);
   else if (rows <= 128) rc = launch_fwd<128, 4>(G, groups, s);
   else rc = launch_fwd<256, 8>(G, groups, s);

@@ -147,8 +147,9 @@ class VideoEngine:
                 ops.gemm(h, wqkv, bias=p[b + aname + ".qkv.bias"], scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
                 a = bufs.get("a%s.%d" % (tag, i), (M, D), BF)
                 lse = bufs.get("lse%s.%d" % (tag, i), (B * H * T,), F32)
-                ws = bufs.get("attn_ws", (max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, Fr)),), F32)
-                ops.attn_fwd(mode, B, T, H, Fr, n, qkv, a, lse, cls_ws=ws if mode == ops.MODE_SPACE else None)
+                ws = bufs.get("attn_ws", (max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, Fr, n),
+                                              ops.attn_fwd_workspace_floats(ops.MODE_TIME, B, H, Fr, n)),), F32)
+                ops.attn_fwd(mode, B, T, H, Fr, n, qkv, a, lse, cls_ws=ws)
                 wproj = _w16(bufs, "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"])
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
                 return wqkv, wproj, qkv, a, lse

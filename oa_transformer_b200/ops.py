@@ -172,9 +172,11 @@ def attn_core_work(mode, B, T, H, F, n):
     return (groups * 128.0 * (2 * nq + 2 * nk), groups * 4.0 * nq * nk * 64)
 
 
-def attn_fwd_workspace_floats(mode, B, H, F):
-    """fp32 workspace the space-attention forward needs for the per-frame partials of the fused CLS query."""
-    return B * H * F * 66 if mode == MODE_SPACE else 0
+def attn_fwd_workspace_floats(mode, B, H, F, n=1):
+    """fp32 words of workspace the space / time forward needs for the partials of the fused CLS query."""
+    f = lib().oat_attn_fwd_workspace_floats
+    f.restype = _sz
+    return int(f(_i32(mode), _i32(B), _i32(H), _i32(F), _i32(n)))
 
 
 def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
@@ -182,7 +184,7 @@ def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
     cls_ws (fp32, attn_fwd_workspace_floats) selects the tcgen05 space kernel with the CLS query fused in."""
     a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
     if cls_ws is not None:
-        assert cls_ws.dtype == torch.float32 and cls_ws.numel() >= attn_fwd_workspace_floats(mode, B, H, F)
+        assert cls_ws.dtype == torch.float32 and cls_ws.numel() >= attn_fwd_workspace_floats(mode, B, H, F, n)
         a.cls_acc = ptr(cls_ws)
     _count(1 if mode == MODE_PLAIN else 2)
     with _Prof("attn_fwd_%d" % mode, attn_core_work(mode, B, T, H, F, n)):

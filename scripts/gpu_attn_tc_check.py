@@ -16,7 +16,7 @@ res = {}
 for name, use in (("old", False), ("tc", True)):
     out = torch.zeros(M, H * 64, device="cuda", dtype=BF)
     lse = torch.zeros(B * H * T, device="cuda")
-    ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda") if use else None
+    ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n), device="cuda") if use else None
     ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
     torch.cuda.synchronize()
     res[name] = (out.float(), lse)
@@ -35,7 +35,7 @@ if os.environ.get("ATT_TIME"):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
     out = torch.zeros(M, H * 64, device="cuda", dtype=BF); lse = torch.zeros(B * H * T, device="cuda")
-    ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda")
+    ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n), device="cuda")
     t_old = timeit(lambda: ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse))
     t_tc = timeit(lambda: ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws))
     by, fl = ops.attn_core_work(ops.MODE_SPACE, B, T, H, F, n)
@@ -43,7 +43,7 @@ if os.environ.get("ATT_TIME"):
 
 # ---- backward: tcgen05 kernel vs the mma.sync kernel (OAT_SPACE_BWD_LEGACY=1)
 out = torch.zeros(M, H * 64, device="cuda", dtype=BF); lse = torch.zeros(B * H * T, device="cuda")
-ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda")
+ws = torch.zeros(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n), device="cuda")
 ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
 dout = torch.randn(M, H * 64, device="cuda").to(BF)
 acc = torch.empty(B * H * 192, device="cuda")

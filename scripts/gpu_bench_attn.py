@@ -14,6 +14,7 @@ lse = torch.empty(B * H * T, device="cuda")
 dout = torch.randn(M, H * 64, device="cuda").to(BF)
 dqkv = torch.empty_like(qkv)
 acc = torch.empty(B * H * 192, device="cuda")
+ws = torch.zeros(max(ops.attn_fwd_workspace_floats(m, B, H, F, n) for m in (ops.MODE_SPACE, ops.MODE_TIME)), device="cuda")
 def timeit(fn, iters=5):
     for _ in range(2): fn()
     torch.cuda.synchronize()
@@ -23,7 +24,7 @@ def timeit(fn, iters=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 for name, mode in (("space", ops.MODE_SPACE), ("time", ops.MODE_TIME)):
-    f = timeit(lambda: ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse))
+    f = timeit(lambda: ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws))
     b = timeit(lambda: ops.attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc))
     by, fl = ops.attn_core_work(mode, B, T, H, F, n)
     print(json.dumps({"mode": name, "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "fwd_GBps": round(by / f / 1e6, 1),

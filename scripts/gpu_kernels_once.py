@@ -45,7 +45,8 @@ dw4 = torch.zeros(4 * D, D, device=dev)
 dw2 = torch.zeros(D, 4 * D, device=dev)
 lse = torch.empty(B * H * T, device=dev)
 acc = torch.empty(B * H * 192, device=dev)
-ws = torch.zeros(max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F)), device=dev)
+ws = torch.zeros(max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n),
+                     ops.attn_fwd_workspace_floats(ops.MODE_TIME, B, H, F, n)), device=dev)
 gamma = torch.ones(D, device=dev)
 beta = torch.zeros(D, device=dev)
 mean = torch.empty(M, device=dev)
@@ -68,7 +69,7 @@ cases = [
     ("gemm_wgrad_fc2", lambda: ops.gemm(x, x4, a_major=1, b_major=1, out_f32=dw2, accumulate=True)),
     ("attn_space_fwd", lambda: ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, x3, o16_1, lse, None, cls_ws=ws)),
     ("attn_space_bwd", lambda: ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, x3, o16_1, lse, x, o16_3, 0.125, acc)),
-    ("attn_time_fwd", lambda: ops.attn_fwd(ops.MODE_TIME, B, T, H, F, n, x3, o16_1, lse)),
+    ("attn_time_fwd", lambda: ops.attn_fwd(ops.MODE_TIME, B, T, H, F, n, x3, o16_1, lse, None, cls_ws=ws)),
     ("attn_time_bwd", lambda: ops.attn_bwd(ops.MODE_TIME, B, T, H, F, n, x3, o16_1, lse, x, o16_3, 0.125, acc)),
     ("layernorm_fwd", lambda: ops.layernorm_fwd(res, gamma, beta, 1e-6, y_bf16=o16_1, mean=mean, rstd=rstd)),
     ("layernorm_bwd", lambda: ops.layernorm_bwd(res, mean, rstd, gamma, dy_bf16=x, add1=o32, dx=dx32, dx_bf16=o16_1,

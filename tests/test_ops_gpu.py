@@ -82,7 +82,7 @@ def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None, fwd_ws=True):
     out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
     lse = torch.zeros(B * H * T, device="cuda")
     km = key_mask.to(torch.int32).cuda().contiguous() if key_mask is not None else None
-    ws = torch.empty(max(1, ops.attn_fwd_workspace_floats(mode, B, H, F)), device="cuda") if fwd_ws else None
+    ws = torch.empty(max(1, ops.attn_fwd_workspace_floats(mode, B, H, F, n)), device="cuda") if fwd_ws else None
     ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse, km, cls_ws=ws)
     dqkv = torch.zeros_like(qkv)
     acc = torch.empty(B * H * 3 * 64, device="cuda") if mode != ops.MODE_PLAIN else None
@@ -94,7 +94,8 @@ def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None, fwd_ws=True):
 @pytest.mark.parametrize("mode,B,F,n,H", [("space", 2, 2, 16, 2), ("time", 2, 2, 16, 2), ("space", 2, 3, 232, 3),
                                           ("time", 1, 8, 40, 2), ("time", 1, 16, 9, 1), ("space", 1, 2, 196, 12),
                                           ("time", 1, 4, 232, 12), ("space", 4, 4, 232, 12), ("space", 1, 2, 128, 2),
-                                          ("space", 1, 3, 255, 2)])
+                                          ("space", 1, 3, 255, 2), ("time", 2, 8, 232, 12), ("time", 1, 6, 19, 2),
+                                          ("time", 3, 4, 7, 1), ("time", 1, 16, 232, 2), ("time", 2, 3, 33, 3)])
 def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     from oa_transformer_b200 import ops
     T = 1 + F * n
@@ -117,6 +118,20 @@ def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     assert rel(out[:, 0], ref.detach()[:, 0]) < 4e-3
 
 
+@pytest.mark.parametrize("B,F,n,H", [(2, 8, 232, 12), (1, 5, 21, 2), (2, 16, 40, 1)])
+def test_time_attention_fused_cls_matches_separate_pass(B, F, n, H):
+    """The CLS query fused into the time kernel (per-warp partials + combine) vs the separate all-keys pass."""
+    from oa_transformer_b200 import ops
+    T = 1 + F * n
+    qkv16 = _qkv(B, T, H, 12, scale=1.5)
+    dout16 = torch.randn(B, T, H * 64, generator=gen(5)).to(BF)
+    o1, g1 = _run_attn(ops.MODE_TIME, B, F, n, H, qkv16, dout16, fwd_ws=True)
+    o2, g2 = _run_attn(ops.MODE_TIME, B, F, n, H, qkv16, dout16, fwd_ws=False)
+    assert torch.equal(o1[:, 1:], o2[:, 1:])
+    assert rel(o1[:, 0], o2[:, 0]) < 4e-3, rel(o1[:, 0], o2[:, 0])
+    assert rel(g1, g2) < 2e-3, rel(g1, g2)
+
+
 @pytest.mark.parametrize("B,F,n,H", [(1, 1, 232, 1), (4, 4, 232, 12), (2, 3, 196, 5), (1, 2, 128, 2), (1, 2, 255, 3),
                                      (1, 3, 160, 2)])
 def test_space_attention_tcgen05_fwd(B, F, n, H):
@@ -130,7 +145,7 @@ def test_space_attention_tcgen05_fwd(B, F, n, H):
     for use_ws in (True, False):
         out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
         lse = torch.zeros(B * H * T, device="cuda")
-        ws = torch.empty(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F), device="cuda") if use_ws else None
+        ws = torch.empty(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n), device="cuda") if use_ws else None
         ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
         torch.cuda.synchronize()
         outs.append((out.cpu().float().view(B, T, H * 64), lse.cpu().view(B, H, T)))
