@@ -322,10 +322,13 @@ def main():
     breakdown = None
     if not args.no_profile:
         # every rank runs the instrumented step (it contains collectives); only rank 0 keeps the numbers
+        from oa_transformer_b200 import engine as _engine
+        side_was, _engine.SIDE_STREAM = _engine.SIDE_STREAM, False   # per-launch durations need serial execution
         ops.PROFILE = []
         step(dev)
         barrier()
         prof, ops.PROFILE = ops.PROFILE, None
+        _engine.SIDE_STREAM = side_was
     if rank == 0 and not args.no_profile:
         agg = {}
         for kind, work, a, b in prof:

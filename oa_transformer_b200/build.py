@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+if os.environ.get("OAT_GEMM_STAGES"):       # experiment knob: TMA ring depth of the GEMM (default 4)
+    NVCC_FLAGS += ["-DOAT_GEMM_STAGES=%d" % int(os.environ["OAT_GEMM_STAGES"])]
 
 
 def _nvcc():

@@ -2,10 +2,14 @@
 //
 //   warp 0      : TMEM allocation, then TMA producer (one elected lane)
 //   warp 1      : mbarrier init, then tcgen05.mma issuer (one elected lane)
-//   warps 2..9  : epilogue (two warps per TMEM lane quarter, alternating 16-column chunks) - tcgen05.ld accumulator
-//                 rows -> per-warp smem transpose (128-bit, conflict-free pitch) -> coalesced global traffic with
-//                 fused bias / q-scale / GELU (+ stored derivative) / fp32 residual / atomic accumulate; residual and
-//                 aux operands of the NEXT chunk are prefetched while the current one is processed
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, alternating column chunks). Specialised epilogues keep
+//                 the accumulator row of a thread in registers (tcgen05.ld 32x32b: lane = row), apply bias / q-scale /
+//                 GELU (+ stored derivative) / x aux / + fp32 residual there, write the row into a 128B-swizzled
+//                 4 KB shared-memory box and hand it to a TMA bulk-tensor STORE (reduce-add for split-K / gradient
+//                 accumulation); residual and aux boxes arrive by TMA load, prefetched one chunk ahead. ~3
+//                 instructions per element, and every global access is a full 128-byte row segment.
+//                 The generic epilogue (any runtime switch of oat_gemm_args, unaligned outputs) transposes through
+//                 shared memory and uses plain vector loads/stores.
 //
 // Operand tiles are staged by TMA into 128B-swizzled shared memory, 4 stages of (128 x 64) + (BLOCK_N x 64) bf16.
 // Either operand may be K-major (contraction dim contiguous in global memory: activations x weights^T) or
@@ -28,7 +32,6 @@ namespace oat {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kChunk = 16;                       // accumulator columns per tcgen05.ld
@@ -70,14 +73,25 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <int BLOCK_N>
+// Epilogue specialisations (compile-time, so the per-element instruction count stays small - the K=768 GEMMs give the
+// epilogue only ~6 k cycles per 128x256 tile): the generic one keeps every runtime switch of oat_gemm_args.
+enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI_MULAUX = 4, EPI_ATOMIC = 5 };
+
+constexpr int kBoxBytes = 32 * 128;              // one epilogue box: 32 rows x 128 B (64 bf16 or 32 fp32 columns)
+
+template <int BLOCK_N, int EPI>
 struct GemmSmem {
+  static constexpr bool kTmaEpi = EPI != EPI_GENERIC;
+  // boxes per epilogue warp: output (+ second output for GELU') (+ residual / aux input)
+  static constexpr int kBoxes = !kTmaEpi ? 0 : (EPI == EPI_BF16 || EPI == EPI_ATOMIC) ? 1 : 2;
+  static constexpr int kEpiBytes = kTmaEpi ? kEpiWarps * kBoxes * kBoxBytes : kEpiWarps * kStagingFloats * 4;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * kStagingFloats * 4;
-  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
+  // the TMA ring takes what the epilogue boxes leave of the 227 KB
+  static constexpr int kStages = (4 * kStageBytes + kEpiBytes + 2048 <= 232448) ? 4 : 3;
+  static constexpr int kBarrierBytes = (2 * kStages + 4 + kEpiWarps) * 8 + 16;
+  static constexpr int kTotal = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
 __device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
@@ -92,27 +106,28 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
-// Epilogue specialisations (compile-time, so the per-element instruction count stays small - the K=768 GEMMs give the
-// epilogue only ~5 us per 128x256 tile): the generic one keeps every runtime switch of oat_gemm_args.
-enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI_MULAUX = 4, EPI_ATOMIC = 5 };
-
+// tmap_o: output box map (bf16 {64,32} or fp32 {32,32}); tmap_x: second output (GELU') or residual / aux input.
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_x,
                  const GemmParams p) {
-  using S = GemmSmem<BLOCK_N>;
+  using S = GemmSmem<BLOCK_N, EPI>;
+  constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                // [kStages][16 KB]
   uint8_t* smem_b = smem + kStages * S::kABytes;          // [kStages][BLOCK_N*128 B]
-  float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
+  uint8_t* epi_smem = smem + kStages * S::kStageBytes;    // boxes (TMA epilogues) or transpose staging (generic)
+  float* staging = reinterpret_cast<float*>(epi_smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + S::kEpiBytes);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * kStages; // [2]        MMA -> epilogue
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]        epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* in_bar = tmem_empty_bar + 2;        // [kEpiWarps] residual / aux box landed (TMA epilogues)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +136,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
+      if constexpr (S::kTmaEpi) tma_prefetch_desc(&tmap_o);
+      if constexpr (S::kTmaEpi && S::kBoxes == 2) tma_prefetch_desc(&tmap_x);
     }
     __syncwarp();
     tmem_alloc<kTmemCols>(tmem_slot);
@@ -133,6 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kEpiWarps);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -214,8 +232,156 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if constexpr (S::kTmaEpi) {
+    // ------------------------------------------------------------------ epilogue warps, TMA boxes
+    // lane = accumulator row (tcgen05.ld 32x32b), CW consecutive columns per chunk in registers. The row is written
+    // into a 128B-swizzled box (16-byte unit j of row r at unit j ^ (r & 7): conflict-free per quarter-warp and
+    // exactly the layout SWIZZLE_128B tensor maps expect) and stored / reduce-added by one TMA instruction.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may address
+    const int half = (warp - 2) >> 2;       // which of the two interleaved chunk streams of that quarter
+    constexpr bool kF32Out = EPI == EPI_F32_RES || EPI == EPI_ATOMIC;
+    constexpr int CW = kF32Out ? 32 : 64;   // columns per 128-byte box row
+    constexpr int kChunksT = BLOCK_N / CW;
+    constexpr bool kHasIn = EPI == EPI_F32_RES || EPI == EPI_MULAUX;
+    uint8_t* box_o = epi_smem + (warp - 2) * (S::kBoxes * kBoxBytes);
+    uint8_t* box_x = box_o + kBoxBytes;     // second output (GELU') or input (residual / aux); only if kBoxes == 2
+    const uint32_t row_sw = static_cast<uint32_t>(lane & 7) << 4;
+    const uint32_t my_o = smem_u32(box_o) + lane * 128;
+    const uint32_t my_x = smem_u32(box_x) + lane * 128;
+    uint64_t* my_in_bar = &in_bar[warp - 2];
+    uint32_t in_count = 0;                  // input boxes consumed so far (mbarrier parity)
+    int local_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
+      const uint32_t acc = local_iter & 1;
+      const uint32_t acc_phase = (local_iter >> 1) & 1;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int col0 = n_blk * BLOCK_N;
+      const bool first_split = (split == 0);
+      const bool use_bias = (EPI == EPI_BF16 || EPI == EPI_F32_RES || EPI == EPI_GELU) && p.bias != nullptr && first_split;
+      const bool use_in = kHasIn && (EPI == EPI_MULAUX || (p.residual != nullptr && first_split));
+      if (use_in && lane == 0) {              // first input box of the tile: in flight while the MMAs finish
+        mbar_arrive_expect_tx(my_in_bar, kBoxBytes);
+        tma_load_2d(box_x, &tmap_x, my_in_bar, col0 + half * CW, row0);
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < kChunksT; c += 2) {
+        const bool last = (c + 2 >= kChunksT);
+        const int col = col0 + c * CW;
+        uint32_t v[CW];
+        {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * CW;
+          tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          if constexpr (CW == 64) tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+        }
+        if (last) {
+          // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        uint4 xin[8];
+        if constexpr (kHasIn) {
+          if (use_in) {
+            mbar_wait(my_in_bar, in_count & 1);
+            ++in_count;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = lds128(my_x + ((static_cast<uint32_t>(j) << 4) ^ row_sw));
+              xin[j] = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+            }
+            __syncwarp();                   // every lane has its row: the box may be refilled
+            if (!last && lane == 0) {
+              mbar_arrive_expect_tx(my_in_bar, kBoxBytes);
+              tma_load_2d(box_x, &tmap_x, my_in_bar, col + 2 * CW, row0);
+            }
+          }
+        }
+        // ---- element-wise part, in registers
+        if (use_bias) {
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+            v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b4.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b4.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b4.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b4.w);
+          }
+        }
+        if constexpr (EPI == EPI_BF16) {
+          if (col < p.scale_cols) {         // q columns (scale_cols is a multiple of 4; usually of CW too)
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+              if (col + j < p.scale_cols) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.scale);
+          }
+        }
+        if constexpr (EPI == EPI_F32_RES) {
+          if (use_in) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + __uint_as_float(xin[j].x));
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + __uint_as_float(xin[j].y));
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + __uint_as_float(xin[j].z));
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + __uint_as_float(xin[j].w));
+            }
+          }
+        }
+        if constexpr (EPI == EPI_MULAUX) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t w[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[8 * j + 2 * k] = __float_as_uint(__uint_as_float(v[8 * j + 2 * k]) * __uint_as_float(w[k] << 16));
+              v[8 * j + 2 * k + 1] = __float_as_uint(__uint_as_float(v[8 * j + 2 * k + 1]) * __uint_as_float(w[k] & 0xffff0000u));
+            }
+          }
+        }
+        // ---- the previous TMA store out of this warp's box(es) must have finished reading them
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        if constexpr (kF32Out) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(my_o + ((static_cast<uint32_t>(j) << 4) ^ row_sw), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if constexpr (EPI == EPI_GELU) {
+          // GELU(erf) and its derivative from one shared exponential; the derivative (bf16) is what backward needs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g[8], d[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gelu_fwd_grad(__uint_as_float(v[8 * j + k]), g[k], d[k]);
+            const uint32_t off = (static_cast<uint32_t>(j) << 4) ^ row_sw;
+            sts128(my_o + off, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+            sts128(my_x + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(my_o + ((static_cast<uint32_t>(j) << 4) ^ row_sw),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+        }
+        fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (EPI == EPI_ATOMIC) tma_reduce_add_2d(&tmap_o, box_o, col, row0);
+          else tma_store_2d(&tmap_o, box_o, col, row0);
+          if constexpr (EPI == EPI_GELU) tma_store_2d(&tmap_x, box_x, col, row0);
+          bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait<0>();          // the boxes must outlive the last store's reads
   } else {
-    // ------------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------------ epilogue warps, generic
     const int q = warp & 3;                 // TMEM lane quarter this warp may address
     const int half = (warp - 2) >> 2;       // which of the two interleaved chunk streams of that quarter
     float* stg = staging + (warp - 2) * kStagingFloats;
@@ -349,22 +515,27 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 tensor, dim0 contiguous (length d0), dim1 with stride ld elements; box = {64, box1}; 128B swizzle.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box1) {
+// 2D tensor, dim0 contiguous (length d0), dim1 with stride ld elements; box = {128 B of dim0, box1}; 128B swizzle.
+static int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box1,
+                        bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(OAT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+  const uint64_t esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * esz) % 16 != 0)
     return set_error(OAT_ERR_ARG, "TMA operand needs 16-byte aligned base and row pitch (ptr=%p ld=%llu)", ptr,
                      (unsigned long long)ld);
   cuuint64_t dims[2] = {d0, d1};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box1};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(OAT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return OAT_OK;
+}
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box1) {
+  return make_tmap_2d(out, ptr, d0, d1, ld, box1, false);
 }
 
 static int pick_split_k(int tiles_mn, int k_blocks, int sms, int requested) {
@@ -384,28 +555,47 @@ static int pick_split_k(int tiles_mn, int k_blocks, int sms, int requested) {
   return best;
 }
 
+static bool tma_ok(const void* ptr, long long ld, int esz) {
+  return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0;
+}
+
+// The specialised (TMA-box) epilogues need 64-column granularity and 16-byte aligned tensors; anything else is generic.
 static int pick_epi(const oat_gemm_args* a) {
-  if (a->alpha != 1.0f) return EPI_GENERIC;
+  if (a->alpha != 1.0f || a->N % 64 != 0) return EPI_GENERIC;
+  if (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15) != 0) return EPI_GENERIC;
   const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
-  if (a->accumulate) return (f32 && !b16 && a->act == 0 && a->bias == nullptr && a->residual == nullptr && a->scale_cols == 0) ? EPI_ATOMIC : EPI_GENERIC;
-  if (a->act == 1) return (b16 && !f32 && a->residual == nullptr && a->scale_cols == 0) ? EPI_GELU : EPI_GENERIC;
-  if (a->act == 2) return (b16 && !f32 && a->residual == nullptr && a->bias == nullptr && a->scale_cols == 0) ? EPI_MULAUX : EPI_GENERIC;
+  const bool f32_ok = tma_ok(a->out_f32, a->ld_f32, 4), b16_ok = tma_ok(a->out_bf16, a->ld_bf16, 2);
+  if (a->accumulate)
+    return (f32_ok && !b16 && a->act == 0 && a->bias == nullptr && a->residual == nullptr && a->scale_cols == 0) ? EPI_ATOMIC : EPI_GENERIC;
+  if (a->act == 1)
+    return (b16_ok && !f32 && a->residual == nullptr && a->scale_cols == 0 && tma_ok(a->out2_bf16, a->ld2, 2)) ? EPI_GELU : EPI_GENERIC;
+  if (a->act == 2)
+    return (b16_ok && !f32 && a->residual == nullptr && a->bias == nullptr && a->scale_cols == 0 && tma_ok(a->aux_bf16, a->ld_aux, 2)) ? EPI_MULAUX : EPI_GENERIC;
   if (a->act != 0) return EPI_GENERIC;
-  if (b16 && !f32 && a->residual == nullptr) return EPI_BF16;
-  if (f32 && !b16 && a->scale_cols == 0) return EPI_F32_RES;
+  if (b16_ok && !f32 && a->residual == nullptr) return EPI_BF16;
+  if (f32_ok && !b16 && a->scale_cols == 0 && (a->residual == nullptr || tma_ok(a->residual, a->ldr, 4))) return EPI_F32_RES;
   return EPI_GENERIC;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N>;
-  CUtensorMap ta, tb;
+  using S = GemmSmem<BLOCK_N, EPI>;
+  CUtensorMap ta, tb, to, tx;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&ta, a->A, a->K, a->M, a->lda, BLOCK_M);
   else rc = make_tmap_bf16_2d(&ta, a->A, a->M, a->K, a->lda, BLOCK_K);
   if (rc != OAT_OK) return rc;
   if (!B_MN) rc = make_tmap_bf16_2d(&tb, a->B, a->K, a->N, a->ldb, BLOCK_N);
   else rc = make_tmap_bf16_2d(&tb, a->B, a->N, a->K, a->ldb, BLOCK_K);
+  if (rc != OAT_OK) return rc;
+  to = ta;
+  tx = ta;
+  if (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_MULAUX) rc = make_tmap_2d(&to, a->out_bf16, a->N, a->M, a->ld_bf16, 32, false);
+  if (EPI == EPI_F32_RES || EPI == EPI_ATOMIC) rc = make_tmap_2d(&to, a->out_f32, a->N, a->M, a->ld_f32, 32, true);
+  if (rc != OAT_OK) return rc;
+  if (EPI == EPI_GELU) rc = make_tmap_2d(&tx, a->out2_bf16, a->N, a->M, a->ld2, 32, false);
+  if (EPI == EPI_MULAUX) rc = make_tmap_2d(&tx, a->aux_bf16, a->N, a->M, a->ld_aux, 32, false);
+  if (EPI == EPI_F32_RES && a->residual != nullptr) rc = make_tmap_2d(&tx, a->residual, a->N, a->M, a->ldr, 32, true);
   if (rc != OAT_OK) return rc;
 
   GemmParams p;
@@ -439,7 +629,7 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   }
   const long long tiles = 1LL * p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, to, tx, p);
   return check_launch("gemm_bf16_kernel");
 }
 

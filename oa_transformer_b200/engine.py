@@ -10,6 +10,8 @@ Arithmetic contract (mirrored by oracle/oracle.py in bf16 mode): GEMM / attentio
 fp32; residual stream, LayerNorm, softmax, logits, loss and every parameter gradient are fp32; activation gradients
 that feed a GEMM are bf16.
 """
+import os
+
 import torch
 
 from . import ops
@@ -20,6 +22,7 @@ HEAD_DIM = 64
 Q_SCALE = HEAD_DIM ** -0.5
 OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py:593-650)
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
+SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 
 
 class _Buffers:
@@ -83,6 +86,7 @@ class VideoEngine:
         self.patch = patch
         self.bufs = _Buffers(device)
         self.saved = None
+        self._side = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
@@ -207,15 +211,37 @@ class VideoEngine:
         prefix = S["prefix"]
         xs, layers = S["xs"], S["layers"]
 
+        # Weight-gradient GEMMs and bias column sums have no consumer inside the backward chain: they run on a second
+        # stream so that the HBM-bound kernels of the chain (LayerNorm backward, attention backward) overlap with them.
+        # Gradient activations they read rotate over two buffer sets (layer parity); the chain waits for the side
+        # stream's layer i+2 before overwriting set i%2.
+        use_side = SIDE_STREAM and torch.cuda.is_available()
+        main = torch.cuda.current_stream(self.device)
+        if use_side:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            side.wait_stream(main)              # gradient book zeroed, forward finished
+        side_done = {}
+
         def wgrad(dy16, act16, name, bias=True):
             # bias=False: the bias gradient was already reduced (fp32) by the LayerNorm-backward kernel that produced dy
-            ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
-                     accumulate=True)
-            if bias:
-                ops.colsum_bf16(dy16, grads[name + ".bias"])
+            def run():
+                ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
+                         accumulate=True)
+                if bias:
+                    ops.colsum_bf16(dy16, grads[name + ".bias"])
+            if not use_side:
+                return run()
+            ev = torch.cuda.Event()
+            ev.record(main)                      # dy16 is complete on the chain
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                run()
 
+        # bf16 d(block output): read by the fc2 weight gradient one layer later, so three buffers rotate
         dy = bufs.get("dy.a", (M, D), F32, zero=True)         # d(block output), non-zero in the CLS rows only
-        dy16 = bufs.get("dy16.a", (M, D), BF, zero=True)
+        dy16 = bufs.get("dy16.%d" % (depth % 3), (M, D), BF, zero=True)
         dcls16 = bufs.get("dcls16", (B, D), BF)
         if S["proj"] is not None:
             wname, bname = S["proj"]
@@ -232,50 +258,59 @@ class VideoEngine:
                           dbeta=grads[prefix + "norm.bias"],
                           dxsum=grads["%sblocks.%d.mlp.fc2.bias" % (prefix, depth - 1)] if depth > 0 else None)
 
-        du = bufs.get("du", (M, 4 * D), BF)
+        nset = 2 if use_side else 1
+        du = [bufs.get("du.%d" % k, (M, 4 * D), BF) for k in range(nset)]
+        dqkv_s = [bufs.get("dqkv_s.%d" % k, (M, 3 * D), BF) for k in range(nset)]
+        dqkv_t = [bufs.get("dqkv_t.%d" % k, (M, 3 * D), BF) for k in range(nset)] if use_side else dqkv_s
+        dsr16 = [bufs.get("dsr16.%d" % k, (M, D), BF) for k in range(nset)]
+        dtr16 = [bufs.get("dtr16.%d" % k, (M, D), BF) for k in range(nset)]
         dh = bufs.get("dh", (M, D), BF)
         da = bufs.get("da", (M, D), BF)
-        dqkv = bufs.get("dqkv", (M, 3 * D), BF)
         dsr = bufs.get("dsr", (M, D), F32)
-        dsr16 = bufs.get("dsr16", (M, D), BF)
         dtr = bufs.get("dtr", (M, D), F32)
-        dtr16 = bufs.get("dtr16", (M, D), BF)
         acc = bufs.get("cls_acc", (B * H * 3 * HEAD_DIM,), F32)
         dyb = bufs.get("dy.b", (M, D), F32)
-        dy16b = bufs.get("dy16.b", (M, D), BF)
 
         for i in reversed(range(depth)):
             b = "%sblocks.%d." % (prefix, i)
             L = layers[i]
+            k = i % nset
+            dy16b = bufs.get("dy16.%d" % (i % 3), (M, D), BF)
+            if use_side and (i + 2) in side_done:
+                main.wait_event(side_done[i + 2])            # buffer set k is free again
             # ---- x_out = sr + fc2(gelu(fc1(norm2(sr))))
-            ops.gemm(dy16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
+            ops.gemm(dy16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du[k])
             wgrad(dy16, L["g"], b + "mlp.fc2", bias=False)
-            ops.gemm(du, L["w1"], b_major=1, out_bf16=dh)
-            wgrad(du, L["h2"], b + "mlp.fc1")
+            ops.gemm(du[k], L["w1"], b_major=1, out_bf16=dh)
+            wgrad(du[k], L["h2"], b + "mlp.fc1")
             ops.layernorm_bwd(L["sr"], L["m2"], L["r2"], p[b + "norm2.weight"], dy_bf16=dh, add1=dy, dx=dsr,
-                              dx_bf16=dsr16, dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"],
+                              dx_bf16=dsr16[k], dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"],
                               dxsum=grads[b + "attn.proj.bias"])
             # ---- sr = x + proj_s(space_attn(qkv_s(norm1(tr))))
-            ops.gemm(dsr16, L["wproj_s"], b_major=1, out_bf16=da)
-            wgrad(dsr16, L["a_s"], b + "attn.proj", bias=False)
-            ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv, Q_SCALE, acc)
-            ops.gemm(dqkv, L["wqkv_s"], b_major=1, out_bf16=dh)
-            wgrad(dqkv, L["h1"], b + "attn.qkv")
-            ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16,
+            ops.gemm(dsr16[k], L["wproj_s"], b_major=1, out_bf16=da)
+            wgrad(dsr16[k], L["a_s"], b + "attn.proj", bias=False)
+            ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv_s[k], Q_SCALE, acc)
+            ops.gemm(dqkv_s[k], L["wqkv_s"], b_major=1, out_bf16=dh)
+            wgrad(dqkv_s[k], L["h1"], b + "attn.qkv")
+            ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16[k],
                               dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"],
                               dxsum=grads[b + "timeattn.proj.bias"])
             # ---- tr = x + proj_t(time_attn(qkv_t(norm3(x))))
-            ops.gemm(dtr16, L["wproj_t"], b_major=1, out_bf16=da)
-            wgrad(dtr16, L["a_t"], b + "timeattn.proj", bias=False)
-            ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv, Q_SCALE, acc)
-            ops.gemm(dqkv, L["wqkv_t"], b_major=1, out_bf16=dh)
-            wgrad(dqkv, L["h3"], b + "timeattn.qkv")
+            ops.gemm(dtr16[k], L["wproj_t"], b_major=1, out_bf16=da)
+            wgrad(dtr16[k], L["a_t"], b + "timeattn.proj", bias=False)
+            ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc)
+            ops.gemm(dqkv_t[k], L["wqkv_t"], b_major=1, out_bf16=dh)
+            wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv")
             # ---- dx = dsr (space skip) + dtr (time skip) + norm3'(dh)
             ops.layernorm_bwd(xs[i], L["m3"], L["r3"], p[b + "norm3.weight"], dy_bf16=dh, add1=dsr, add2=dtr, dx=dyb,
                               dx_bf16=dy16b, dgamma=grads[b + "norm3.weight"], dbeta=grads[b + "norm3.bias"],
                               dxsum=grads["%sblocks.%d.mlp.fc2.bias" % (prefix, i - 1)] if i > 0 else None)
+            if use_side:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                side_done[i] = ev
             dy, dyb = dyb, dy
-            dy16, dy16b = dy16b, dy16
+            dy16 = dy16b
 
         # ---- token assembly / embeddings
         dpatch = bufs.get("dpatch", (B * Fr * N, D), BF)
@@ -290,6 +325,8 @@ class VideoEngine:
             ops.gemm(dobj, S["obj16"], a_major=1, b_major=1, out_f32=dwo, accumulate=True)
             grads[prefix + "object_embed.weight"].copy_(dwo[:, :OBJ_DIM])
             ops.colsum_bf16(dobj, grads[prefix + "object_embed.bias"])
+        if use_side:
+            main.wait_stream(side)
 
 
 # ==================================================================================================== text tower

@@ -99,3 +99,36 @@ def test_gemm_many_tiles_persistent():
     ops.gemm(A, B, out_bf16=out)
     ref = A.float() @ B.float().t()
     assert torch.allclose(out.float(), ref, rtol=1e-2, atol=0.15)
+
+
+@pytest.mark.parametrize("M", [500, 128 * 149 + 33])
+def test_gemm_tma_epilogue_f32_bias_residual(M):
+    """fp32 output = acc + bias + fp32 residual through the TMA-box epilogue (ragged last row block, > 148 tiles)."""
+    from oa_transformer_b200 import ops
+    N, K = 768, 768
+    A, B = _mk((M, K), 21), _mk((N, K), 22)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    out = torch.full((M + 3, N), 7.0, device="cuda")            # rows beyond M must stay untouched
+    ops.gemm(A, B, bias=bias, residual=res, out_f32=out[:M])
+    ref = A.float() @ B.float().t() + bias + res
+    assert torch.allclose(out[:M], ref, rtol=1e-3, atol=2e-3)
+    assert bool((out[M:] == 7.0).all())
+    out2 = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, bias=bias, out_f32=out2)                      # no residual
+    assert torch.allclose(out2, ref - res, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("scale_cols", [768, 68, 0])
+def test_gemm_tma_epilogue_bf16_bias_qscale(scale_cols):
+    from oa_transformer_b200 import ops
+    M, N, K = 1857, 2304, 768
+    A, B = _mk((M, K), 23), _mk((N, K), 24)
+    B = (B.float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    out = torch.full((M + 2, N), 3.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, scale_cols=scale_cols, scale=0.125, out_bf16=out[:M])
+    ref = A.float() @ B.float().t() + bias
+    ref[:, :scale_cols] *= 0.125
+    assert torch.allclose(out[:M].float(), ref, rtol=1e-2, atol=2e-2)
+    assert bool((out[M:].float() == 3.0).all())
