@@ -314,24 +314,121 @@ __global__ void __launch_bounds__(TD) attn_time_cls_combine_kernel(const TimeGeo
   if (d == 0 && G.lse != nullptr) G.lse[static_cast<long long>(bh) * G.T] = M + __logf(L);
 }
 
-// ------------------------------------------------------------------------------------------------ backward
-// Per warp: stage Q, K, V, dO rows (coalesced), O rows straight into registers for delta. Query side: lane = query row
-// (P / dS row, dQ, the CLS-key shares); P and dS go to shared memory (over the V rows, dead by then) for the key side:
-// lane = key row (dK, dV). The CLS query's row of P / dS against this lane's key is recomputed from the staged CLS rows.
-// Gradient rows are written over dead staged rows and stored by the warp as full 128-byte lines.
-template <int KMAX>
+// ------------------------------------------------------------------------------------------------ backward (tensor cores)
+// The SIMT formulation above issues ~6 k instructions per token row in the backward; here the same arithmetic runs on
+// bf16 m16n8k16 MMAs. A warp owns 32 staged token rows = two independent 16-row tiles (groups never straddle a tile:
+// Fp | 16). Per tile the (16 x 16) score block  S = Q K^T  is computed densely and masked to its block diagonal
+// (same group, valid rows), so one code path serves F <= 16. The CLS key is a 17th key column, the CLS query a 17th
+// query row; both are expressed as MMAs against 8-row matrices whose row 0 holds the CLS vector (rows 1-7 zero):
+//   query side   S, dP = dO V^T, s_i0 = q_i.k_cls, dp_i0 = dO_i.v_cls  ->  P = exp(S - lse_i), dS = P (dP - delta_i)
+//                dQ  = dS K  + ds_i0 k_cls
+//   key side     P^T, dS^T by movmatrix;  s_cj = k_j.q_cls, dp_cj = v_j.dO_cls -> P_cj, dS_cj
+//                dK  = dS^T Q + dS_cj q_cls          dV = P^T dO + P_cj dO_cls
+//   CLS rows     dQ_cls += sum_j dS_cj k_j,  dK_cls += sum_i ds_i0 q_i,  dV_cls += sum_i p_i0 dO_i  (row-vector x matrix
+//                MMAs whose A operand has a single non-zero row) -> shared-memory atomics -> one global atomic per CTA.
+// One ldmatrix.x4 of a staged (16 rows x 16 dims) block is both the A fragment of that block and the B fragments of
+// its two 8-row halves, so Q, K, V, dO are read from shared memory once for all score-type products.
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// transpose an 8x8 b16 matrix held one 32-bit register per lane (row = lane / 4, columns 2 * (lane % 4), +1)
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// non-transposed fragments of the (16 rows x 64 dims) tile at staged row R0: f[ks] = {rows 0-7 | dims lo, rows 8-15 | lo,
+// rows 0-7 | hi, rows 8-15 | hi} of k-step ks. As A operand: f[ks]; as B operand of the 8-row half h: (f[ks][h], f[ks][2 + h]).
+__device__ __forceinline__ void load_tile_frags(uint32_t arr, int R0, int lane, uint32_t (&f)[4][4]) {
+  const int row = R0 + (lane & 7) + ((lane & 8) ? 8 : 0);
+  const uint32_t rowaddr = arr + static_cast<uint32_t>(row) * 128u;
+  const uint32_t x = static_cast<uint32_t>(row & 7);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm4(rowaddr + (((2u * ks + (lane >> 4)) ^ x) << 4), f[ks]);
+}
+// B fragments of the 8-row CLS matrix `mat` (row 0 = vector) as an [n = row][k = dim] operand: b[ks][0..1]
+__device__ __forceinline__ void load_cls_frags(uint32_t mat, int lane, uint32_t (&b)[4][2]) {
+  const uint32_t rowaddr = mat + static_cast<uint32_t>(lane & 7) * 128u;
+  const uint32_t x = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t r[4];
+    ldsm4(rowaddr + (((4u * h + (lane >> 3)) ^ x) << 4), r);
+    b[2 * h][0] = r[0]; b[2 * h][1] = r[1]; b[2 * h + 1][0] = r[2]; b[2 * h + 1][1] = r[3];
+  }
+}
+// acc[j] (+)= A . X[k = tile row][n = dims 8j..8j+7]  and  acc2[j] (+)= A2 . X   for the 16-row tile at R0 (transposed loads)
+__device__ __forceinline__ void mma_rows_t(uint32_t arr, int R0, int lane, const uint32_t (&A)[4], float (&acc)[8][4],
+                                           const uint32_t (&A2)[4], float (&acc2)[8][4]) {
+  const int row = R0 + (lane & 7) + ((lane & 8) ? 8 : 0);
+  const uint32_t rowaddr = arr + static_cast<uint32_t>(row) * 128u;
+  const uint32_t x = static_cast<uint32_t>(row & 7);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    uint32_t r[4];
+    ldsm4_t(rowaddr + (((static_cast<uint32_t>(j) + (lane >> 4)) ^ x) << 4), r);
+    mma_bf16(acc[j], A, r[0], r[1]);
+    mma_bf16(acc[j + 1], A, r[2], r[3]);
+    mma_bf16(acc2[j], A2, r[0], r[1]);
+    mma_bf16(acc2[j + 1], A2, r[2], r[3]);
+  }
+}
+// acc[j] += E . C[k = matrix row][n = dims]: rank-1 update with the CLS vector in row 0 of the 8-row matrix (E: column 0)
+__device__ __forceinline__ void mma_cls_t(uint32_t mat, int lane, const uint32_t (&E)[4], float (&acc)[8][4]) {
+  const uint32_t rowaddr = mat + static_cast<uint32_t>(lane & 7) * 128u;
+  const uint32_t x = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; j += 4) {
+    uint32_t r[4];
+    ldsm4_t(rowaddr + (((static_cast<uint32_t>(j) + (lane >> 3)) ^ x) << 4), r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mma_bf16(acc[j + i], E, r[i], 0u);
+  }
+}
+// rows g / g + 8 of the accumulator tile -> bf16 -> staged rows (conflict-free 32-bit stores)
+__device__ __forceinline__ void store_acc_rows(uint8_t* arr, int R0, int lane, const float (&acc)[8][4], float mul) {
+  const int g = lane >> 2, t = lane & 3;
+  const int ra = R0 + g, rb = ra + 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(arr + sw_off(ra, j) + 4 * t) = pack_bf16x2(acc[j][0] * mul, acc[j][1] * mul);
+    *reinterpret_cast<uint32_t*>(arr + sw_off(rb, j) + 4 * t) = pack_bf16x2(acc[j][2] * mul, acc[j][3] * mul);
+  }
+}
+// row 0 of the accumulator tile (lanes 0-3) -> shared accumulators
+__device__ __forceinline__ void add_row0(float* dst, int lane, const float (&acc)[8][4]) {
+  if (lane < 4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dst + 8 * j + 2 * lane, acc[j][0]);
+      atomicAdd(dst + 8 * j + 2 * lane + 1, acc[j][1]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom G) {
   extern __shared__ __align__(128) uint8_t sm_time_raw[];
   uint8_t* Qs = sm_time_raw;
   uint8_t* Ks = Qs + kArr;
   uint8_t* Vs = Ks + kArr;
   uint8_t* Ds = Vs + kArr;                                                  // dO rows
-  uint8_t* Cs = Ds + kArr;                                                  // CLS rows: q, k, v, dO, O  [5][128 B]
-  float* sDelta = reinterpret_cast<float*>(Cs + 5 * 128);                   // [kRows]
-  float* sAcc = sDelta + kRows;                                             // [3][64] CTA accumulators for the CLS rows
+  uint8_t* Cm = Ds + kArr;                                                  // 4 CLS matrices [8][128 B]: q, k, v, dO
+  float* sLse = reinterpret_cast<float*>(Cm + 4 * 1024);                    // [kRows]
+  float* sDelta = sLse + kRows;                                             // [kRows]
+  float* sAcc = sDelta + kRows;                                             // [3][64]: dq_cls, dk_cls, dv_cls
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sP = reinterpret_cast<float*>(Vs + warp * (32 * 128));             // [32][KMAX-1] over this warp's V rows
-  float* sDS = sP + 32 * (KMAX - 1);                                        // (2 * 32 * 16 * 4 B = 4 KB at KMAX = 17)
   const int bh = blockIdx.x / G.chunks, chunk = blockIdx.x - bh * G.chunks;
   const int b = bh / G.H, h = bh - b * G.H;
   const int HD3 = G.H * TD;
@@ -347,36 +444,45 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   stage_rows_warp(Vs, base + 2 * HD3, G.ld_qkv, tok, warp, lane);
   stage_rows_warp(Ks, base + HD3, G.ld_qkv, tok, warp, lane);
   stage_rows_warp(Qs, base, G.ld_qkv, tok, warp, lane);
-  if (threadIdx.x < 40) {
-    const int rr = threadIdx.x >> 3, c = threadIdx.x & 7;
-    const __nv_bfloat16* src = rr < 3 ? base + rr * HD3 : (rr == 3 ? dbase : obase);
-    cp_async16_t(smem_u32(Cs + rr * 128 + c * 16), src + c * 8);
+  {  // CLS matrices: row 0 <- vector, rows 1-7 <- 0
+    const int m = threadIdx.x >> 5, rr = (threadIdx.x >> 3) & 3, c = threadIdx.x & 7;   // 4 matrices x (4 rows x 8 chunks) per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 4 + rr;
+      uint8_t* dst = Cm + m * 1024 + r * 128 + ((c ^ r) << 4);
+      if (r == 0) cp_async16_t(smem_u32(dst), (m < 3 ? base + m * HD3 : dbase) + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
-  for (int t = threadIdx.x; t < 3 * TD; t += kRows) sAcc[t] = 0.f;
-  uint4 raw[8];
+  for (int i = threadIdx.x; i < 3 * TD; i += kRows) sAcc[i] = 0.f;
+  uint4 oraw[8];
   {  // O chunks of the rows this lane helps with (coalesced), for delta = dO . O
     const int c = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      raw[it] = tok[it] >= 0 ? *reinterpret_cast<const uint4*>(obase + static_cast<long long>(tok[it]) * G.ld_out + c * 8)
-                             : make_uint4(0u, 0u, 0u, 0u);
+      oraw[it] = tok[it] >= 0 ? *reinterpret_cast<const uint4*>(obase + static_cast<long long>(tok[it]) * G.ld_out + c * 8)
+                              : make_uint4(0u, 0u, 0u, 0u);
   }
   const int my_tok = row_token(G, chunk, warp, lane);
-  const bool valid = my_tok >= 0;
-  const float lse = valid ? lrow[my_tok] : 0.f;
+  const uint32_t vm = __ballot_sync(0xffffffffu, my_tok >= 0);              // valid rows of this warp
+  sLse[threadIdx.x] = my_tok >= 0 ? lrow[my_tok] : 0.f;
+  // CLS query statistics: lse_c, delta_c = dO_cls . O_cls (lane holds dims 2 * lane, +1)
   const float lse_c = lrow[0];
-  const int r = threadIdx.x;
-  const int fi = lane % G.Fp;                                   // frame index of this lane
-  const int g0 = r - fi;
+  float delta_c;
+  {
+    const float2 dc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dbase + 2 * lane));
+    const float2 oc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(obase + 2 * lane));
+    delta_c = warp_sum(dc.x * oc.x + dc.y * oc.y);
+  }
   cp_async_wait_all_t();
-  __syncthreads();                                              // CLS rows + sAcc zeroing are CTA-wide
+  __syncthreads();                                              // CLS matrices + sAcc zeroing are CTA-wide
   {
     const int c = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = warp * 32 + it * 4 + (lane >> 3);
       const uint4 dv = *reinterpret_cast<const uint4*>(Ds + sw_off(rr, c));
-      const uint32_t x[4] = {dv.x, dv.y, dv.z, dv.w}, y[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
+      const uint32_t x[4] = {dv.x, dv.y, dv.z, dv.w}, y[4] = {oraw[it].x, oraw[it].y, oraw[it].z, oraw[it].w};
       float part = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -390,125 +496,117 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     }
   }
   __syncwarp();
-  const float delta = sDelta[r];
 
-  float a[TD];
-  float p[KMAX], ds[KMAX];
-  // ================= CLS query against this lane's key: P_cj, dS_cj and the dQ_cls share dS_cj * k_j =================
-  float pc = 0.f, dsc = 0.f;
-  {
-    uint4 kv[8];
-    load_row_sw(Ks, r, kv);                                     // k_own
-    load_row_lin(Cs, raw);                                      // q_cls
-    const float sc = dot_packed(kv, raw);
-    unpack_row(kv, a);                                          // a = k_own
-    load_row_sw(Vs, r, kv);                                     // v_own
-    load_row_lin(Cs + 3 * 128, raw);                            // dO_cls
-    const float dp = dot_packed(kv, raw);
-    load_row_lin(Cs + 4 * 128, kv);                             // O_cls
-    const float delta_c = dot_packed(raw, kv);
-    if (valid) {
-      pc = __expf(sc - lse_c);
-      dsc = pc * (dp - delta_c);
-    }
-#pragma unroll
-    for (int d = 0; d < TD; ++d) a[d] *= dsc;
-    const int cb = warp_transpose_reduce(a, lane);
-    atomicAdd(&sAcc[cb], a[0]); atomicAdd(&sAcc[cb + 1], a[1]);
-  }
-  // ================= query side: row i of P / dS, dQ_i, shares of dK_cls / dV_cls =================
-  load_row_sw(Ds, r, raw);
-  unpack_row(raw, a);                                           // a = dO_i
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) {                              // dP_ij - delta_i = dO_i . v_j - delta_i
-    ds[j] = 0.f;
-    if (j <= G.F) {
-      if (j == 0) load_row_lin(Cs + 2 * 128, raw); else load_row_sw(Vs, g0 + j - 1, raw);
-      ds[j] = dot_row(a, raw) - delta;
-    }
-  }
-  uint4 qr[8];
-  load_row_sw(Qs, r, qr);                                       // own q row
-  {
-    // P_i0 first (q_i . k_cls), so that dO_i can be consumed in place: dV_cls share = P_i0 * dO_i
-    load_row_lin(Cs + 128, raw);
-    const float p0 = valid ? bf16_round(__expf(dot_packed(qr, raw) - lse)) : 0.f;
-#pragma unroll
-    for (int d = 0; d < TD; ++d) a[d] *= p0;
-    const int cb = warp_transpose_reduce(a, lane);
-    atomicAdd(&sAcc[2 * TD + cb], a[0]); atomicAdd(&sAcc[2 * TD + cb + 1], a[1]);
-  }
-  unpack_row(qr, a);                                            // a = q_i
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) {                              // P_ij = exp(q_i . k_j - lse_i), dS = P (dP - delta)
-    p[j] = 0.f;
-    if (j <= G.F) {
-      if (j == 0) load_row_lin(Cs + 128, raw); else load_row_sw(Ks, g0 + j - 1, raw);
-      p[j] = valid ? __expf(dot_row(a, raw) - lse) : 0.f;
-    }
-    ds[j] *= p[j];
-  }
-  __syncwarp();                                                 // every lane is done with the V rows: they become P / dS
-#pragma unroll
-  for (int j = 1; j < KMAX; ++j) {
-    sP[lane * (KMAX - 1) + j - 1] = p[j];
-    sDS[lane * (KMAX - 1) + j - 1] = ds[j];
-  }
-#pragma unroll
-  for (int d = 0; d < TD; ++d) a[d] *= ds[0];                   // dK_cls share = dS_i0 * q_i (in place)
-  {
-    const int cb = warp_transpose_reduce(a, lane);
-    atomicAdd(&sAcc[TD + cb], a[0]); atomicAdd(&sAcc[TD + cb + 1], a[1]);
-  }
-  // dQ_i = sum_j dS_ij k_j
-#pragma unroll
-  for (int d = 0; d < TD; ++d) a[d] = 0.f;
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) {
-    if (j <= G.F) {
-      if (j == 0) load_row_lin(Cs + 128, raw); else load_row_sw(Ks, g0 + j - 1, raw);
-      axpy_row(ds[j], raw, a);
-    }
-  }
-  __syncwarp();                                                 // K rows are dead: dQ rows take their place
-  store_row_sw(Ks, r, a, G.scale);
-  __syncwarp();
-  store_rows_warp(Ks, G.dqkv + row0 * G.ld_dqkv + h * TD, G.ld_dqkv, tok, warp, lane);
-  __syncwarp();
+  const uint32_t aQ = smem_u32(Qs), aK = smem_u32(Ks), aV = smem_u32(Vs), aD = smem_u32(Ds);
+  const uint32_t mQ = smem_u32(Cm), mK = mQ + 1024, mV = mQ + 2048, mD = mQ + 3072;
+  const int g = lane >> 2, t = lane & 3;
+  int lg = 0;
+  while ((1 << lg) < G.Fp) ++lg;
+  uint32_t bq[4][2], bk[4][2], bv[4][2], bd[4][2];              // CLS vectors as B operands of the score-type products
+  load_cls_frags(mQ, lane, bq);
+  load_cls_frags(mK, lane, bk);
+  load_cls_frags(mV, lane, bv);
+  load_cls_frags(mD, lane, bd);
 
-  // ================= key side: this lane's token as key j = fi + 1 =================
-  // dK_j = sum_i dS_ij q_i + dS_cj q_cls
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int R0 = warp * 32 + mt * 16;                         // first staged row of the tile
+    const int wr = mt * 16;                                     // same, within the warp (validity mask bits)
+    uint32_t Pa[4], dSa[4], E0[4], Ep[4], Ec[4], Epc[4];
+    {
+      uint32_t fq[4][4], fk[4][4], fv[4][4], fd[4][4];
+      load_tile_frags(aQ, R0, lane, fq);
+      load_tile_frags(aK, R0, lane, fk);
+      load_tile_frags(aV, R0, lane, fv);
+      load_tile_frags(aD, R0, lane, fd);
+      float S[2][4] = {}, dP[2][4] = {}, s0[4] = {}, dp0[4] = {}, sc[4] = {}, dpc[4] = {};
 #pragma unroll
-  for (int d = 0; d < TD; ++d) a[d] = 0.f;
+      for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-  for (int i = 0; i < KMAX - 1; ++i) {
-    if (i < G.F) {
-      load_row_sw(Qs, g0 + i, raw);
-      axpy_row(valid ? sDS[(lane - fi + i) * (KMAX - 1) + fi] : 0.f, raw, a);
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16(S[nt], fq[ks], fk[ks][nt], fk[ks][2 + nt]);
+          mma_bf16(dP[nt], fd[ks], fv[ks][nt], fv[ks][2 + nt]);
+        }
+        mma_bf16(s0, fq[ks], bk[ks][0], bk[ks][1]);            // q_i . k_cls       (column 0)
+        mma_bf16(dp0, fd[ks], bv[ks][0], bv[ks][1]);           // dO_i . v_cls
+        mma_bf16(sc, fk[ks], bq[ks][0], bq[ks][1]);            // k_j . q_cls
+        mma_bf16(dpc, fv[ks], bd[ks][0], bd[ks][1]);           // v_j . dO_cls
+      }
+      // ---- element-wise: rows ra = g, rb = g + 8 of the tile; columns (keys) nt * 8 + 2t + {0, 1}
+      const int ra = wr + g, rb = ra + 8;
+      const bool va = (vm >> ra) & 1u, vb = (vm >> rb) & 1u;
+      const float lse_a = sLse[warp * 32 + ra], lse_b = sLse[warp * 32 + rb];
+      const float del_a = sDelta[warp * 32 + ra], del_b = sDelta[warp * 32 + rb];
+      float P[2][4], dS[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = wr + nt * 8 + 2 * t + e;
+          const bool vk = (vm >> key) & 1u;
+          const bool oka = va && vk && ((ra >> lg) == (key >> lg));
+          const bool okb = vb && vk && ((rb >> lg) == (key >> lg));
+          P[nt][e] = oka ? __expf(S[nt][e] - lse_a) : 0.f;
+          P[nt][2 + e] = okb ? __expf(S[nt][2 + e] - lse_b) : 0.f;
+          dS[nt][e] = P[nt][e] * (dP[nt][e] - del_a);
+          dS[nt][2 + e] = P[nt][2 + e] * (dP[nt][2 + e] - del_b);
+        }
+      }
+      Pa[0] = pack_bf16x2(P[0][0], P[0][1]); Pa[1] = pack_bf16x2(P[0][2], P[0][3]);
+      Pa[2] = pack_bf16x2(P[1][0], P[1][1]); Pa[3] = pack_bf16x2(P[1][2], P[1][3]);
+      dSa[0] = pack_bf16x2(dS[0][0], dS[0][1]); dSa[1] = pack_bf16x2(dS[0][2], dS[0][3]);
+      dSa[2] = pack_bf16x2(dS[1][0], dS[1][1]); dSa[3] = pack_bf16x2(dS[1][2], dS[1][3]);
+      // CLS key column (valid in the t == 0 lanes: column 0 of the MMA tile) and CLS query row (same lanes, keys g, g+8)
+      const bool c0 = (t == 0);
+      const float p0a = (c0 && va) ? __expf(s0[0] - lse_a) : 0.f, p0b = (c0 && vb) ? __expf(s0[2] - lse_b) : 0.f;
+      const float ds0a = p0a * (dp0[0] - del_a), ds0b = p0b * (dp0[2] - del_b);
+      const float pca = (c0 && va) ? __expf(sc[0] - lse_c) : 0.f, pcb = (c0 && vb) ? __expf(sc[2] - lse_c) : 0.f;
+      const float dsca = pca * (dpc[0] - delta_c), dscb = pcb * (dpc[2] - delta_c);
+      E0[0] = pack_bf16x2(ds0a, 0.f); E0[1] = pack_bf16x2(ds0b, 0.f); E0[2] = 0u; E0[3] = 0u;
+      Ep[0] = pack_bf16x2(p0a, 0.f); Ep[1] = pack_bf16x2(p0b, 0.f); Ep[2] = 0u; Ep[3] = 0u;
+      Ec[0] = pack_bf16x2(dsca, 0.f); Ec[1] = pack_bf16x2(dscb, 0.f); Ec[2] = 0u; Ec[3] = 0u;
+      Epc[0] = pack_bf16x2(pca, 0.f); Epc[1] = pack_bf16x2(pcb, 0.f); Epc[2] = 0u; Epc[3] = 0u;
     }
-  }
-  load_row_lin(Cs, raw);
-  axpy_row(dsc, raw, a);
-  store_row_sw(Ks, r, a, 1.f);
-  // dV_j = sum_i P_ij dO_i + P_cj dO_cls   (P rounded to bf16 like the forward's P.V operand)
+    // transposes for the key side, and the single-row A operands of the CLS-row reductions
+    uint32_t PTa[4], dSTa[4], Rk[4], Rv[4], Rq[4];
+    PTa[0] = movm_t(Pa[0]); PTa[1] = movm_t(Pa[2]); PTa[2] = movm_t(Pa[1]); PTa[3] = movm_t(Pa[3]);
+    dSTa[0] = movm_t(dSa[0]); dSTa[1] = movm_t(dSa[2]); dSTa[2] = movm_t(dSa[1]); dSTa[3] = movm_t(dSa[3]);
+    Rk[0] = movm_t(E0[0]); Rk[1] = 0u; Rk[2] = movm_t(E0[1]); Rk[3] = 0u;      // row 0 = ds_i0 over queries i
+    Rv[0] = movm_t(Ep[0]); Rv[1] = 0u; Rv[2] = movm_t(Ep[1]); Rv[3] = 0u;      // row 0 = p_i0
+    Rq[0] = movm_t(Ec[0]); Rq[1] = 0u; Rq[2] = movm_t(Ec[1]); Rq[3] = 0u;      // row 0 = dS_cj over keys j
+
+    float acc[8][4], acc2[8][4];
+    // ---- dQ = dS K + ds_i0 k_cls (-> V rows, dead since their fragments were loaded) ; dQ_cls += dS_c. K
 #pragma unroll
-  for (int d = 0; d < TD; ++d) a[d] = 0.f;
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
+    mma_rows_t(aK, R0, lane, dSa, acc, Rq, acc2);
+    mma_cls_t(mK, lane, E0, acc);
+    add_row0(sAcc, lane, acc2);
+    __syncwarp();                                               // every lane has loaded its V / K fragments of this tile
+    store_acc_rows(Vs, R0, lane, acc, G.scale);
+    // ---- dK = dS^T Q + dS_cj q_cls (-> K rows) ; dK_cls += ds_.0 Q
 #pragma unroll
-  for (int i = 0; i < KMAX - 1; ++i) {
-    if (i < G.F) {
-      load_row_sw(Ds, g0 + i, raw);
-      axpy_row(valid ? bf16_round(sP[(lane - fi + i) * (KMAX - 1) + fi]) : 0.f, raw, a);
-    }
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
+    mma_rows_t(aQ, R0, lane, dSTa, acc, Rk, acc2);
+    mma_cls_t(mQ, lane, Ec, acc);
+    add_row0(sAcc + TD, lane, acc2);
+    store_acc_rows(Ks, R0, lane, acc, 1.f);
+    // ---- dV = P^T dO + P_cj dO_cls (-> Q rows) ; dV_cls += p_.0 dO
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
+    mma_rows_t(aD, R0, lane, PTa, acc, Rv, acc2);
+    mma_cls_t(mD, lane, Epc, acc);
+    add_row0(sAcc + 2 * TD, lane, acc2);
+    __syncwarp();                                               // every lane is done with the Q rows of this tile
+    store_acc_rows(Qs, R0, lane, acc, 1.f);
   }
-  load_row_lin(Cs + 3 * 128, raw);
-  axpy_row(bf16_round(pc), raw, a);
-  __syncwarp();                                                 // every lane is done with the Q rows
-  store_row_sw(Qs, r, a, 1.f);
   __syncwarp();
-  store_rows_warp(Ks, G.dqkv + row0 * G.ld_dqkv + HD3 + h * TD, G.ld_dqkv, tok, warp, lane);
-  store_rows_warp(Qs, G.dqkv + row0 * G.ld_dqkv + 2 * HD3 + h * TD, G.ld_dqkv, tok, warp, lane);
+  __nv_bfloat16* gbase = G.dqkv + row0 * G.ld_dqkv + h * TD;
+  store_rows_warp(Vs, gbase, G.ld_dqkv, tok, warp, lane);                   // dq (already scaled)
+  store_rows_warp(Ks, gbase + HD3, G.ld_dqkv, tok, warp, lane);             // dk
+  store_rows_warp(Qs, gbase + 2 * HD3, G.ld_dqkv, tok, warp, lane);         // dv
   __syncthreads();
-  for (int t = threadIdx.x; t < 3 * TD; t += kRows) atomicAdd(G.cls_acc + static_cast<long long>(bh) * 3 * TD + t, sAcc[t]);
+  for (int i = threadIdx.x; i < 3 * TD; i += kRows) atomicAdd(G.cls_acc + static_cast<long long>(bh) * 3 * TD + i, sAcc[i]);
 }
 
 // Adds the (CLS query, CLS key) pair and writes row 0 of dqkv: dq = scale * (acc_q + dS_cc k_c), dk = acc_k + dS_cc q_c,
@@ -600,19 +698,11 @@ int launch_time_fwd(const oat_attn_args* a, cudaStream_t s, bool* cls_done) {
 int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   const TimeGeom G = make_time_geom(a);
   const int grid = a->B * a->H * G.chunks;
-  constexpr int smem = 4 * kArr + 5 * 128 + (kRows + 3 * TD) * static_cast<int>(sizeof(float));
-  static bool d5 = false, d9 = false, d17 = false;
-  int rc;
-  if (a->F + 1 <= 5) {
-    if ((rc = set_smem_once(attn_time_bwd_kernel<5>, smem, &d5, "attn_time_bwd")) != OAT_OK) return rc;
-    attn_time_bwd_kernel<5><<<grid, kRows, smem, s>>>(G);
-  } else if (a->F + 1 <= 9) {
-    if ((rc = set_smem_once(attn_time_bwd_kernel<9>, smem, &d9, "attn_time_bwd")) != OAT_OK) return rc;
-    attn_time_bwd_kernel<9><<<grid, kRows, smem, s>>>(G);
-  } else {
-    if ((rc = set_smem_once(attn_time_bwd_kernel<17>, smem, &d17, "attn_time_bwd")) != OAT_OK) return rc;
-    attn_time_bwd_kernel<17><<<grid, kRows, smem, s>>>(G);
-  }
+  constexpr int smem = 4 * kArr + 4 * 1024 + (2 * kRows + 3 * TD) * static_cast<int>(sizeof(float));
+  static bool done = false;
+  int rc = set_smem_once(attn_time_bwd_kernel, smem, &done, "attn_time_bwd");
+  if (rc != OAT_OK) return rc;
+  attn_time_bwd_kernel<<<grid, kRows, smem, s>>>(G);
   rc = check_launch("attn_time_bwd_kernel");
   if (rc != OAT_OK) return rc;
   attn_time_cls_finalize_kernel<<<a->B * a->H, 32, 0, s>>>(G);
