@@ -293,19 +293,23 @@ def main():
     if not args.no_e2e:
         h2d = host["video"].numel() * 4 + host["object"].numel() * 4 + sum(v.numel() * 8 for v in host["text"].values())
 
-        def e2e_step():
-            data = {"video": host["video"].to(device, non_blocking=True),
-                    "object": host["object"].to(device, non_blocking=True),
-                    "text": {k: v.to(device, non_blocking=True) for k, v in host["text"].items()}}
-            return float(step(data).item())     # D2H read of the loss closes the step
+        # the plugin's own input path: pinned host batches staged one step ahead on a copy stream
+        # (data_loader.DevicePrefetcher); every step still moves one full batch host -> device inside the timed region
+        from oa_transformer_b200.data_loader import DevicePrefetcher
 
-        for _ in range(2):
-            e2e_step()
+        def host_batches(n):
+            for _ in range(n):
+                yield host
+
+        def run_e2e(n):
+            for data in DevicePrefetcher(host_batches(n), device):
+                float(step(data).item())        # D2H read of the loss closes the step
+
+        run_e2e(2)
         barrier()
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(K):
-            e2e_step()
+        run_e2e(K)
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) / K * 1e3
@@ -314,7 +318,8 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / (float(t) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 4, "ms_per_step": float(t)}
+               "d2h_bytes_per_step": 4, "ms_per_step": float(t),
+               "h2d": "pinned host batch -> device on a copy stream, one step ahead (double-buffered), every step"}
 
     # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)
     roofline = roofline_attn = None

@@ -1,17 +1,21 @@
-// Time attention (sequence length F + 1 <= 17) as an HBM-bound gather kernel: one THREAD per (batch, slot, head,
-// frame) row, fp32 SIMT math, 128-bit row loads. Reference: VarAttention.forward with '(b n) f d' grouping,
+// Time attention (sequence length F + 1 <= 17). Reference: VarAttention.forward with the '(b n) f d' grouping,
 // OATrans/model/video_transformer.py:112-122: token (f, i) attends to [CLS] + tokens (f', i) of every frame f'.
 //
-// A group (b, slot i, head h) has F queries and F + 1 keys of 64 dims: 2-8 FLOP per byte, far too small for 128-row
-// tensor-core tiles, so the goal is to touch every 128-byte head slice once and keep the SM busy:
-//   lane = group_in_warp * Fp + frame   (Fp = F rounded up to a power of two; 32 / Fp groups per warp)
-//   every warp stages the head slices of its 32 token rows into shared memory with cp.async, 8 lanes per 128-byte
-//   slice (full lines on the global side, all loads of a CTA in flight at once); every lane then owns one token row
-//   and reads the other rows of its group from shared memory (broadcast). Result rows go back through shared memory
-//   so that the global stores are full lines too.
-// Backward computes the (F x (F+1)) probability / dS rows once on the query side, hands them to the key side through
-// shared memory, and reduces the three CLS-row vectors (dQ of the CLS query, dK / dV of the CLS key) with a warp
-// transpose-reduce -> shared memory -> one global atomic per component per CTA.
+// A group (b, slot i, head h) has F queries and F + 1 keys of 64 dims: 2-8 FLOP per byte, an HBM-bound gather. The
+// kernels touch every 128-byte head slice exactly once and keep the instruction count per token row low:
+//   * CTA = 4 warps = 128 token rows of one (batch, head): row = group_in_warp * Fp + frame (Fp = F rounded up to a
+//     power of two), i.e. 128 / Fp consecutive slots. Every warp stages the head slices of its 32 rows into shared
+//     memory with cp.async, 8 lanes per 128-byte slice (full lines on the global side, all loads of the CTA in flight
+//     at once), into 128B-pitch rows with an XOR-swizzled 16-byte unit order (conflict-free ldmatrix and row stores).
+//   * The arithmetic runs on bf16 m16n8k16 MMAs (fp32 accumulate): a warp's 32 rows are two independent 16-row tiles
+//     (groups never straddle a tile since Fp | 16); the 16 x 16 score block of a tile is computed densely and masked
+//     to its block diagonal, so one code path serves every F <= 16. The CLS key is a 17th key column and the CLS
+//     query a 17th query row, both expressed as MMAs against 8-row matrices whose row 0 holds the CLS vector.
+//   * Results go back through the (dead) staged rows so that the global stores are full 128-byte lines too.
+// A first SIMT version (one thread per token row, fp32 FMAs) needed ~3 k / ~6 k instructions per row (forward /
+// backward) and ran 3x / 5x off the HBM roofline; the MMA formulation needs ~10x fewer.
+#include <stdlib.h>
+
 #include "oat_host.h"
 #include "oat_ptx.cuh"
 
@@ -19,7 +23,6 @@ namespace oat {
 
 constexpr int TD = 64;            // head dim
 constexpr int kTimeWarps = 4;     // 128 threads = 128 token rows staged per CTA
-constexpr int TP = 72;            // smem row pitch (bf16): 144 B keeps the per-group broadcast reads conflict-free
 
 struct TimeGeom {
   int B, T, H, F, n, Fp, gpc, chunks;   // gpc: groups per CTA, chunks: CTAs per (b, h)
@@ -34,124 +37,12 @@ struct TimeGeom {
   float* cls_part;                      // forward: [B*H][chunks*warps][2+64] partials of the CLS query (or null)
 };
 
-__device__ __forceinline__ void load_row(const __nv_bfloat16* p, uint4 (&r)[8]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) r[c] = reinterpret_cast<const uint4*>(p)[c];
-}
-__device__ __forceinline__ void unpack_row(const uint4 (&r)[8], float (&f)[TD]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t w[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      f[c * 8 + 2 * k] = __uint_as_float(w[k] << 16);
-      f[c * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-    }
-  }
-}
-// dot(f, row) and axpy with a packed bf16 row
-__device__ __forceinline__ float dot_row(const float (&f)[TD], const uint4 (&r)[8]) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t w[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
-    a0 = fmaf(f[c * 8 + 0], __uint_as_float(w[0] << 16), a0);
-    a1 = fmaf(f[c * 8 + 1], __uint_as_float(w[0] & 0xffff0000u), a1);
-    a2 = fmaf(f[c * 8 + 2], __uint_as_float(w[1] << 16), a2);
-    a3 = fmaf(f[c * 8 + 3], __uint_as_float(w[1] & 0xffff0000u), a3);
-    a0 = fmaf(f[c * 8 + 4], __uint_as_float(w[2] << 16), a0);
-    a1 = fmaf(f[c * 8 + 5], __uint_as_float(w[2] & 0xffff0000u), a1);
-    a2 = fmaf(f[c * 8 + 6], __uint_as_float(w[3] << 16), a2);
-    a3 = fmaf(f[c * 8 + 7], __uint_as_float(w[3] & 0xffff0000u), a3);
-  }
-  return (a0 + a1) + (a2 + a3);
-}
-__device__ __forceinline__ void axpy_row(float a, const uint4 (&r)[8], float (&acc)[TD]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t w[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      acc[c * 8 + 2 * k] = fmaf(a, __uint_as_float(w[k] << 16), acc[c * 8 + 2 * k]);
-      acc[c * 8 + 2 * k + 1] = fmaf(a, __uint_as_float(w[k] & 0xffff0000u), acc[c * 8 + 2 * k + 1]);
-    }
-  }
-}
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* p, const float (&f)[TD], float mul) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 v;
-    v.x = pack_bf16x2(f[c * 8 + 0] * mul, f[c * 8 + 1] * mul);
-    v.y = pack_bf16x2(f[c * 8 + 2] * mul, f[c * 8 + 3] * mul);
-    v.z = pack_bf16x2(f[c * 8 + 4] * mul, f[c * 8 + 5] * mul);
-    v.w = pack_bf16x2(f[c * 8 + 6] * mul, f[c * 8 + 7] * mul);
-    reinterpret_cast<uint4*>(p)[c] = v;
-  }
-}
-
-// Sum a 64-vector over the 32 lanes of a warp; afterwards lane L holds components (2 * rev-index(L), +1) in v[0..1]
-// and `base` tells which. 62 shuffles instead of 320.
-__device__ __forceinline__ int warp_transpose_reduce(float (&v)[TD], int lane) {
-  int base = 0;
-#pragma unroll
-  for (int step = 0; step < 5; ++step) {
-    const int width = 16 >> step;      // lane distance
-    const int half = 32 >> step;       // components kept
-    const bool upper = (lane & width) != 0;
-#pragma unroll
-    for (int c = 0; c < half; ++c) {
-      const float send = upper ? v[c] : v[c + half];
-      const float keep = upper ? v[c + half] : v[c];
-      v[c] = keep + __shfl_xor_sync(0xffffffffu, send, width);
-    }
-    base += upper ? half : 0;
-  }
-  return base;                         // v[0], v[1] are components base, base + 1
-}
-__device__ __forceinline__ float dot_packed(const uint4 (&x)[8], const uint4 (&y)[8]) {
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t xw[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
-    const uint32_t yw[4] = {y[c].x, y[c].y, y[c].z, y[c].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      a0 = fmaf(__uint_as_float(xw[k] << 16), __uint_as_float(yw[k] << 16), a0);
-      a1 = fmaf(__uint_as_float(xw[k] & 0xffff0000u), __uint_as_float(yw[k] & 0xffff0000u), a1);
-    }
-  }
-  return a0 + a1;
-}
-
 // ------------------------------------------------------------------------------------------------ shared-memory rows
 // A staged row is one head slice (64 bf16 = 128 B = 8 chunks of 16 B). Rows are packed at a 128-byte pitch and chunk c
 // of row r lives at chunk position (c ^ (r & 7)): the 8 lanes that stage one row write one full 128-byte line (global
 // side: one coalesced line per 8 lanes), a thread that reads ITS OWN row hits 8 distinct bank groups across a
-// quarter-warp, and the lanes of a group that read the SAME row get a broadcast.
+// quarter-warp, and ldmatrix reads of 8 consecutive rows are conflict-free.
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return static_cast<uint32_t>(r) * 128u + ((static_cast<uint32_t>(c ^ (r & 7))) << 4); }
-__device__ __forceinline__ void load_row_sw(const uint8_t* arr, int r, uint4 (&raw)[8]) {
-  const uint8_t* row = arr + static_cast<uint32_t>(r) * 128u;
-  const uint32_t x = static_cast<uint32_t>(r & 7) << 4;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) raw[c] = *reinterpret_cast<const uint4*>(row + ((static_cast<uint32_t>(c) << 4) ^ x));
-}
-__device__ __forceinline__ void store_row_sw(uint8_t* arr, int r, const float (&f)[TD], float mul) {
-  uint8_t* row = arr + static_cast<uint32_t>(r) * 128u;
-  const uint32_t x = static_cast<uint32_t>(r & 7) << 4;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 v;
-    v.x = pack_bf16x2(f[c * 8 + 0] * mul, f[c * 8 + 1] * mul);
-    v.y = pack_bf16x2(f[c * 8 + 2] * mul, f[c * 8 + 3] * mul);
-    v.z = pack_bf16x2(f[c * 8 + 4] * mul, f[c * 8 + 5] * mul);
-    v.w = pack_bf16x2(f[c * 8 + 6] * mul, f[c * 8 + 7] * mul);
-    *reinterpret_cast<uint4*>(row + ((static_cast<uint32_t>(c) << 4) ^ x)) = v;
-  }
-}
-__device__ __forceinline__ void load_row_lin(const uint8_t* row, uint4 (&raw)[8]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) raw[c] = reinterpret_cast<const uint4*>(row)[c];
-}
 
 __device__ __forceinline__ void cp_async16_t(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -192,127 +83,8 @@ __device__ __forceinline__ void store_rows_warp(const uint8_t* arr, __nv_bfloat1
 
 constexpr int kRows = kTimeWarps * 32;
 constexpr int kArr = kRows * 128;            // bytes of one staged array (Q, K, V or dO rows of the CTA)
-constexpr int kClsPartT = 2 + TD;            // per-warp partial of the CLS query: running max, sum, 64 weighted-V sums
-
-// ------------------------------------------------------------------------------------------------ forward
-// Every warp is autonomous (no block-wide barrier): it stages its 32 token rows of Q, K, V (+ the three CLS rows),
-// each lane then runs the softmax row of its own token against [CLS key] + the F keys of its group, writes the
-// output row back over its Q row and the warp stores the 32 output rows with full 128-byte lines.
-// CLS query (video_transformer.py:108-110: attends to every token): every lane also scores its own key row against
-// q_cls; the warp reduces (max, sum, sum p.v) to one partial in `cls_part`, merged by attn_time_cls_combine_kernel.
-template <int KMAX>   // F + 1 <= KMAX
-__global__ void __launch_bounds__(kRows, 4) attn_time_fwd_kernel(const TimeGeom G) {
-  extern __shared__ __align__(128) uint8_t sm_time_raw[];
-  uint8_t* Qs = sm_time_raw;
-  uint8_t* Ks = Qs + kArr;
-  uint8_t* Vs = Ks + kArr;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* Cs = Vs + kArr + warp * (3 * 128);                  // this warp's copy of the CLS q / k / v rows
-  const int bh = blockIdx.x / G.chunks, chunk = blockIdx.x - bh * G.chunks;
-  const int b = bh / G.H, h = bh - b * G.H;
-  const int HD3 = G.H * TD;
-  const long long row0 = static_cast<long long>(b) * G.T;
-  const __nv_bfloat16* base = G.qkv + row0 * G.ld_qkv + h * TD;
-  int tok[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) tok[it] = row_token(G, chunk, warp, it * 4 + (lane >> 3));
-  stage_rows_warp(Ks, base + HD3, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Vs, base + 2 * HD3, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Qs, base, G.ld_qkv, tok, warp, lane);
-  if (lane < 24) cp_async16_t(smem_u32(Cs + (lane >> 3) * 128 + (lane & 7) * 16), base + (lane >> 3) * HD3 + (lane & 7) * 8);
-  const int my_tok = row_token(G, chunk, warp, lane);
-  const bool valid = my_tok >= 0;
-  const int r = threadIdx.x;                                   // this lane's row in the staged arrays
-  const int g0 = r - (lane % G.Fp);                            // row of frame 0 of this lane's group
-  cp_async_wait_all_t();
-  __syncwarp();
-
-  uint4 raw[8];
-  float a[TD];
-  // ---- CLS query partial over this warp's 32 keys
-  if (G.cls_part != nullptr) {
-    uint4 kr[8];
-    load_row_sw(Ks, r, kr);
-    load_row_lin(Cs, raw);
-    const float sc = valid ? dot_packed(kr, raw) : -INFINITY;
-    const float mw = warp_max(sc);
-    const float p = valid ? __expf(sc - mw) : 0.f;             // a warp without valid rows never gets here with mw finite
-    const float lw = warp_sum(p);
-    load_row_sw(Vs, r, raw);
-    unpack_row(raw, a);
-    const float pb = bf16_round(p);
-#pragma unroll
-    for (int d = 0; d < TD; ++d) a[d] *= pb;
-    const int cb = warp_transpose_reduce(a, lane);
-    float* part = G.cls_part + (static_cast<long long>(bh) * G.chunks * kTimeWarps + chunk * kTimeWarps + warp) * kClsPartT;
-    const bool any = mw > -INFINITY;
-    if (lane == 0) { part[0] = mw; part[1] = any ? lw : 0.f; }
-    part[2 + cb] = any ? a[0] : 0.f;
-    part[2 + cb + 1] = any ? a[1] : 0.f;
-  }
-  // ---- patch queries
-  float lse_val = 0.f;
-  {
-    load_row_sw(Qs, r, raw);
-    unpack_row(raw, a);                                        // a = q_i
-    float s[KMAX];
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j <= G.F) {
-        if (j == 0) load_row_lin(Cs + 128, raw); else load_row_sw(Ks, g0 + j - 1, raw);
-        s[j] = dot_row(a, raw);
-        m = fmaxf(m, s[j]);
-      } else {
-        s[j] = -INFINITY;
-      }
-    }
-    float l = 0.f;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      s[j] = (j <= G.F) ? __expf(s[j] - m) : 0.f;
-      l += s[j];
-    }
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int d = 0; d < TD; ++d) a[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j <= G.F) {
-        if (j == 0) load_row_lin(Cs + 256, raw); else load_row_sw(Vs, g0 + j - 1, raw);
-        axpy_row(bf16_round(s[j] * inv), raw, a);
-      }
-    }
-    lse_val = m + __logf(l);
-  }
-  store_row_sw(Qs, r, a, 1.f);                                 // own Q row is dead: it becomes the output staging row
-  if (valid && G.lse != nullptr) G.lse[(static_cast<long long>(b) * G.H + h) * G.T + my_tok] = lse_val;
-  __syncwarp();
-  store_rows_warp(Qs, G.out + row0 * G.ld_out + h * TD, G.ld_out, tok, warp, lane);
-}
-
-// Merges the per-warp partials of the CLS query with the (CLS query, CLS key) pair; writes out row 0 and lse[0].
-__global__ void __launch_bounds__(TD) attn_time_cls_combine_kernel(const TimeGeom G) {
-  const int bh = blockIdx.x, b = bh / G.H, h = bh - b * G.H, d = threadIdx.x;
-  const int HD3 = G.H * TD;
-  const int parts = G.chunks * kTimeWarps;
-  const float* part = G.cls_part + static_cast<long long>(bh) * parts * kClsPartT;
-  const __nv_bfloat16* base = G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + h * TD;
-  float scc = 0.f;
-  for (int k = 0; k < TD; ++k) scc = fmaf(__bfloat162float(base[k]), __bfloat162float(base[HD3 + k]), scc);
-  float M = scc;
-  for (int p = 0; p < parts; ++p) M = fmaxf(M, part[p * kClsPartT]);
-  const float pcc = __expf(scc - M);
-  float L = pcc;
-  float o = bf16_round(pcc) * __bfloat162float(base[2 * HD3 + d]);
-  for (int p = 0; p < parts; ++p) {
-    const float w = __expf(part[p * kClsPartT] - M);           // exp(-inf) = 0 for empty partials
-    L = fmaf(part[p * kClsPartT + 1], w, L);
-    o = fmaf(part[p * kClsPartT + 2 + d], w, o);
-  }
-  G.out[static_cast<long long>(b) * G.T * G.ld_out + h * TD + d] = __float2bfloat16_rn(o / L);
-  if (d == 0 && G.lse != nullptr) G.lse[static_cast<long long>(bh) * G.T] = M + __logf(L);
-}
+constexpr int kClsPartT = 2 + TD;            // per-tile partial of the CLS query: running max, sum, 64 weighted-V sums
+constexpr int kClsParts = 2 * kTimeWarps;    // partials per CTA (two 16-row tiles per warp)
 
 // ------------------------------------------------------------------------------------------------ backward (tensor cores)
 // The SIMT formulation above issues ~6 k instructions per token row in the backward; here the same arithmetic runs on
@@ -418,6 +190,171 @@ __device__ __forceinline__ void add_row0(float* dst, int lane, const float (&acc
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward (tensor cores)
+// Same tiling as the backward below: a warp owns two independent 16-row tiles; S = Q K^T is computed densely per
+// tile and masked to the group diagonal; the CLS key is a 17th column (MMA against the 8-row k_cls matrix), the CLS
+// value a rank-1 MMA update. CLS query (video_transformer.py:108-110: attends to every token): every tile also scores
+// its 16 keys against q_cls and reduces (max, sum, sum p.v) to one partial in `cls_part`, merged by
+// attn_time_cls_combine_kernel; without a workspace the caller runs the separate all-keys pass instead.
+template <int MINB>
+__global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGeom G) {
+  extern __shared__ __align__(128) uint8_t sm_time_raw[];
+  uint8_t* Qs = sm_time_raw;
+  uint8_t* Ks = Qs + kArr;
+  uint8_t* Vs = Ks + kArr;
+  uint8_t* Cm = Vs + kArr;                                     // 3 CLS matrices [8][128 B]: q, k, v
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bh = blockIdx.x / G.chunks, chunk = blockIdx.x - bh * G.chunks;
+  const int b = bh / G.H, h = bh - b * G.H;
+  const int HD3 = G.H * TD;
+  const long long row0 = static_cast<long long>(b) * G.T;
+  const __nv_bfloat16* base = G.qkv + row0 * G.ld_qkv + h * TD;
+  int tok[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) tok[it] = row_token(G, chunk, warp, it * 4 + (lane >> 3));
+  stage_rows_warp(Ks, base + HD3, G.ld_qkv, tok, warp, lane);
+  stage_rows_warp(Qs, base, G.ld_qkv, tok, warp, lane);
+  stage_rows_warp(Vs, base + 2 * HD3, G.ld_qkv, tok, warp, lane);
+  if (threadIdx.x < 96) {  // CLS matrices: row 0 <- vector, rows 1-7 <- 0
+    const int m = threadIdx.x >> 5, rr = (threadIdx.x >> 3) & 3, c = threadIdx.x & 7;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 4 + rr;
+      uint8_t* dst = Cm + m * 1024 + r * 128 + ((c ^ r) << 4);
+      if (r == 0) cp_async16_t(smem_u32(dst), base + m * HD3 + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const int my_tok = row_token(G, chunk, warp, lane);
+  const uint32_t vm = __ballot_sync(0xffffffffu, my_tok >= 0);
+  cp_async_wait_all_t();
+  __syncthreads();
+
+  const uint32_t aQ = smem_u32(Qs), aK = smem_u32(Ks), aV = smem_u32(Vs);
+  const uint32_t mQ = smem_u32(Cm), mK = mQ + 1024, mV = mQ + 2048;
+  const int g = lane >> 2, t = lane & 3;
+  int lg = 0;
+  while ((1 << lg) < G.Fp) ++lg;
+  uint32_t bq[4][2], bk[4][2];
+  load_cls_frags(mQ, lane, bq);
+  load_cls_frags(mK, lane, bk);
+  float* lse_out = G.lse != nullptr ? G.lse + (static_cast<long long>(b) * G.H + h) * G.T : nullptr;
+
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int R0 = warp * 32 + mt * 16;
+    const int wr = mt * 16;
+    uint32_t Pa[4], E0[4], Rc[4];
+    float lse_a, lse_b, mc, lc;
+    {
+      uint32_t fq[4][4], fk[4][4];
+      load_tile_frags(aQ, R0, lane, fq);
+      load_tile_frags(aK, R0, lane, fk);
+      float S[2][4] = {}, s0[4] = {}, sc[4] = {};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) mma_bf16(S[nt], fq[ks], fk[ks][nt], fk[ks][2 + nt]);
+        mma_bf16(s0, fq[ks], bk[ks][0], bk[ks][1]);            // q_i . k_cls (column 0)
+        mma_bf16(sc, fk[ks], bq[ks][0], bq[ks][1]);            // k_j . q_cls (column 0)
+      }
+      const int ra = wr + g, rb = ra + 8;
+      const bool va = (vm >> ra) & 1u, vb = (vm >> rb) & 1u;
+      // the CLS-key score of rows g / g+8 lives in the t == 0 lane of the quad
+      const float s0a = __shfl_sync(0xffffffffu, s0[0], lane & ~3), s0b = __shfl_sync(0xffffffffu, s0[2], lane & ~3);
+      float ma = s0a, mb = s0b;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = wr + nt * 8 + 2 * t + e;
+          const bool vk = (vm >> key) & 1u;
+          if (!(va && vk && ((ra >> lg) == (key >> lg)))) S[nt][e] = -INFINITY;
+          if (!(vb && vk && ((rb >> lg) == (key >> lg)))) S[nt][2 + e] = -INFINITY;
+          ma = fmaxf(ma, S[nt][e]);
+          mb = fmaxf(mb, S[nt][2 + e]);
+        }
+      }
+      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+      float la = 0.f, lb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          S[nt][e] = __expf(S[nt][e] - ma); la += S[nt][e];
+          S[nt][2 + e] = __expf(S[nt][2 + e] - mb); lb += S[nt][2 + e];
+        }
+      }
+      la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+      lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+      const float p0a = __expf(s0a - ma), p0b = __expf(s0b - mb);
+      la += p0a; lb += p0b;
+      const float ia = 1.f / la, ib = 1.f / lb;
+      lse_a = ma + __logf(la); lse_b = mb + __logf(lb);
+      Pa[0] = pack_bf16x2(S[0][0] * ia, S[0][1] * ia); Pa[1] = pack_bf16x2(S[0][2] * ib, S[0][3] * ib);
+      Pa[2] = pack_bf16x2(S[1][0] * ia, S[1][1] * ia); Pa[3] = pack_bf16x2(S[1][2] * ib, S[1][3] * ib);
+      E0[0] = t == 0 ? pack_bf16x2(p0a * ia, 0.f) : 0u; E0[1] = t == 0 ? pack_bf16x2(p0b * ib, 0.f) : 0u; E0[2] = 0u; E0[3] = 0u;
+      // CLS query vs the 16 keys of this tile (t == 0 lanes hold keys g, g+8)
+      const float ca = (t == 0 && va) ? sc[0] : -INFINITY, cb = (t == 0 && vb) ? sc[2] : -INFINITY;
+      mc = warp_max(fmaxf(ca, cb));
+      const float pa = mc > -INFINITY ? __expf(ca - mc) : 0.f, pb = mc > -INFINITY ? __expf(cb - mc) : 0.f;
+      lc = warp_sum(pa + pb);
+      Rc[0] = movm_t(pack_bf16x2(pa, 0.f)); Rc[1] = 0u; Rc[2] = movm_t(pack_bf16x2(pb, 0.f)); Rc[3] = 0u;
+    }
+    float acc[8][4], acc2[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
+    mma_rows_t(aV, R0, lane, Pa, acc, Rc, acc2);               // O = P V ; CLS partial sum_j p_cj v_j (row 0 of acc2)
+    mma_cls_t(mV, lane, E0, acc);                              // + p_i0 v_cls
+    if (G.cls_part != nullptr) {
+      float* part = G.cls_part + ((static_cast<long long>(bh) * G.chunks + chunk) * kClsParts + warp * 2 + mt) * kClsPartT;
+      if (lane == 0) { part[0] = mc; part[1] = lc; }
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          part[2 + 8 * j + 2 * lane] = acc2[j][0];
+          part[2 + 8 * j + 2 * lane + 1] = acc2[j][1];
+        }
+      }
+    }
+    if (lse_out != nullptr && t == 0) {
+      const int ta = row_token(G, chunk, warp, wr + g), tb = row_token(G, chunk, warp, wr + g + 8);
+      if (ta >= 0) lse_out[ta] = lse_a;
+      if (tb >= 0) lse_out[tb] = lse_b;
+    }
+    __syncwarp();                                              // every lane has its Q fragments of this tile
+    store_acc_rows(Qs, R0, lane, acc, 1.f);
+  }
+  __syncwarp();
+  store_rows_warp(Qs, G.out + row0 * G.ld_out + h * TD, G.ld_out, tok, warp, lane);
+}
+
+
+// Merges the per-tile partials of the CLS query with the (CLS query, CLS key) pair; writes out row 0 and lse[0].
+__global__ void __launch_bounds__(TD) attn_time_cls_combine_kernel(const TimeGeom G) {
+  const int bh = blockIdx.x, b = bh / G.H, h = bh - b * G.H, d = threadIdx.x;
+  const int HD3 = G.H * TD;
+  const int parts = G.chunks * kClsParts;
+  const float* part = G.cls_part + static_cast<long long>(bh) * parts * kClsPartT;
+  const __nv_bfloat16* base = G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + h * TD;
+  float scc = 0.f;
+  for (int k = 0; k < TD; ++k) scc = fmaf(__bfloat162float(base[k]), __bfloat162float(base[HD3 + k]), scc);
+  float M = scc;
+  for (int p = 0; p < parts; ++p) M = fmaxf(M, part[p * kClsPartT]);
+  const float pcc = __expf(scc - M);
+  float L = pcc;
+  float o = bf16_round(pcc) * __bfloat162float(base[2 * HD3 + d]);
+  for (int p = 0; p < parts; ++p) {
+    const float w = __expf(part[p * kClsPartT] - M);           // exp(-inf) = 0 for empty partials
+    L = fmaf(part[p * kClsPartT + 1], w, L);
+    o = fmaf(part[p * kClsPartT + 2 + d], w, o);
+  }
+  G.out[static_cast<long long>(b) * G.T * G.ld_out + h * TD + d] = __float2bfloat16_rn(o / L);
+  if (d == 0 && G.lse != nullptr) G.lse[static_cast<long long>(bh) * G.T] = M + __logf(L);
+}
+
+// ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom G) {
   extern __shared__ __align__(128) uint8_t sm_time_raw[];
   uint8_t* Qs = sm_time_raw;
@@ -656,7 +593,7 @@ long long time_fwd_workspace_floats(int B, int H, int F, int n) {
   while (fp < F) fp <<= 1;
   const int gpc = kTimeWarps * (32 / fp);
   const long long chunks = (n + gpc - 1) / gpc;
-  return static_cast<long long>(B) * H * chunks * kTimeWarps * kClsPartT;
+  return static_cast<long long>(B) * H * chunks * kClsParts * kClsPartT;
 }
 
 template <typename K>
@@ -675,18 +612,16 @@ int launch_time_fwd(const oat_attn_args* a, cudaStream_t s, bool* cls_done) {
   G.cls_part = a->cls_acc;
   *cls_done = G.cls_part != nullptr;
   const int grid = a->B * a->H * G.chunks;
-  constexpr int smem = 3 * kArr + kTimeWarps * 3 * 128;
-  static bool d5 = false, d9 = false, d17 = false;
+  constexpr int smem = 3 * kArr + 3 * 1024;
+  static bool done3 = false, done4 = false;
+  static const bool four = getenv("OAT_TIME_FWD_CTAS") != nullptr && atoi(getenv("OAT_TIME_FWD_CTAS")) == 4;
   int rc;
-  if (a->F + 1 <= 5) {
-    if ((rc = set_smem_once(attn_time_fwd_kernel<5>, smem, &d5, "attn_time_fwd")) != OAT_OK) return rc;
-    attn_time_fwd_kernel<5><<<grid, kRows, smem, s>>>(G);
-  } else if (a->F + 1 <= 9) {
-    if ((rc = set_smem_once(attn_time_fwd_kernel<9>, smem, &d9, "attn_time_fwd")) != OAT_OK) return rc;
-    attn_time_fwd_kernel<9><<<grid, kRows, smem, s>>>(G);
+  if (four) {
+    if ((rc = set_smem_once(attn_time_fwd_kernel<4>, smem, &done4, "attn_time_fwd")) != OAT_OK) return rc;
+    attn_time_fwd_kernel<4><<<grid, kRows, smem, s>>>(G);
   } else {
-    if ((rc = set_smem_once(attn_time_fwd_kernel<17>, smem, &d17, "attn_time_fwd")) != OAT_OK) return rc;
-    attn_time_fwd_kernel<17><<<grid, kRows, smem, s>>>(G);
+    if ((rc = set_smem_once(attn_time_fwd_kernel<3>, smem, &done3, "attn_time_fwd")) != OAT_OK) return rc;
+    attn_time_fwd_kernel<3><<<grid, kRows, smem, s>>>(G);
   }
   rc = check_launch("attn_time_fwd_kernel");
   if (rc != OAT_OK || !*cls_done) return rc;

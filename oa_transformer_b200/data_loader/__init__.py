@@ -46,3 +46,83 @@ class SyntheticTextObjectVideoDataLoader:
 
 MultiDistTextObjectVideoDataLoader = SyntheticTextObjectVideoDataLoader
 TextObjectVideoDataLoader = SyntheticTextObjectVideoDataLoader
+
+
+class DevicePrefetcher:
+    """Host -> device staging one batch ahead on a copy stream (what `pin_memory=True` + `.to(device,
+    non_blocking=True)` in the reference trainer, trainer/trainer_dist.py:150-156, aims at): while step i computes,
+    the pinned tensors of batch i+1 are already crossing PCIe into the other of two device buffer sets.
+
+        pf = DevicePrefetcher(iterable_of_host_batches, device)
+        for data in pf: ...            # data tensors live on `device`; valid until the next-but-one batch is requested
+    """
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]          # device buffer sets
+        self.ready = [None, None]          # copy-finished events
+        self.free = [None, None]           # compute-finished events (buffer may be overwritten)
+        self.k = 0
+        self._stage(0)
+
+    @staticmethod
+    def _tensors(d, prefix=()):
+        for key, v in d.items():
+            if isinstance(v, dict):
+                yield from DevicePrefetcher._tensors(v, prefix + (key,))
+            elif torch.is_tensor(v):
+                yield prefix + (key,), v
+
+    def _stage(self, slot):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.slots[slot] = None
+            return
+        if self.free[slot] is not None:
+            self.copy_stream.wait_event(self.free[slot])
+        prev = self.slots[slot]["dev"] if isinstance(self.slots[slot], dict) and "dev" in self.slots[slot] else {}
+        dev = {}
+        with torch.cuda.stream(self.copy_stream):
+            for path, t in self._tensors(host):
+                buf = prev.get(path)
+                if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                    buf = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                buf.copy_(t, non_blocking=True)
+                dev[path] = buf
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
+        self.ready[slot] = ev
+        self.slots[slot] = {"host": host, "dev": dev}
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        slot = self.k & 1
+        cur = self.slots[slot]
+        if cur is None:
+            raise StopIteration
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self.ready[slot])
+        # the other buffer set was consumed by the previous step: mark it free once the work queued so far is done
+        other = slot ^ 1
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.free[other] = ev
+        self._stage(other)
+        self.k += 1
+
+        def build(d, prefix=()):
+            out = {}
+            for key, v in d.items():
+                if isinstance(v, dict):
+                    out[key] = build(v, prefix + (key,))
+                elif torch.is_tensor(v):
+                    out[key] = cur["dev"][prefix + (key,)]
+                else:
+                    out[key] = v
+            return out
+        return build(cur["host"])

@@ -295,3 +295,15 @@ def test_object_patch_attention_modes(mode, C, Ob):
                                       v.cuda(), mode, None if masks is None else masks.cuda().contiguous())
     assert rel(w.cpu(), w_ref) < 1e-5
     assert rel(o.cpu(), o_ref) < 1e-5
+
+
+def test_device_prefetcher_stages_batches_in_order():
+    from oa_transformer_b200.data_loader import DevicePrefetcher
+    host = [{"video": torch.full((2, 3, 8), float(i)).pin_memory(),
+             "text": {"input_ids": torch.full((2, 4), i, dtype=torch.int64).pin_memory()}, "meta": {"i": i}}
+            for i in range(5)]
+    seen = []
+    for data in DevicePrefetcher(host, torch.device("cuda", 0)):
+        assert data["video"].is_cuda and data["text"]["input_ids"].is_cuda
+        seen.append((float(data["video"].sum()) / 48.0, int(data["text"]["input_ids"][0, 0]), data["meta"]["i"]))
+    assert seen == [(float(i), i, i) for i in range(5)]
