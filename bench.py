@@ -281,7 +281,7 @@ def main():
     ms = e0.elapsed_time(e1) / K
     launches = (ops.LAUNCHES - launches0) // K
     clocks = sampler.stop() if rank == 0 else None
-    loss_val = float(loss)
+    loss_val = float(loss.detach())
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,9 +303,19 @@ def main():
 
         def run_e2e(n):
             for data in DevicePrefetcher(host_batches(n), device):
-                float(step(data).item())        # D2H read of the loss closes the step
+                float(step(data).detach().item())        # D2H read of the loss closes the step
 
         run_e2e(2)
+        barrier()
+        # diagnostic: the bare H2D copy of one batch (PCIe + host memory of this box), not part of any metric
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            host["video"].to(device, non_blocking=True)
+            host["object"].to(device, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_ms = c0.elapsed_time(c1) / 3
         barrier()
         t0 = time.perf_counter()
         e0.record()
@@ -318,7 +328,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / (float(t) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 4, "ms_per_step": float(t),
+               "d2h_bytes_per_step": 4, "ms_per_step": float(t), "bare_h2d_copy_ms": h2d_ms,
                "h2d": "pinned host batch -> device on a copy stream, one step ahead (double-buffered), every step"}
 
     # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)

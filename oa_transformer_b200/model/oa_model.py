@@ -107,8 +107,11 @@ class FrozenInTime(BaseModel):
         self.device = device
 
     def forward(self, data, aug=False, return_embeds=True):
-        text_embeddings = self.compute_text(data['text'])
+        # The towers are independent (oa_model.py:97-104 runs text first). The video tower is enqueued first here: its
+        # long GEMMs let the host run ahead, so the ~200 small launches of the text tower are already queued when the
+        # GPU reaches them (matters right after a host sync, e.g. the per-step loss read-back).
         video_embeddings = self.compute_video(data['video'], aug=aug, object_data=data.get('object'))
+        text_embeddings = self.compute_text(data['text'])
         if return_embeds:
             return text_embeddings, video_embeddings
         from .model import sim_matrix
