@@ -44,6 +44,25 @@ def pair_flops(frames=FRAMES, objects=OBJECTS, text_len=TEXT_LEN, n_patches=196)
     return video + text
 
 
+def load_gemm_traffic():
+    """Measured DRAM bytes per GEMM launch (ncu --set full, profiles/r1_kernel_traffic.json made by
+    scripts/ncu_traffic_table.py from one launch of every per-layer GEMM shape at the bench geometry), averaged over the
+    18 GEMM launches of one transformer layer; beside it the algorithmic operand + output bytes of the same launches."""
+    path = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    count = {"gemm_fwd_qkv": 2, "gemm_fwd_proj": 2, "gemm_fwd_fc1": 1, "gemm_fwd_fc2": 1, "gemm_dgrad_fc2": 1,
+             "gemm_dgrad_fc1": 1, "gemm_dgrad_qkv": 2, "gemm_dgrad_proj": 2, "gemm_wgrad_proj": 2, "gemm_wgrad_qkv": 2,
+             "gemm_wgrad_fc1": 1, "gemm_wgrad_fc2": 1}
+    if any(k not in t for k in count):
+        return None, None
+    n = sum(count.values())
+    meas = sum(c * (t[k]["dram_read_bytes"] + t[k]["dram_write_bytes"]) for k, c in count.items()) / n
+    return meas, "average over the 18 GEMM launches of one layer at M=59424 (B=32); per shape in profiles/r1_kernel_traffic.json"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -358,19 +377,37 @@ def main():
         gm = agg.get("gemm")
         if gm and gm["ms"] > 0:
             ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+            traffic, traffic_note = load_gemm_traffic() if B == 32 else (None, None)
             roofline = {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": ach,
                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "launches": gm["n"],
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                        "traffic_note": traffic_note, "launches": gm["n"],
                         "ms_in_step": gm["ms"], "peak_source": peaks["source"] + ", sustained bf16",
                         "note": "algorithmic 2*M*N*K summed over every GEMM launch of one step / summed CUDA-event "
                                 "durations of those launches (instrumented extra step)"}
-        sp = agg.get("attn_fwd_0")
-        if sp and sp["ms"] > 0:
-            gbs = sp["bytes"] / (sp["ms"] / 1e3) / 1e9
-            roofline_attn = {"kernel": "attn_fwd_kernel space (+cls)", "bound": "hbm", "achieved": gbs,
-                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                             "tflops": sp["flops"] / (sp["ms"] / 1e3) / 1e12, "traffic": None, "launches": sp["n"],
-                             "ms_in_step": sp["ms"]}
+        # attention cores: HBM-bound. Algorithmic bytes per group = 128 B x (q + out rows, k + v rows) forward and
+        # twice that backward (q, dO, O, dQ rows; k, v, dK, dV rows) - ops.attn_core_work / SURVEY.md 8(d).
+        ktraffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+        if B == 32 and os.path.exists(tpath):
+            with open(tpath) as f:
+                ktraffic = json.load(f)
+        roofline_attn = {}
+        for key, label, mult, tkey in (("attn_fwd_0", "space_fwd (tcgen05, CLS fused)", 1.0, "attn_space_fwd"),
+                                       ("attn_bwd_0", "space_bwd (tcgen05)", 2.0, "attn_space_bwd"),
+                                       ("attn_fwd_1", "time_fwd (mma.sync, CLS fused)", 1.0, "attn_time_fwd"),
+                                       ("attn_bwd_1", "time_bwd (mma.sync)", 2.0, "attn_time_bwd")):
+            sp = agg.get(key)
+            if not sp or sp["ms"] <= 0:
+                continue
+            gbs = mult * sp["bytes"] / (sp["ms"] / 1e3) / 1e9
+            tr = None
+            if ktraffic and tkey in ktraffic:
+                tr = ktraffic[tkey]["dram_read_bytes"] + ktraffic[tkey]["dram_write_bytes"]
+            roofline_attn[label] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": mult * sp["bytes"] / sp["n"],
+                                    "traffic": tr, "launches": sp["n"], "ms_in_step": sp["ms"],
+                                    "tflops": (1.0 if mult == 1.0 else 2.5) * sp["flops"] / (sp["ms"] / 1e3) / 1e12}
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"]} for k, v in agg.items()}
 
     # ---------------- CPU baseline (rank 0, N = 1 only)

@@ -43,6 +43,7 @@ b4 = torch.randn(4 * D, device=dev)
 dw3 = torch.zeros(3 * D, D, device=dev)
 dw4 = torch.zeros(4 * D, D, device=dev)
 dw2 = torch.zeros(D, 4 * D, device=dev)
+dwp = torch.zeros(D, D, device=dev)
 lse = torch.empty(B * H * T, device=dev)
 acc = torch.empty(B * H * 192, device=dev)
 ws = torch.zeros(max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n),
@@ -64,6 +65,9 @@ cases = [
     ("gemm_fwd_fc2", lambda: ops.gemm(x4, w2, bias=b1, residual=res, out_f32=o32)),
     ("gemm_dgrad_fc2", lambda: ops.gemm(x, w2, b_major=1, act=ops.ACT_GELU_BWD, aux=o16_4b, out_bf16=o16_4)),
     ("gemm_dgrad_fc1", lambda: ops.gemm(x4, w1, b_major=1, out_bf16=o16_1)),
+    ("gemm_dgrad_qkv", lambda: ops.gemm(x3, wqkv, b_major=1, out_bf16=o16_1)),
+    ("gemm_dgrad_proj", lambda: ops.gemm(x, wproj, b_major=1, out_bf16=o16_1)),
+    ("gemm_wgrad_proj", lambda: ops.gemm(x, x, a_major=1, b_major=1, out_f32=dwp, accumulate=True)),
     ("gemm_wgrad_qkv", lambda: ops.gemm(x3, x, a_major=1, b_major=1, out_f32=dw3, accumulate=True)),
     ("gemm_wgrad_fc1", lambda: ops.gemm(x4, x, a_major=1, b_major=1, out_f32=dw4, accumulate=True)),
     ("gemm_wgrad_fc2", lambda: ops.gemm(x, x4, a_major=1, b_major=1, out_f32=dw2, accumulate=True)),
