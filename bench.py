@@ -152,11 +152,28 @@ def cpu_oracle_step_fn(batch, threads=None):
     return step
 
 
+class _StdoutToStderr:
+    """Everything written to fd 1 while the run is in flight (NCCL's version banner, library chatter) goes to stderr, so
+    that stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     batch = 2
@@ -179,7 +196,7 @@ def run_reference_arm(args):
                                    "reference path, batch %d per step" % batch},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -225,8 +242,18 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference_arm(args)
+        with _StdoutToStderr():
+            line = run_reference_arm(args)
+        if line is not None:
+            print(json.dumps(line))
         return
+    with _StdoutToStderr():
+        line = run_ours(args)
+    if line is not None:
+        print(json.dumps(line))
+
+
+def run_ours(args):
 
     import torch
     import torch.distributed as dist
@@ -446,9 +473,9 @@ def main():
                 "mfu_vs_sustained_bf16": value * flops / 1e12 / world / peaks["bf16_tflops_sustained"],
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
                 "roofline_attention": roofline_attn, "kernel_ms_breakdown": breakdown, "cpu_baseline": cpu}
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":
