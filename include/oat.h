@@ -166,6 +166,15 @@ int oat_object_patch_attn(const float* q, const float* k, const float* v, const 
 int oat_patch_masks_from_bbox(const double* boxes, int32_t stride, float* masks, int32_t n, int32_t grid,
                               oat_stream_t stream);
 
+/* ---- retrieval ranks on a square similarity matrix (rows = text queries, columns = videos) ------------------------------
+ * t2v_rank[i] = #{j : sims[i][j] > sims[i][i]}                       ties broken optimistically (model/metric.py:62-69)
+ * v2t_rank[i] = #{j : sims[j][i] > sims[i][i]} + (ties_i - 1) / 2     tied ranks averaged        (model/metric.py:153,183)
+ * i.e. the column of the ground-truth pair in the sorted distance row, exactly as np.sort + np.where produce it;
+ * R@K / MedR / MeanR (cols2metrics, metric.py:281-291) are then counts over these n numbers. Integer bookkeeping:
+ * bit-exact with the reference. */
+int oat_retrieval_ranks(const float* sims, int32_t n, int64_t ld, float* t2v_rank, float* v2t_rank,
+                        oat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,3 +244,46 @@ extern "C" int oat_infonce_fwd_bwd(const float* text, const float* video, int32_
   if (rc != OAT_OK || !want_grad) return rc;
   return oat_sim_matrix_bwd(dsims, n, n, P, eps, dtext, dvideo, workspace, simb, stream);
 }
+
+// ---------------------------------------------------------------------------------------------- retrieval ranks
+// One CTA per ground-truth pair i: counts over row i (text -> video) and column i (video -> text) of the matrix.
+namespace oat {
+__global__ void __launch_bounds__(256) retrieval_ranks_kernel(const float* __restrict__ sims, int n, long long ld,
+                                                              float* __restrict__ t2v, float* __restrict__ v2t) {
+  __shared__ int s_cnt[3];
+  const int i = blockIdx.x;
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const float gt = sims[static_cast<long long>(i) * ld + i];
+  int row_gt = 0, col_gt = 0, col_eq = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float r = sims[static_cast<long long>(i) * ld + j];
+    const float c = sims[static_cast<long long>(j) * ld + i];
+    row_gt += r > gt;
+    col_gt += c > gt;
+    col_eq += c == gt;
+  }
+  row_gt = __reduce_add_sync(0xffffffffu, row_gt);
+  col_gt = __reduce_add_sync(0xffffffffu, col_gt);
+  col_eq = __reduce_add_sync(0xffffffffu, col_eq);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_cnt[0], row_gt);
+    atomicAdd(&s_cnt[1], col_gt);
+    atomicAdd(&s_cnt[2], col_eq);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (t2v != nullptr) t2v[i] = static_cast<float>(s_cnt[0]);
+    if (v2t != nullptr) v2t[i] = static_cast<float>(s_cnt[1]) + 0.5f * static_cast<float>(s_cnt[2] - 1);
+  }
+}
+}  // namespace oat
+
+extern "C" int oat_retrieval_ranks(const float* sims, int32_t n, int64_t ld, float* t2v_rank, float* v2t_rank,
+                                   oat_stream_t stream) {
+  using namespace oat;
+  OAT_REQUIRE(sims != nullptr && n > 0 && ld >= n, "oat_retrieval_ranks: bad arguments (n=%d ld=%lld)", n, (long long)ld);
+  OAT_REQUIRE(t2v_rank != nullptr || v2t_rank != nullptr, "oat_retrieval_ranks: no output");
+  retrieval_ranks_kernel<<<n, 256, 0, as_stream(stream)>>>(sims, n, ld, t2v_rank, v2t_rank);
+  return check_launch("retrieval_ranks_kernel");
+}

@@ -1,8 +1,19 @@
 """Retrieval metrics on a similarity matrix, same definitions and tie rules as OATrans/model/metric.py
 (t2v_metrics :16-121 breaks ties optimistically, v2t_metrics :123-212 averages tied ranks, cols2metrics :281-291).
 numpy on the host, as in the reference (`_valid_epoch` moves the embeddings to the CPU first,
-trainer/trainer_dist.py:237-264). Square matrices (one caption per video) and the query_masks-free path only."""
+trainer/trainer_dist.py:237-264). Square matrices (one caption per video) and the query_masks-free path only.
+A CUDA tensor takes the device path instead: the O(n^2) rank-of-the-diagonal counting runs in `oat_retrieval_ranks`
+(same tie rules, bit-identical ranks) and only the n ranks come back to the host for cols2metrics."""
 import numpy as np
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _device_ranks(sims):
+    from .. import ops
+    return ops.retrieval_ranks(sims.detach().float().contiguous())
 
 
 def cols2metrics(cols, num_queries):
@@ -21,6 +32,9 @@ def cols2metrics(cols, num_queries):
 
 def t2v_metrics(sims, query_masks=None):
     assert query_masks is None, "query_masks path is outside the hot-path scope"
+    if _is_cuda_tensor(sims):
+        assert sims.dim() == 2 and sims.shape[0] == sims.shape[1], "one caption per video expected"
+        return cols2metrics(_device_ranks(sims)[0].cpu().numpy().astype(np.int64), sims.shape[0])
     sims = np.asarray(sims)
     assert sims.ndim == 2, "expected a matrix"
     num_queries, num_vids = sims.shape
@@ -38,6 +52,9 @@ def t2v_metrics(sims, query_masks=None):
 
 def v2t_metrics(sims, query_masks=None):
     assert query_masks is None, "query_masks path is outside the hot-path scope"
+    if _is_cuda_tensor(sims):
+        assert sims.dim() == 2 and sims.shape[0] == sims.shape[1], "one caption per video expected"
+        return cols2metrics(_device_ranks(sims)[1].cpu().numpy().astype(np.float64), sims.shape[0])
     sims = np.asarray(sims).T
     assert sims.ndim == 2, "expected a matrix"
     num_queries, num_caps = sims.shape

@@ -316,6 +316,19 @@ def norm_softmax_loss(sims, temperature, loss, dsims):
                                       ptr(dsims), ptr(scratch), stream_ptr()), "oat_norm_softmax_loss")
 
 
+def retrieval_ranks(sims):
+    """sims: fp32 CUDA [n, n] (rows = text queries, columns = videos) -> (t2v_rank[n], v2t_rank[n]) fp32, the column of
+    the ground-truth pair in the sorted distance row with the reference tie rules (model/metric.py:62-69, 153, 183)."""
+    assert sims.dtype == torch.float32 and sims.dim() == 2 and sims.shape[0] == sims.shape[1] and sims.stride(1) == 1
+    n = sims.shape[0]
+    t2v = torch.empty(n, dtype=torch.float32, device=sims.device)
+    v2t = torch.empty(n, dtype=torch.float32, device=sims.device)
+    _count(1)
+    check(lib().oat_retrieval_ranks(ptr(sims), _i32(n), _i64(sims.stride(0)), ptr(t2v), ptr(v2t), stream_ptr()),
+          "oat_retrieval_ranks")
+    return t2v, v2t
+
+
 # ------------------------------------------------------------------------------------------------ object -> patch
 XATTN_MASK, XATTN_SIGMOID, XATTN_SOFTMAX = 0, 1, 2
 

@@ -307,3 +307,22 @@ def test_device_prefetcher_stages_batches_in_order():
         assert data["video"].is_cuda and data["text"]["input_ids"].is_cuda
         seen.append((float(data["video"].sum()) / 48.0, int(data["text"]["input_ids"][0, 0]), data["meta"]["i"]))
     assert seen == [(float(i), i, i) for i in range(5)]
+
+
+@pytest.mark.parametrize("n,ties", [(1000, False), (257, True), (7, True)])
+def test_retrieval_metrics_device_matches_host(n, ties):
+    """oat_retrieval_ranks + cols2metrics vs the numpy port (itself pinned to the reference fixture), incl. tied scores."""
+    from oa_transformer_b200.model import metric as M
+    g = gen(31)
+    sims = torch.randn(n, n, generator=g)
+    sims += 2.0 * torch.eye(n) * (torch.rand(n, generator=g) > 0.3).float().diag()   # some pairs retrieved, some not
+    if ties:
+        sims = (sims * 2).round() / 2            # coarse grid: many exact ties, also with the diagonal
+        sims[0] = 0.0                            # a constant row: the optimistic rule gives rank 0, averaging (n-1)/2
+    dev = sims.cuda()
+    for fn in (M.t2v_metrics, M.v2t_metrics):
+        host = fn(sims.numpy())
+        devm = fn(dev)
+        assert host.keys() == devm.keys()
+        for k in host:
+            assert host[k] == devm[k], (fn.__name__, k, host[k], devm[k])
