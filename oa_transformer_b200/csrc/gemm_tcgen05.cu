@@ -23,6 +23,7 @@
 // OATrans/model/oa_model.py:68-75 (projections), OATrans/model/model.py:164-172 (sim matrix),
 // HF DistilBERT linears) and their autograd counterparts.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "oat_host.h"
 #include "oat_ptx.cuh"
@@ -79,17 +80,22 @@ enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI
 
 constexpr int kBoxBytes = 32 * 128;              // one epilogue box: 32 rows x 128 B (64 bf16 or 32 fp32 columns)
 
-template <int BLOCK_N, int EPI>
+// TWO: CTA pair (cluster of 2, tcgen05 cta_group::2). The pair computes a 256 x BLOCK_N tile: each CTA stages its own
+// 128 rows of A and HALF of the B tile, so the L2 -> shared-memory traffic per MMA drops from 48 KB to 32 KB per
+// 128x256x64 step (the 1-CTA kernel is bound by exactly that traffic: ~7 KB/clk chip-wide at 1.2 PFLOP/s).
+template <int BLOCK_N, int EPI, bool TWO>
 struct GemmSmem {
   static constexpr bool kTmaEpi = EPI != EPI_GENERIC;
   // boxes per epilogue warp: output (+ second output for GELU') (+ residual / aux input)
   static constexpr int kBoxes = !kTmaEpi ? 0 : (EPI == EPI_BF16 || EPI == EPI_ATOMIC) ? 1 : 2;
   static constexpr int kEpiBytes = kTmaEpi ? kEpiWarps * kBoxes * kBoxBytes : kEpiWarps * kStagingFloats * 4;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kLoadN = TWO ? BLOCK_N / 2 : BLOCK_N;          // B rows staged by this CTA
+  static constexpr int kBBytes = kLoadN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the TMA ring takes what the epilogue boxes leave of the 227 KB
-  static constexpr int kStages = (4 * kStageBytes + kEpiBytes + 2048 <= 232448) ? 4 : 3;
+  static constexpr int kStagesFit = (232448 - 2048 - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kBarrierBytes = (2 * kStages + 4 + kEpiWarps) * 8 + 16;
   static constexpr int kTotal = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
@@ -107,18 +113,20 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
 }
 
 // tmap_o: output box map (bf16 {64,32} or fp32 {32,32}); tmap_x: second output (GELU') or residual / aux input.
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TWO>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_x,
                  const GemmParams p) {
-  using S = GemmSmem<BLOCK_N, EPI>;
+  using S = GemmSmem<BLOCK_N, EPI, TWO>;
+  static_assert(!TWO || S::kTmaEpi, "CTA pairs are implemented for the TMA-box epilogues only");
   constexpr int kStages = S::kStages;
+  constexpr int kPair = TWO ? 2 : 1;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                // [kStages][16 KB]
-  uint8_t* smem_b = smem + kStages * S::kABytes;          // [kStages][BLOCK_N*128 B]
+  uint8_t* smem_b = smem + kStages * S::kABytes;          // [kStages][kLoadN*128 B]
   uint8_t* epi_smem = smem + kStages * S::kStageBytes;    // boxes (TMA epilogues) or transpose staging (generic)
   float* staging = reinterpret_cast<float*>(epi_smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + S::kEpiBytes);
@@ -140,23 +148,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if constexpr (S::kTmaEpi && S::kBoxes == 2) tma_prefetch_desc(&tmap_x);
     }
     __syncwarp();
-    tmem_alloc<kTmemCols>(tmem_slot);
+    if constexpr (TWO) tmem_alloc_pair<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kPair);             // pair: the producers of both CTAs arrive on the leader's barrier
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps);
+      mbar_init(&tmem_empty_bar[i], kPair * kEpiWarps);   // pair: the epilogue warps of both CTAs release the leader
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+  const int worker = TWO ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int num_workers = TWO ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_mn * p.split_k;
@@ -166,7 +179,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int split = tile / tiles_mn;
         const int mn = tile - split * tiles_mn;
         const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
@@ -176,35 +189,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_a + stage * S::kABytes;
           uint8_t* sb = smem_b + stage * S::kBBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          } else {
+          const int m_row = (m_blk * kPair + static_cast<int>(cta_rank)) * BLOCK_M;        // this CTA's 128 rows of A / D
+          const int n_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * S::kLoadN;     // this CTA's part of the B tile
+          if constexpr (!TWO) {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-          } else {
+              for (int i = 0; i < BLOCK_M / 64; ++i)
+                tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_row + i * 64, kb * BLOCK_K);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+              for (int i = 0; i < S::kLoadN / 64; ++i)
+                tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_row + i * 64, kb * BLOCK_K);
+            }
+          } else {
+            // both CTAs count their bytes on the LEADER's barrier (the leader's MMA thread consumes both halves)
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0u);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            else mbar_arrive_cluster(lead_bar);
+            if constexpr (!A_MN) {
+              tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * BLOCK_K, m_row);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i)
+                tma_load_2d_pair(sa + i * (BLOCK_K * 128), &tmap_a, lead_bar, m_row + i * 64, kb * BLOCK_K);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_pair(sb, &tmap_b, lead_bar, kb * BLOCK_K, n_row);
+            } else {
+#pragma unroll
+              for (int i = 0; i < S::kLoadN / 64; ++i)
+                tma_load_2d_pair(sb + i * (BLOCK_K * 128), &tmap_b, lead_bar, n_row + i * 64, kb * BLOCK_K);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(kPair * BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
     // K-major: 8-row groups 1024 B apart; k-step of 16 elements = 32 B inside the swizzle row.
     // MN-major: 8-k-row groups 1024 B apart, 64-wide MN atoms BLOCK_K*128 B apart; k-step of 16 rows = 2048 B.
     constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 0, b_lbo = B_MN ? BLOCK_K * 128 : 0;
     constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2, b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
     uint32_t stage = 0, phase = 0;
     int local_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
       const int split = tile / tiles_mn;
       const int kb0 = split * kb_per_split;
       const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
@@ -223,15 +259,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (kb == kb1 - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
+          if constexpr (TWO) {
+            tc_commit_pair(&empty_bar[stage]);                       // frees the slot in both CTAs
+            if (kb == kb1 - 1) tc_commit_pair(&tmem_full_bar[acc]);  // both epilogues may start
+          } else {
+            tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+            if (kb == kb1 - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp == 1) {
+    // pair, non-leader CTA: the leader issues the MMAs for both
   } else if constexpr (S::kTmaEpi) {
     // ------------------------------------------------------------------ epilogue warps, TMA boxes
     // lane = accumulator row (tcgen05.ld 32x32b), CW consecutive columns per chunk in registers. The row is written
@@ -251,13 +295,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* my_in_bar = &in_bar[warp - 2];
     uint32_t in_count = 0;                  // input boxes consumed so far (mbarrier parity)
     int local_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
       const uint32_t acc = local_iter & 1;
       const uint32_t acc_phase = (local_iter >> 1) & 1;
-      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row0 = (m_blk * kPair + static_cast<int>(cta_rank)) * BLOCK_M + q * 32;
       const int col0 = n_blk * BLOCK_N;
       const bool first_split = (split == 0);
       const bool use_bias = (EPI == EPI_BF16 || EPI == EPI_F32_RES || EPI == EPI_GELU) && p.bias != nullptr && first_split;
@@ -283,7 +327,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0u));
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         uint4 xin[8];
         if constexpr (kHasIn) {
@@ -392,7 +439,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int kChunks = BLOCK_N / kChunk;
     constexpr bool kGeneric = EPI == EPI_GENERIC;
     int local_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_iter) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
@@ -491,10 +538,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all();          // the peer may still be reading operands / signalling barriers here
+  else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (TWO) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -577,15 +626,16 @@ static int pick_epi(const oat_gemm_args* a) {
   return EPI_GENERIC;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TWO>
 static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, EPI>;
+  using S = GemmSmem<BLOCK_N, EPI, TWO>;
+  constexpr int kPair = TWO ? 2 : 1;
   CUtensorMap ta, tb, to, tx;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&ta, a->A, a->K, a->M, a->lda, BLOCK_M);
   else rc = make_tmap_bf16_2d(&ta, a->A, a->M, a->K, a->lda, BLOCK_K);
   if (rc != OAT_OK) return rc;
-  if (!B_MN) rc = make_tmap_bf16_2d(&tb, a->B, a->K, a->N, a->ldb, BLOCK_N);
+  if (!B_MN) rc = make_tmap_bf16_2d(&tb, a->B, a->K, a->N, a->ldb, S::kLoadN);
   else rc = make_tmap_bf16_2d(&tb, a->B, a->N, a->K, a->ldb, BLOCK_K);
   if (rc != OAT_OK) return rc;
   to = ta;
@@ -600,12 +650,12 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
 
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
-  p.num_m_blocks = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_blocks = (a->M + kPair * BLOCK_M - 1) / (kPair * BLOCK_M);
   p.num_n_blocks = (a->N + BLOCK_N - 1) / BLOCK_N;
   p.k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
-  const int sms = num_sms();
+  const int workers = num_sms() / kPair;          // CTAs, or CTA pairs
   const bool can_split = a->accumulate && a->out_f32 != nullptr && a->out_bf16 == nullptr && a->act == 0;
-  p.split_k = (a->split_k == 0 && !can_split) ? 1 : pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, sms, a->split_k);
+  p.split_k = (a->split_k == 0 && !can_split) ? 1 : pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, workers, a->split_k);
   {  // no empty splits
     const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
     p.split_k = (p.k_blocks + per - 1) / per;
@@ -620,7 +670,7 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
   p.accumulate = a->accumulate;
 
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -628,9 +678,33 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   const long long tiles = 1LL * p.num_m_blocks * p.num_n_blocks * p.split_k;
-  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, to, tx, p);
+  const int nwork = static_cast<int>(tiles < workers ? tiles : workers);
+  if constexpr (!TWO) {
+    kern<<<nwork, kGemmThreads, S::kTotal, stream>>>(ta, tb, to, tx, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nwork, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "gemm_bf16_kernel (CTA pair) launch: %s", cudaGetErrorString(e));
+  }
   return check_launch("gemm_bf16_kernel");
+}
+
+// CTA pairs for every problem with more than one 128-row block; OAT_GEMM_2CTA=0 keeps every launch on single CTAs.
+static bool use_pairs(const oat_gemm_args* a, int epi) {
+  const char* env = getenv("OAT_GEMM_2CTA");
+  const bool enabled = env == nullptr || atoi(env) != 0;
+  return enabled && epi != EPI_GENERIC && a->M > BLOCK_M;
 }
 
 }  // namespace oat
@@ -651,21 +725,23 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
   const int code = (amn ? 2 : 0) | (bmn ? 1 : 0);
   if (!wide) {
     switch (code) {
-      case 0: return launch_gemm<128, false, false, EPI_GENERIC>(a, s);
-      case 1: return launch_gemm<128, false, true, EPI_GENERIC>(a, s);
-      case 2: return launch_gemm<128, true, false, EPI_GENERIC>(a, s);
-      default: return launch_gemm<128, true, true, EPI_GENERIC>(a, s);
+      case 0: return launch_gemm<128, false, false, EPI_GENERIC, false>(a, s);
+      case 1: return launch_gemm<128, false, true, EPI_GENERIC, false>(a, s);
+      case 2: return launch_gemm<128, true, false, EPI_GENERIC, false>(a, s);
+      default: return launch_gemm<128, true, true, EPI_GENERIC, false>(a, s);
     }
   }
   const int epi = pick_epi(a);
+  const bool two = use_pairs(a, epi);
+#define OAT_GEMM_EPI(AM, BM, E) return two ? launch_gemm<256, AM, BM, E, true>(a, s) : launch_gemm<256, AM, BM, E, false>(a, s)
 #define OAT_GEMM_CASE(AM, BM)                                                         \
   switch (epi) {                                                                      \
-    case EPI_BF16: return launch_gemm<256, AM, BM, EPI_BF16>(a, s);                   \
-    case EPI_F32_RES: return launch_gemm<256, AM, BM, EPI_F32_RES>(a, s);             \
-    case EPI_GELU: return launch_gemm<256, AM, BM, EPI_GELU>(a, s);                   \
-    case EPI_MULAUX: return launch_gemm<256, AM, BM, EPI_MULAUX>(a, s);               \
-    case EPI_ATOMIC: return launch_gemm<256, AM, BM, EPI_ATOMIC>(a, s);               \
-    default: return launch_gemm<256, AM, BM, EPI_GENERIC>(a, s);                      \
+    case EPI_BF16: OAT_GEMM_EPI(AM, BM, EPI_BF16);                                    \
+    case EPI_F32_RES: OAT_GEMM_EPI(AM, BM, EPI_F32_RES);                              \
+    case EPI_GELU: OAT_GEMM_EPI(AM, BM, EPI_GELU);                                    \
+    case EPI_MULAUX: OAT_GEMM_EPI(AM, BM, EPI_MULAUX);                                \
+    case EPI_ATOMIC: OAT_GEMM_EPI(AM, BM, EPI_ATOMIC);                                \
+    default: return launch_gemm<256, AM, BM, EPI_GENERIC, false>(a, s);               \
   }
   switch (code) {
     case 0: OAT_GEMM_CASE(false, false)
@@ -674,4 +750,5 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
     default: OAT_GEMM_CASE(true, true)
   }
 #undef OAT_GEMM_CASE
+#undef OAT_GEMM_EPI
 }

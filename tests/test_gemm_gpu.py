@@ -132,3 +132,40 @@ def test_gemm_tma_epilogue_bf16_bias_qscale(scale_cols):
     ref[:, :scale_cols] *= 0.125
     assert torch.allclose(out[:M].float(), ref, rtol=1e-2, atol=2e-2)
     assert bool((out[M:].float() == 3.0).all())
+
+
+@pytest.mark.parametrize("pairs", ["1", "0"])
+def test_gemm_cta_pairs_and_single_cta_agree(pairs, monkeypatch):
+    """Every specialised epilogue through CTA pairs (cta_group::2, default) and through single CTAs (OAT_GEMM_2CTA=0)."""
+    from oa_transformer_b200 import ops
+    monkeypatch.setenv("OAT_GEMM_2CTA", pairs)
+    M, N, K = 128 * 75 + 40, 768, 768            # odd number of 128-row blocks: the last pair has an empty second CTA
+    A, B = _mk((M, K), 31), _mk((N, K), 32)
+    B = (B.float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = torch.randn(M, N, device="cuda")
+    ref = A.float() @ B.float().t()
+    o32 = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, bias=bias, residual=res, out_f32=o32)
+    assert torch.allclose(o32, ref + bias + res, rtol=1e-3, atol=2e-3)
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, scale_cols=256, scale=0.125, out_bf16=o16)
+    r2 = ref + bias
+    r2[:, :256] *= 0.125
+    assert torch.allclose(o16.float(), r2, rtol=1e-2, atol=2e-2)
+    g16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    d16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_bf16=g16, out2_bf16=d16)
+    assert torch.allclose(g16.float(), torch.nn.functional.gelu(ref + bias), rtol=1e-2, atol=1e-2)
+    m16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, b_major=0, act=ops.ACT_GELU_BWD, aux=d16, out_bf16=m16)
+    assert torch.allclose(m16.float(), ref * d16.float(), rtol=2e-2, atol=2e-2)
+    # MN-major operands + split-K reduce-add (weight-gradient shape): dW[N, K] += dY[M, N]^T X[M, K]
+    dW = torch.ones(N, K, device="cuda")
+    ops.gemm(o16, A, a_major=1, b_major=1, out_f32=dW, accumulate=True)
+    refw = o16.float().t() @ A.float() + 1.0
+    assert (dW - refw).abs().max().item() <= 2e-3 * refw.abs().max().item() + 2e-2
+    # dgrad shape: B MN-major
+    dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(o16, B, b_major=1, out_bf16=dx)
+    assert torch.allclose(dx.float(), o16.float() @ B.float(), rtol=2e-2, atol=5e-2)
