@@ -200,8 +200,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive. Default semantics (release at CTA scope): a `.release.cluster` arrive compiles to MEMBAR.ALL + ERRBAR,
+// which drains the thread's outstanding memory traffic (TMA stores included) on every call - measured 3x slower GEMM.
+// The data these arrivals order (TMEM reads, TMA transactions) is synchronised by tcgen05 fences / complete_tx.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the mbarrier at
 // `mbar_cluster_addr` (the leader CTA's barrier, a shared::cluster address)
