@@ -402,7 +402,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < 8; ++j) {
             float g[8], d[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) gelu_fwd_grad(__uint_as_float(v[8 * j + k]), g[k], d[k]);
+            for (int k = 0; k < 8; k += 2)
+              gelu_fwd_grad2(__uint_as_float(v[8 * j + k]), __uint_as_float(v[8 * j + k + 1]), g[k], g[k + 1], d[k], d[k + 1]);
             const uint32_t off = (static_cast<uint32_t>(j) << 4) ^ row_sw;
             sts128(my_o + off, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
             sts128(my_x + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
