@@ -175,6 +175,14 @@ int oat_patch_masks_from_bbox(const double* boxes, int32_t stride, float* masks,
 int oat_retrieval_ranks(const float* sims, int32_t n, int64_t ld, float* t2v_rank, float* v2t_rank,
                         oat_stream_t stream);
 
+/* ---- optimizer step (the step right after the path) ------------------------------------------------
+ * Fused multi-tensor AdamW with transformers.AdamW semantics (train_dist_multi.py:66 builds the optimizer from the
+ * `transformers` module): table[n][4] = device pointers (p, g, m, v), all fp32; sizes[n] = element counts;
+ * chunk_prefix[n+1] = prefix sum of ceil(size / 1024). All three tables live in DEVICE memory. `step` is 1-based. */
+int oat_adamw_multi(const int64_t* table, const int64_t* chunk_prefix, const int64_t* sizes, int32_t n,
+                    int64_t total_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int32_t step, int32_t correct_bias, oat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -334,8 +334,8 @@ __device__ __forceinline__ void gelu_fwd_grad2(float x0, float x1, float& g0, fl
   const uint64_t e = f2_pack(e0, e1);
   float t0, t1;
   f2_unpack(f2_fma(f2_pack(fabsf(x0), fabsf(x1)), f2_pack(0.23164189f, 0.23164189f), f2_pack(1.0f, 1.0f)), t0, t1);  // 1 + 0.3275911 |x| / sqrt2
-  t0 = __fdividef(1.0f, t0);
-  t1 = __fdividef(1.0f, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t0) : "f"(t0));   // denominators are in [1, inf): no special cases needed
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(t1) : "f"(t1));
   const uint64_t t = f2_pack(t0, t1);
   // -poly(t) (negated coefficients, so that 1 - poly * e is one fma)
   uint64_t p = f2_fma(t, f2_pack(-1.061405429f, -1.061405429f), f2_pack(1.453152027f, 1.453152027f));

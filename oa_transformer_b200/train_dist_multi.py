@@ -56,7 +56,11 @@ def run(config, args):
     metrics = [getattr(module_metric, met) for met in config['metrics']]
     trainable = [p for p in model.parameters() if p.requires_grad]
     import transformers
-    opt_module = transformers if hasattr(transformers, config['optimizer']['type']) else torch.optim
+    # `transformers.AdamW` (what the reference's configs name) is gone in transformers 5.x: the fused liboat AdamW keeps
+    # its semantics; any other optimizer type resolves in transformers / torch.optim as before
+    from oa_transformer_b200 import optim as oat_optim
+    opt_module = oat_optim if hasattr(oat_optim, config['optimizer']['type']) else (
+        transformers if hasattr(transformers, config['optimizer']['type']) else torch.optim)
     optimizer = config.initialize('optimizer', opt_module, trainable)
     trainer = Multi_Trainer_dist(args, model, loss, metrics, optimizer, config=config, data_loader=data_loader,
                                  valid_data_loader=valid_data_loader, tokenizer=tokenizer,

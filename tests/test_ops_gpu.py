@@ -326,3 +326,37 @@ def test_retrieval_metrics_device_matches_host(n, ties):
         assert host.keys() == devm.keys()
         for k in host:
             assert host[k] == devm[k], (fn.__name__, k, host[k], devm[k])
+
+
+@pytest.mark.parametrize("correct_bias,wd", [(True, 0.0), (False, 0.01), (True, 0.05)])
+def test_fused_adamw_matches_transformers_semantics(correct_bias, wd):
+    """oat_adamw_multi vs a plain-torch restatement of transformers.AdamW.step (optimization.py, 4.6), several steps,
+    odd sizes and an unaligned view (scalar tail path)."""
+    from oa_transformer_b200.optim import AdamW
+    g = gen(41)
+    flat = torch.randn(5000, generator=g).cuda()
+    shapes = [(768, 33), (1,), (1027,), (256, 768)]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    params.append(torch.nn.Parameter(flat[1:1 + 999]))            # 4-byte aligned only
+    ref = [p.detach().clone() for p in params]
+    m = [torch.zeros_like(p) for p in ref]
+    v = [torch.zeros_like(p) for p in ref]
+    lr, b1, b2, eps = 3e-3, 0.9, 0.999, 1e-6
+    opt = AdamW(params, lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd, correct_bias=correct_bias)
+    for step in range(1, 4):
+        grads = [torch.randn(p.shape, generator=g).cuda() * 0.1 for p in params]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        opt.step()
+        for i, gr in enumerate(grads):
+            m[i].mul_(b1).add_(gr, alpha=1 - b1)
+            v[i].mul_(b2).addcmul_(gr, gr, value=1 - b2)
+            step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step) if correct_bias else lr
+            ref[i].addcdiv_(m[i], v[i].sqrt().add_(eps), value=-step_size)
+            if wd > 0:
+                ref[i].add_(ref[i], alpha=-lr * wd)
+    torch.cuda.synchronize()
+    for p, r in zip(params, ref):
+        assert torch.allclose(p.detach(), r, rtol=2e-6, atol=2e-7), (p.shape, (p.detach() - r).abs().max())
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 3 and sd["state"][0]["exp_avg"].shape == (768, 33)
