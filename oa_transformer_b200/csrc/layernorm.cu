@@ -155,6 +155,141 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb,
   }
 }
 
+// Same arithmetic with the row operands staged through shared memory by cp.async, double-buffered per warp: while a
+// warp reduces / writes row r, the 14 bytes per column of row r + stride (x, dy, the two residual-gradient addends)
+// are already in flight - 86 KB of loads per SM instead of what 8 warps x one row can keep outstanding from
+// registers (the register version sits at 239 registers, one 8-warp CTA per SM, ~70 % of the HBM roofline).
+// Slots per stage: x fp32 | f0 fp32 (add1, or dy_f32 for the post-LN text tower) | f1 fp32 (add2) | dy bf16.
+__device__ __forceinline__ void ln_cp16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32, 1)
+layernorm_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long lddyb, const float* __restrict__ dy_f32,
+                            long long lddyf, const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows,
+                            const float* __restrict__ add1, const float* __restrict__ add2, long long ldadd,
+                            float* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dx_bf16, long long lddxb,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
+  constexpr int D = NV * 128;
+  constexpr int kRowBytes = D * 14;
+  extern __shared__ __align__(16) uint8_t ln_smem[];
+  float(*red)[D] = reinterpret_cast<float(*)[D]>(ln_smem);                       // [kLnWarps][D]
+  float* s_gamma = reinterpret_cast<float*>(ln_smem + kLnWarps * D * 4);           // [D]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* stage = ln_smem + (kLnWarps + 1) * D * 4 + warp * 2 * kRowBytes;
+  const float* f0 = dy_f32 != nullptr ? dy_f32 : add1;
+  const long long ldf0 = dy_f32 != nullptr ? lddyf : ldadd;
+  const float* f1 = dy_f32 != nullptr ? nullptr : add2;
+  const bool f0_is_dy = dy_f32 != nullptr;
+  for (int c = threadIdx.x; c < D; c += kLnWarps * 32) s_gamma[c] = gamma[c];
+  float4 dg[NV], db[NV], ds[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  auto issue = [&](long long row, int buf) {
+    uint8_t* b = stage + buf * kRowBytes;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      ln_cp16(b + c * 16, x + row * ldx + c * 4);
+      if (f0 != nullptr) ln_cp16(b + D * 4 + c * 16, f0 + row * ldf0 + c * 4);
+      if (f1 != nullptr) ln_cp16(b + D * 8 + c * 16, f1 + row * ldadd + c * 4);
+    }
+    if (dy_bf16 != nullptr) {
+      for (int c = lane; c < NV * 16; c += 32) ln_cp16(b + D * 12 + c * 16, dy_bf16 + row * lddyb + c * 8);
+    }
+  };
+  const long long stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  long long row = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  if (row < rows) issue(row, 0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  __syncthreads();                                            // s_gamma
+  int buf = 0;
+  for (; row < rows; row += stride, buf ^= 1) {
+    if (row + stride < rows) issue(row + stride, buf ^ 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncwarp();
+    const uint8_t* b = stage + buf * kRowBytes;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      const float4 xv = *reinterpret_cast<const float4*>(b + c * 16);
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy_bf16 != nullptr) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(b + D * 12 + c * 8);
+        const float2 a = unpack_bf16x2(raw.x), bb = unpack_bf16x2(raw.y);
+        d = make_float4(a.x, a.y, bb.x, bb.y);
+      }
+      if (f0_is_dy) {
+        const float4 f = *reinterpret_cast<const float4*>(b + D * 4 + c * 16);
+        d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+      }
+      const float4 gm = *reinterpret_cast<const float4*>(s_gamma + c * 4);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      float4 o;
+      o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+      o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+      o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+      o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+      if (!f0_is_dy && f0 != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(b + D * 4 + c * 16);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (f1 != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(b + D * 8 + c * 16);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
+      if (dx != nullptr) reinterpret_cast<float4*>(dx + row * lddx)[c] = o;
+      if (dx_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * lddxb)[c] = pk;
+      }
+    }
+    __syncwarp();                                             // this stage is refilled by the next iteration's prefetch
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  if (dgamma == nullptr && dbeta == nullptr && dxsum == nullptr) return;
+  for (int pass = 0; pass < 3; ++pass) {
+    float4* src = pass == 0 ? dg : (pass == 1 ? db : ds);
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(red[warp])[i * 32 + lane] = src[i];
+    __syncthreads();
+    if (dst != nullptr) {
+      for (int c = threadIdx.x; c < D; c += kLnWarps * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) acc += red[w][c];
+        atomicAdd(dst + c, acc);
+      }
+    }
+  }
+}
+
 template <int NV>
 static int launch_ln_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                          long long rows, void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean,
@@ -171,7 +306,28 @@ static int launch_ln_bwd(const void* dyb, long long lddyb, const float* dyf, lon
                          long long ldx, const float* mean, const float* rstd, const float* gamma, long long rows,
                          const float* add1, const float* add2, long long ldadd, float* dx, long long lddx,
                          void* dxb, long long lddxb, float* dgamma, float* dbeta, float* dxsum, cudaStream_t s) {
+  constexpr int D = NV * 128;
   long long want = (rows + kLnWarps - 1) / kLnWarps;
+  const bool aligned = ldx % 4 == 0 && (dyb == nullptr || (lddyb % 8 == 0 && (reinterpret_cast<uintptr_t>(dyb) & 15) == 0)) &&
+                       (dyf == nullptr || (lddyf % 4 == 0 && (reinterpret_cast<uintptr_t>(dyf) & 15) == 0)) &&
+                       ((add1 == nullptr && add2 == nullptr) || ldadd % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(add1) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(add2) & 15) == 0 && !(dyf != nullptr && (add1 != nullptr || add2 != nullptr));
+  constexpr int smem = (kLnWarps + 1) * D * 4 + kLnWarps * 2 * D * 14;
+  if (smem <= 227 * 1024 && aligned && rows >= 4 * kLnWarps) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_staged_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "layernorm_bwd smem attr: %s", cudaGetErrorString(e));
+      attr_done = true;
+    }
+    const long long cap1 = static_cast<long long>(num_sms());
+    const unsigned grid1 = static_cast<unsigned>(want < cap1 ? want : cap1);
+    layernorm_bwd_staged_kernel<NV><<<grid1, kLnWarps * 32, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dyb), lddyb, dyf, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2,
+        ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, dxsum);
+    return check_launch("layernorm_bwd_staged_kernel");
+  }
   const long long cap = static_cast<long long>(num_sms()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(

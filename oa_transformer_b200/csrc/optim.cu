@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
                                                          const long long* __restrict__ chunk_prefix,  // [n + 1]
                                                          const long long* __restrict__ sizes,         // [n]
                                                          int n, long long total_chunks, float lr, float b1, float b2,
-                                                         float eps, float wd, float step_size) {
+                                                         float omb1, float omb2, float eps, float wd, float step_size) {
   for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int lo = 0, hi = n - 1;                       // last tensor whose first chunk is <= chunk
     while (lo < hi) {
@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      mv[i] = b1 * mv[i] + (1.f - b1) * gv[i];
-      vv[i] = b2 * vv[i] + (1.f - b2) * gv[i] * gv[i];
+      mv[i] = b1 * mv[i] + omb1 * gv[i];
+      vv[i] = b2 * vv[i] + omb2 * gv[i] * gv[i];
       pv[i] = pv[i] - step_size * (mv[i] / (sqrtf(vv[i]) + eps));
       if (wd > 0.f) pv[i] = pv[i] - lr * wd * pv[i];
     }
@@ -81,6 +81,7 @@ extern "C" int oat_adamw_multi(const int64_t* table, const int64_t* chunk_prefix
   adamw_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(table),
                                                           reinterpret_cast<const long long*>(chunk_prefix),
                                                           reinterpret_cast<const long long*>(sizes), n, total_chunks, lr,
-                                                          beta1, beta2, eps, weight_decay, step_size);
+                                                          beta1, beta2, static_cast<float>(1.0 - static_cast<double>(beta1)),
+                                                          static_cast<float>(1.0 - static_cast<double>(beta2)), eps, weight_decay, step_size);
   return check_launch("adamw_multi_kernel");
 }

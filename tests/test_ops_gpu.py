@@ -57,6 +57,39 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     assert rel(dxsum, dx.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("variant", ["adds", "add1", "plain", "text"])
+@pytest.mark.parametrize("rows,D", [(5000, 768), (8 * 148 + 3, 768), (100, 256)])
+def test_layernorm_bwd_staged_variants(rows, D, variant):
+    """The cp.async double-buffered backward (the operand combinations the two towers use) vs torch autograd."""
+    from oa_transformer_b200 import ops
+    g = gen(2)
+    x = (torch.randn(rows, D, generator=g) * 2 + 0.5).cuda()
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).cuda()
+    beta = (0.1 * torch.randn(D, generator=g)).cuda()
+    mean = torch.empty(rows, device="cuda")
+    rstd = torch.empty(rows, device="cuda")
+    y16 = torch.empty(rows, D, device="cuda", dtype=BF)
+    ops.layernorm_fwd(x, gamma, beta, 1e-6, y_bf16=y16, mean=mean, rstd=rstd)
+    dy16 = torch.randn(rows, D, generator=g).to(BF).cuda()
+    dy32 = torch.randn(rows, D, generator=g).cuda() if variant == "text" else None
+    add1 = torch.randn(rows, D, generator=g).cuda() if variant in ("adds", "add1") else None
+    add2 = torch.randn(rows, D, generator=g).cuda() if variant == "adds" else None
+    dx = torch.empty(rows, D, device="cuda")
+    dx16 = torch.empty(rows, D, device="cuda", dtype=BF)
+    dgamma, dbeta, dxsum = (torch.zeros(D, device="cuda") for _ in range(3))
+    ops.layernorm_bwd(x, mean, rstd, gamma, dy_bf16=dy16, dy_f32=dy32, add1=add1, add2=add2, dx=dx, dx_bf16=dx16,
+                      dgamma=dgamma, dbeta=dbeta, dxsum=dxsum)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
+    ref.backward(dy16.float() + (dy32 if dy32 is not None else 0))
+    want = xr.grad + (add1 if add1 is not None else 0) + (add2 if add2 is not None else 0)
+    assert rel(dx, want) < 1e-5
+    assert rel(dx16.float(), want) < 5e-3
+    assert rel(dgamma, gr.grad) < 1e-4 and rel(dbeta, br.grad) < 1e-4
+    assert rel(dxsum, dx.sum(0)) < 1e-4
+
+
 def test_layernorm_strided_cls_rows():
     from oa_transformer_b200 import ops
     B, T, D = 5, 33, 768
@@ -357,6 +390,6 @@ def test_fused_adamw_matches_transformers_semantics(correct_bias, wd):
                 ref[i].add_(ref[i], alpha=-lr * wd)
     torch.cuda.synchronize()
     for p, r in zip(params, ref):
-        assert torch.allclose(p.detach(), r, rtol=2e-6, atol=2e-7), (p.shape, (p.detach() - r).abs().max())
+        assert torch.allclose(p.detach(), r, rtol=2e-6, atol=1e-6), (p.shape, (p.detach() - r).abs().max())
     sd = opt.state_dict()
     assert sd["state"][0]["step"] == 3 and sd["state"][0]["exp_avg"].shape == (768, 33)
