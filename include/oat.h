@@ -119,6 +119,11 @@ int oat_attn_bwd(const oat_attn_args* args, oat_stream_t stream);
  * oat_text_embed(_bwd): DistilBERT word + position embedding sum and its scatter-add gradient. */
 int oat_cast_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
                   int32_t cols_padded, int32_t relu, oat_stream_t stream);
+/* Many casts in one launch. table[n][8] (device memory) = {src fp32*, dst*, rows, cols, cols_padded, src pitch,
+ * dst pitch, dst_is_f32}; chunk_prefix[n+1] = prefix sum of ceil(rows * cols_padded / 1024). Same element semantics as
+ * oat_cast_bf16 (dst_is_f32 rows are plain fp32 copies, used to pack q/k/v biases). */
+int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,
+                   oat_stream_t stream);
 int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,
                  int64_t rows, int32_t cols, oat_stream_t stream);
 int oat_im2col_patches(const float* video, void* out_bf16, int64_t BF, int32_t C, int32_t H, int32_t W, int32_t P,

@@ -41,6 +41,47 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, _
   }
 }
 
+// Many casts in one launch (the bf16 operand copies of every weight of a tower, re-packed each step): a device table
+// row = {src, dst, rows, cols, cols_padded, src pitch, dst pitch, dst_is_f32}, chunk_prefix = prefix sum of the
+// 1024-element chunks of each tensor's padded (rows x cols_padded) extent. dst_is_f32 rows are plain copies (bias packing).
+__global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __restrict__ table,
+                                                        const long long* __restrict__ chunk_prefix, int n,
+                                                        long long total_chunks) {
+  for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (chunk_prefix[mid] <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const long long* t = table + 8 * lo;
+    const float* src = reinterpret_cast<const float*>(t[0]);
+    const long long rows = t[2], cols = t[3], colsp = t[4], lds = t[5], ldd = t[6];
+    const long long idx = (chunk - chunk_prefix[lo]) * 1024 + threadIdx.x * 4;      // over rows x cols_padded
+    if (idx >= rows * colsp) continue;
+    const long long r = idx / colsp;
+    const long long c = idx - r * colsp;                                            // multiple of 4 (cols_padded % 4 == 0)
+    float v[4];
+    const float* sp = src + r * lds + c;
+    if (c + 3 < cols && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+      const float4 f = *reinterpret_cast<const float4*>(sp);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < cols) ? sp[k] : 0.f;
+    }
+    if (t[7] != 0) {
+      float* d = reinterpret_cast<float*>(t[1]) + r * ldd + c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = v[k];
+    } else {
+      uint2 pk;
+      pk.x = pack_bf16x2(v[0], v[1]);
+      pk.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t[1]) + r * ldd + c) = pk;
+    }
+  }
+}
+
 // dx[r, c] = relu_mask(x[r, c]) * dy_bf16[r, c]  (fp32 out) - backward of the ReLU in txt_proj (oa_model.py:68)
 __global__ void relu_bwd_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
                                 long long lddy, float* __restrict__ dx, long long lddx, long long rows, int cols) {
@@ -166,9 +207,10 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a 256-row slab; a thread owns 8 adjacent columns
-// (one 16-byte load per row) and keeps 8 independent loads in flight.
-constexpr int kColsumRowsPerCta = 256;
+// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a 64-row slab (929 slabs at M = 59424: every CTA of
+// the grid is resident at once, no partial last wave); a thread owns 8 adjacent columns (one 16-byte load per row) and
+// keeps 8 independent loads in flight.
+constexpr int kColsumRowsPerCta = 64;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                           long long rows, int cols, float* __restrict__ out) {
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
@@ -256,6 +298,16 @@ extern "C" int oat_cast_bf16(const float* src, int64_t lds, void* dst, int64_t l
   cast_bf16_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
       src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded, relu);
   return check_launch("cast_bf16_kernel");
+}
+
+extern "C" int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,
+                              oat_stream_t stream) {
+  OAT_REQUIRE(table != nullptr && chunk_prefix != nullptr && n > 0 && total_chunks > 0, "oat_cast_multi: bad arguments");
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const unsigned grid = static_cast<unsigned>(total_chunks < cap ? total_chunks : cap);
+  cast_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(table),
+                                                         reinterpret_cast<const long long*>(chunk_prefix), n, total_chunks);
+  return check_launch("cast_multi_kernel");
 }
 
 extern "C" int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,

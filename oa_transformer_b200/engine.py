@@ -45,13 +45,17 @@ class _Buffers:
         return t
 
 
-def _w16(bufs, name, w, rows=None, cols=None, pitch=None):
-    """bf16 operand copy of an fp32 weight (re-packed every step: the optimizer owns the fp32 master)."""
+def _w16(bufs, name, w, rows=None, cols=None, pitch=None, plan=None):
+    """bf16 operand copy of an fp32 weight (re-packed every step: the optimizer owns the fp32 master). With a CastPlan
+    the copy is only registered; plan.run() performs every registered copy of the tower in one launch."""
     w2 = w.detach().reshape(w.shape[0], -1)
     rows = w2.shape[0] if rows is None else rows
     cols = w2.shape[1] if cols is None else cols
     dst = bufs.get(name, (rows, pitch or cols), BF)
-    ops.cast_bf16(w2, dst, rows=rows, cols=cols)
+    if plan is not None:
+        plan.add(w2, dst, rows=rows, cols=cols)
+    else:
+        ops.cast_bf16(w2, dst, rows=rows, cols=cols)
     return dst
 
 
@@ -87,6 +91,7 @@ class VideoEngine:
         self.bufs = _Buffers(device)
         self.saved = None
         self._side = None
+        self._plan = ops.CastPlan()
 
     # ------------------------------------------------------------------ forward
     def forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
@@ -111,11 +116,27 @@ class VideoEngine:
             depth += 1
         video = video.contiguous()
 
+        # --- bf16 operand copies of every weight of the tower: one launch
+        plan = self._plan
+        W = {"patch": _w16(bufs, "w.patch", p[prefix + "patch_embed.proj.weight"], plan=plan)}
+        if O > 0:
+            W["object"] = _w16(bufs, "w.object", p[prefix + "object_embed.weight"], pitch=OBJ_PITCH, plan=plan)
+        for i in range(depth):
+            b = "%sblocks.%d." % (prefix, i)
+            for tag, aname in (("t", "timeattn"), ("s", "attn")):
+                W[(i, tag, "qkv")] = _w16(bufs, "w.%s.qkv.%d" % (tag, i), p[b + aname + ".qkv.weight"], plan=plan)
+                W[(i, tag, "proj")] = _w16(bufs, "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"], plan=plan)
+            W[(i, "fc1")] = _w16(bufs, "w.fc1.%d" % i, p[b + "mlp.fc1.weight"], plan=plan)
+            W[(i, "fc2")] = _w16(bufs, "w.fc2.%d" % i, p[b + "mlp.fc2.weight"], plan=plan)
+        if proj is not None:
+            W["vid_proj"] = _w16(bufs, "w.vid_proj", p[proj[0]], plan=plan)
+        plan.run()
+
         # --- patch / object embedding + token assembly (video_transformer.py:71-76, 303-325)
         K0 = C * ps * ps
         cols = bufs.get("cols", (B * Fr * N, K0), BF)
         ops.im2col_patches(video, cols, ps)
-        wp = _w16(bufs, "w.patch", p[prefix + "patch_embed.proj.weight"])
+        wp = W["patch"]
         patch = bufs.get("patch", (B * Fr * N, D), F32)
         ops.gemm(cols, wp, bias=p[prefix + "patch_embed.proj.bias"], out_f32=patch)
         objemb = obj16 = None
@@ -123,7 +144,7 @@ class VideoEngine:
             assert objects.shape[-1] == OBJ_DIM
             obj16 = bufs.get("obj16", (B * Fr * O, OBJ_PITCH), BF)
             ops.cast_bf16(objects.contiguous().reshape(-1, OBJ_DIM), obj16)
-            wo = _w16(bufs, "w.object", p[prefix + "object_embed.weight"], pitch=OBJ_PITCH)
+            wo = W["object"]
             objemb = bufs.get("objemb", (B * Fr * O, D), F32)
             ops.gemm(obj16, wo, bias=p[prefix + "object_embed.bias"], out_f32=objemb)
         type_embed = p.get(prefix + "token_type_embeddings.weight")
@@ -146,7 +167,7 @@ class VideoEngine:
                 return h, mean, rstd
 
             def attention(tag, mode, h, aname, resid, out):
-                wqkv = _w16(bufs, "w.%s.qkv.%d" % (tag, i), p[b + aname + ".qkv.weight"])
+                wqkv = W[(i, tag, "qkv")]
                 qkv = bufs.get("qkv%s.%d" % (tag, i), (M, 3 * D), BF)
                 ops.gemm(h, wqkv, bias=p[b + aname + ".qkv.bias"], scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
                 a = bufs.get("a%s.%d" % (tag, i), (M, D), BF)
@@ -154,7 +175,7 @@ class VideoEngine:
                 ws = bufs.get("attn_ws", (max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, Fr, n),
                                               ops.attn_fwd_workspace_floats(ops.MODE_TIME, B, H, Fr, n)),), F32)
                 ops.attn_fwd(mode, B, T, H, Fr, n, qkv, a, lse, cls_ws=ws)
-                wproj = _w16(bufs, "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"])
+                wproj = W[(i, tag, "proj")]
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
                 return wqkv, wproj, qkv, a, lse
 
@@ -170,8 +191,8 @@ class VideoEngine:
                                                                                     "attn", x, sr)
             # MLP on norm2(space_residual)                                   (:174, Mlp :45-51)
             L["h2"], L["m2"], L["r2"] = ln("2", sr, "norm2")
-            L["w1"] = _w16(bufs, "w.fc1.%d" % i, p[b + "mlp.fc1.weight"])
-            L["w2"] = _w16(bufs, "w.fc2.%d" % i, p[b + "mlp.fc2.weight"])
+            L["w1"] = W[(i, "fc1")]
+            L["w2"] = W[(i, "fc2")]
             u = bufs.get("u.%d" % i, (M, 4 * D), BF)
             g = bufs.get("g.%d" % i, (M, 4 * D), BF)
             ops.gemm(L["h2"], L["w1"], bias=p[b + "mlp.fc1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
@@ -189,7 +210,7 @@ class VideoEngine:
         out = cls32.clone() if proj is None else None
         wv = None
         if proj is not None:
-            wv = _w16(bufs, "w.vid_proj", p[proj[0]])
+            wv = W["vid_proj"]
             P = p[proj[0]].shape[0]
             out = torch.empty((B, P), dtype=F32, device=self.device)
             ops.gemm(cls16, wv, bias=p[proj[1]], out_f32=out)
@@ -339,6 +360,7 @@ class TextEngine:
         self.eps = eps
         self.bufs = _Buffers(device)
         self.saved = None
+        self._plan = ops.CastPlan()
 
     def forward(self, p, input_ids, attention_mask=None, proj=("txt_proj.1.weight", "txt_proj.1.bias"),
                 prefix="text_model.", save=True):
@@ -359,6 +381,24 @@ class TextEngine:
         if attention_mask is not None:
             key_mask = attention_mask.to(torch.int32).contiguous().view(-1)
 
+        # --- bf16 operand copies of every weight (q / k / v packed into one [3D, D] operand, biases likewise): one launch
+        plan = self._plan
+        W = {}
+        for i in range(layers_n):
+            b = "%stransformer.layer.%d." % (prefix, i)
+            wqkv = bufs.get("w.qkv.%d" % i, (3 * D, D), BF)
+            bqkv = bufs.get("b.qkv.%d" % i, (3 * D,), F32)
+            for j, nm in enumerate(("q_lin", "k_lin", "v_lin")):
+                plan.add(p[b + "attention.%s.weight" % nm], wqkv[j * D:(j + 1) * D])
+                plan.add(p[b + "attention.%s.bias" % nm].detach().view(1, D), bqkv[j * D:(j + 1) * D].view(1, D))
+            W[(i, "qkv")], W[(i, "bqkv")] = wqkv, bqkv
+            W[(i, "o")] = _w16(bufs, "w.o.%d" % i, p[b + "attention.out_lin.weight"], plan=plan)
+            W[(i, "l1")] = _w16(bufs, "w.l1.%d" % i, p[b + "ffn.lin1.weight"], plan=plan)
+            W[(i, "l2")] = _w16(bufs, "w.l2.%d" % i, p[b + "ffn.lin2.weight"], plan=plan)
+        if proj is not None:
+            W["txt_proj"] = _w16(bufs, "w.txt_proj", p[proj[0]], plan=plan)
+        plan.run()
+
         emb = bufs.get("emb", (M, D), F32)
         ops.text_embed(ids, word, pos, emb, Lq)
 
@@ -376,22 +416,17 @@ class TextEngine:
         for i in range(layers_n):
             b = "%stransformer.layer.%d." % (prefix, i)
             L = {"x16": x16, "x32": x32}
-            wqkv = bufs.get("w.qkv.%d" % i, (3 * D, D), BF)
-            bqkv = bufs.get("b.qkv.%d" % i, (3 * D,), F32)
-            for j, nm in enumerate(("q_lin", "k_lin", "v_lin")):
-                ops.cast_bf16(p[b + "attention.%s.weight" % nm].detach(), wqkv[j * D:(j + 1) * D])
-                bqkv[j * D:(j + 1) * D].copy_(p[b + "attention.%s.bias" % nm].detach())
+            wqkv, bqkv = W[(i, "qkv")], W[(i, "bqkv")]
             qkv = bufs.get("qkv.%d" % i, (M, 3 * D), BF)
             ops.gemm(x16, wqkv, bias=bqkv, scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
             ctx = bufs.get("ctx.%d" % i, (M, D), BF)
             lse = bufs.get("lse.%d" % i, (B * H * Lq,), F32)
             ops.attn_fwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, qkv, ctx, lse, key_mask)
-            wo = _w16(bufs, "w.o.%d" % i, p[b + "attention.out_lin.weight"])
+            wo = W[(i, "o")]
             sa_sum = bufs.get("sa_sum.%d" % i, (M, D), F32)
             ops.gemm(ctx, wo, bias=p[b + "attention.out_lin.bias"], residual=x32, out_f32=sa_sum)
             y16, y32, m1, r1 = ln("sa.%d" % i, sa_sum, b + "sa_layer_norm")
-            w1 = _w16(bufs, "w.l1.%d" % i, p[b + "ffn.lin1.weight"])
-            w2 = _w16(bufs, "w.l2.%d" % i, p[b + "ffn.lin2.weight"])
+            w1, w2 = W[(i, "l1")], W[(i, "l2")]
             Hd = w1.shape[0]
             u = bufs.get("u.%d" % i, (M, Hd), BF)
             g = bufs.get("g.%d" % i, (M, Hd), BF)
@@ -409,7 +444,7 @@ class TextEngine:
         if proj is not None:
             r16 = bufs.get("relu16", (B, D), BF)
             ops.cast_bf16(x32, r16, rows=B, cols=D, lds=Lq * D, relu=True)
-            wt = _w16(bufs, "w.txt_proj", p[proj[0]])
+            wt = W["txt_proj"]
             out = torch.empty((B, p[proj[0]].shape[0]), dtype=F32, device=self.device)
             ops.gemm(r16, wt, bias=p[proj[1]], out_f32=out)
         if save:

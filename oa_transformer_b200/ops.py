@@ -214,6 +214,46 @@ def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
                               _i32(dst.shape[1]), _i32(1 if relu else 0), stream_ptr()), "oat_cast_bf16")
 
 
+class CastPlan:
+    """A set of fp32 -> bf16 (or fp32 -> fp32) 2-D copies executed by ONE launch (oat_cast_multi). The device table is
+    built once and re-used for as long as the source / destination pointers stay the same."""
+
+    def __init__(self):
+        self.items = []
+        self._key = None
+        self._dev = None
+
+    def add(self, src, dst, rows=None, cols=None):
+        """dst[:rows, :] <- src (2-D view, last dim contiguous); columns [cols, dst.shape[1]) are zero-filled."""
+        src2 = src.detach()
+        src2 = src2.reshape(src2.shape[0], -1) if src2.dim() != 2 else src2
+        rows = src2.shape[0] if rows is None else rows
+        cols = src2.shape[1] if cols is None else cols
+        assert src2.dtype == torch.float32 and src2.stride(1) == 1 and dst.dim() == 2 and dst.stride(1) == 1
+        assert dst.shape[1] % 4 == 0 and dst.stride(0) % 4 == 0 and dst.shape[1] >= cols
+        self.items.append((src2, dst, rows, cols))
+
+    def run(self):
+        if not self.items:
+            return
+        key = tuple((s.data_ptr(), d.data_ptr(), r, c) for s, d, r, c in self.items)
+        if key != self._key:
+            rows_, prefix = [], [0]
+            for s, d, r, c in self.items:
+                colsp = d.shape[1]
+                rows_.append([s.data_ptr(), d.data_ptr(), r, c, colsp, s.stride(0), d.stride(0),
+                              1 if d.dtype == torch.float32 else 0])
+                prefix.append(prefix[-1] + (r * colsp + 1023) // 1024)
+            dev = self.items[0][1].device
+            self._dev = (torch.tensor(rows_, dtype=torch.int64, device=dev),
+                         torch.tensor(prefix, dtype=torch.int64, device=dev), len(rows_), prefix[-1])
+            self._key = key
+        table, prefix, n, total = self._dev
+        _count(1)
+        check(lib().oat_cast_multi(ptr(table), ptr(prefix), _i32(n), _i64(total), stream_ptr()), "oat_cast_multi")
+        self.items = []
+
+
 def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx, lddx=None):
     _count(1)
     check(lib().oat_relu_bwd(ptr(x), _i64(ldx), ptr(dy_bf16), _i64(dy_bf16.stride(0)), ptr(dx),
