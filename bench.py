@@ -324,6 +324,11 @@ def run_ours(args):
         loss = step(dev)
     e1.record()
     barrier()
+    # diagnostic: host time to enqueue ONE step into an empty stream (no queue back-pressure), not part of any metric
+    t_host = time.perf_counter()
+    step(dev)
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
+    barrier()
     ms = e0.elapsed_time(e1) / K
     launches = (ops.LAUNCHES - launches0) // K
     clocks = sampler.stop() if rank == 0 else None
@@ -471,7 +476,7 @@ def run_ours(args):
                 "loss": loss_val,
                 "model_tflops": value * flops / 1e12,
                 "mfu_vs_sustained_bf16": value * flops / 1e12 / world / peaks["bf16_tflops_sustained"],
-                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
                 "roofline_attention": roofline_attn, "kernel_ms_breakdown": breakdown, "cpu_baseline": cpu}
     if world > 1:
         dist.destroy_process_group()

@@ -164,6 +164,28 @@ def test_object_tokens_224_vs_bf16_oracle():
     assert "video_model.object_embed.weight" in grads
 
 
+@pytest.mark.parametrize("frames,tag", [(4, "cfg3"), (16, "cfg5")])
+def test_config_shaped_frames_and_objects_vs_bf16_oracle(frames, tag):
+    """BASELINE configs[2] / configs[4] geometry (4 and 16 frames of 224x224, 36 object regions per frame, 32-token text:
+    T = 929 / 3713 tokens per video) on a 2-block video tower, batch 2: logits and gradients vs the bf16 oracle. Exercises
+    the time-attention kernels at Fp = 4 and Fp = 16 and the tcgen05 space kernels at n = 232 inside the full schedule."""
+    spec = dual_encoder_spec(frames=frames, objects=True, depth=2)
+    w = fill_seeded(spec, 91, 0.02)
+    g = torch.Generator().manual_seed(92 + frames)
+    B, Oo, L = 2, 36, 32
+    video = torch.randn(B, frames, 3, 224, 224, generator=g)
+    objects = O.synth_objects(B, frames, Oo, g)
+    text = O.synth_text(B, L, g)
+    te, ve, sims, loss, grads = cuda_dual(w, video, text["input_ids"], text["attention_mask"], heads=12,
+                                          objects=objects)
+    cfg = O.OracleCfg(bf16=True)
+    _, _, osims, oloss, ograds = oracle_dual(w, video, text["input_ids"], text["attention_mask"], cfg, objects=objects)
+    rep = summarize("%s_depth2_vs_bf16_oracle" % tag, sims, osims, loss, oloss, grads, ograds)
+    assert rep["logit_max_abs_err"] < 1e-3
+    assert rep["grad_rel_err_median"] < 8e-2 and rep["grad_rel_err_max"] < 0.4
+    assert not rep["missing"]
+
+
 def test_frozen_in_time_module_surface():
     """The nn.Module mirror: constructor, forward(data) -> (text, video) embeddings, backward into .grad."""
     from oa_transformer_b200.model import FrozenInTime, NormSoftmaxLoss, sim_matrix
