@@ -25,7 +25,7 @@ constexpr int TD = 64;            // head dim
 constexpr int kTimeWarps = 4;     // 128 threads = 128 token rows staged per CTA
 
 struct TimeGeom {
-  int B, T, H, F, n, Fp, gpc, chunks;   // gpc: groups per CTA, chunks: CTAs per (b, h)
+  int B, T, H, F, n, Fp, lgFp, gpc, chunks;   // Fp = 1 << lgFp; gpc: groups per CTA, chunks: CTAs per (b, h)
   long long ld_qkv, ld_out, ld_dout, ld_dqkv;
   const __nv_bfloat16* qkv;
   __nv_bfloat16* out;
@@ -52,8 +52,8 @@ __device__ __forceinline__ void cp_async_wait_all_t() { asm volatile("cp.async.w
 // Token of local row lr (0..31) of warp `warp` in CTA chunk `chunk`; -1 when the row is padding.
 //   lr = group_in_warp * Fp + frame,  slot = chunk * gpc + warp * (32 / Fp) + group_in_warp,  token = 1 + frame * n + slot
 __device__ __forceinline__ int row_token(const TimeGeom& G, int chunk, int warp, int lr) {
-  const int gl = lr / G.Fp, i = lr - gl * G.Fp;
-  const int pos = chunk * G.gpc + warp * (32 / G.Fp) + gl;
+  const int gl = lr >> G.lgFp, i = lr & (G.Fp - 1);
+  const int pos = chunk * G.gpc + ((warp * 32) >> G.lgFp) + gl;
   return (i < G.F && pos < G.n) ? 1 + i * G.n + pos : -1;
 }
 
@@ -78,6 +78,42 @@ __device__ __forceinline__ void store_rows_warp(const uint8_t* arr, __nv_bfloat1
     const int r = warp * 32 + it * 4 + (lane >> 3);
     if (tok[it] >= 0)
       *reinterpret_cast<uint4*>(dst_col + static_cast<long long>(tok[it]) * ld + c * 8) = *reinterpret_cast<const uint4*>(arr + sw_off(r, c));
+  }
+}
+
+// several arrays that share the row pitch (q | k | v slices of one qkv row, dq | dk | dv of one dqkv row): one 64-bit row
+// offset per pass instead of one per array and pass
+template <int NA>
+__device__ __forceinline__ void stage_rows_warp_n(uint8_t* const (&arr)[NA], const __nv_bfloat16* const (&src_col)[NA],
+                                                  long long ld, const int (&tok)[8], int warp, int lane) {
+  const int c = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = warp * 32 + it * 4 + (lane >> 3);
+    const uint32_t off = sw_off(r, c);
+    if (tok[it] >= 0) {
+      const long long roff = static_cast<long long>(tok[it]) * ld + c * 8;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) cp_async16_t(smem_u32(arr[a] + off), src_col[a] + roff);
+    } else {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) *reinterpret_cast<uint4*>(arr[a] + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+template <int NA>
+__device__ __forceinline__ void store_rows_warp_n(const uint8_t* const (&arr)[NA], __nv_bfloat16* const (&dst_col)[NA],
+                                                  long long ld, const int (&tok)[8], int warp, int lane) {
+  const int c = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = warp * 32 + it * 4 + (lane >> 3);
+    if (tok[it] >= 0) {
+      const uint32_t off = sw_off(r, c);
+      const long long roff = static_cast<long long>(tok[it]) * ld + c * 8;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) *reinterpret_cast<uint4*>(dst_col[a] + roff) = *reinterpret_cast<const uint4*>(arr[a] + off);
+    }
   }
 }
 
@@ -170,13 +206,23 @@ __device__ __forceinline__ void mma_cls_t(uint32_t mat, int lane, const uint32_t
   }
 }
 // rows g / g + 8 of the accumulator tile -> bf16 -> staged rows (conflict-free 32-bit stores)
-__device__ __forceinline__ void store_acc_rows(uint8_t* arr, int R0, int lane, const float (&acc)[8][4], float mul) {
+template <bool SCALED>
+__device__ __forceinline__ void store_acc_rows(uint8_t* arr, int R0, int lane, const float (&acc)[8][4], float mul = 1.f) {
   const int g = lane >> 2, t = lane & 3;
   const int ra = R0 + g, rb = ra + 8;
+  uint8_t* pa = arr + static_cast<uint32_t>(ra) * 128u + 4 * t;
+  uint8_t* pb = arr + static_cast<uint32_t>(rb) * 128u + 4 * t;
+  const uint32_t x = static_cast<uint32_t>(ra & 7);        // (ra & 7) == (rb & 7)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    *reinterpret_cast<uint32_t*>(arr + sw_off(ra, j) + 4 * t) = pack_bf16x2(acc[j][0] * mul, acc[j][1] * mul);
-    *reinterpret_cast<uint32_t*>(arr + sw_off(rb, j) + 4 * t) = pack_bf16x2(acc[j][2] * mul, acc[j][3] * mul);
+    const uint32_t o = (static_cast<uint32_t>(j) ^ x) << 4;
+    if (SCALED) {
+      *reinterpret_cast<uint32_t*>(pa + o) = pack_bf16x2(acc[j][0] * mul, acc[j][1] * mul);
+      *reinterpret_cast<uint32_t*>(pb + o) = pack_bf16x2(acc[j][2] * mul, acc[j][3] * mul);
+    } else {
+      *reinterpret_cast<uint32_t*>(pa + o) = pack_bf16x2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<uint32_t*>(pb + o) = pack_bf16x2(acc[j][2], acc[j][3]);
+    }
   }
 }
 // row 0 of the accumulator tile (lanes 0-3) -> shared accumulators
@@ -212,9 +258,11 @@ __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGe
   int tok[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) tok[it] = row_token(G, chunk, warp, it * 4 + (lane >> 3));
-  stage_rows_warp(Ks, base + HD3, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Qs, base, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Vs, base + 2 * HD3, G.ld_qkv, tok, warp, lane);
+  {
+    uint8_t* const arrs[3] = {Ks, Qs, Vs};
+    const __nv_bfloat16* const srcs[3] = {base + HD3, base, base + 2 * HD3};
+    stage_rows_warp_n<3>(arrs, srcs, G.ld_qkv, tok, warp, lane);
+  }
   if (threadIdx.x < 96) {  // CLS matrices: row 0 <- vector, rows 1-7 <- 0
     const int m = threadIdx.x >> 5, rr = (threadIdx.x >> 3) & 3, c = threadIdx.x & 7;
 #pragma unroll
@@ -233,8 +281,7 @@ __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGe
   const uint32_t aQ = smem_u32(Qs), aK = smem_u32(Ks), aV = smem_u32(Vs);
   const uint32_t mQ = smem_u32(Cm), mK = mQ + 1024, mV = mQ + 2048;
   const int g = lane >> 2, t = lane & 3;
-  int lg = 0;
-  while ((1 << lg) < G.Fp) ++lg;
+  const int lg = G.lgFp;
   uint32_t bq[4][2], bk[4][2];
   load_cls_frags(mQ, lane, bq);
   load_cls_frags(mK, lane, bk);
@@ -324,7 +371,7 @@ __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGe
       if (tb >= 0) lse_out[tb] = lse_b;
     }
     __syncwarp();                                              // every lane has its Q fragments of this tile
-    store_acc_rows(Qs, R0, lane, acc, 1.f);
+    store_acc_rows<false>(Qs, R0, lane, acc);
   }
   __syncwarp();
   store_rows_warp(Qs, G.out + row0 * G.ld_out + h * TD, G.ld_out, tok, warp, lane);
@@ -401,9 +448,11 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
 #pragma unroll
   for (int it = 0; it < 8; ++it) tok[it] = row_token(G, chunk, warp, it * 4 + (lane >> 3));
   stage_rows_warp(Ds, dbase, G.ld_dout, tok, warp, lane);
-  stage_rows_warp(Vs, base + 2 * HD3, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Ks, base + HD3, G.ld_qkv, tok, warp, lane);
-  stage_rows_warp(Qs, base, G.ld_qkv, tok, warp, lane);
+  {
+    uint8_t* const arrs[3] = {Vs, Ks, Qs};
+    const __nv_bfloat16* const srcs[3] = {base + 2 * HD3, base + HD3, base};
+    stage_rows_warp_n<3>(arrs, srcs, G.ld_qkv, tok, warp, lane);
+  }
   {  // CLS matrices: row 0 <- vector, rows 1-7 <- 0
     const int m = threadIdx.x >> 5, rr = (threadIdx.x >> 3) & 3, c = threadIdx.x & 7;   // 4 matrices x (4 rows x 8 chunks) per pass
 #pragma unroll
@@ -460,8 +509,7 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   const uint32_t aQ = smem_u32(Qs), aK = smem_u32(Ks), aV = smem_u32(Vs), aD = smem_u32(Ds);
   const uint32_t mQ = smem_u32(Cm), mK = mQ + 1024, mV = mQ + 2048, mD = mQ + 3072;
   const int g = lane >> 2, t = lane & 3;
-  int lg = 0;
-  while ((1 << lg) < G.Fp) ++lg;
+  const int lg = G.lgFp;
   uint32_t bq[4][2], bk[4][2], bv[4][2], bd[4][2];              // CLS vectors as B operands of the score-type products
   load_cls_frags(mQ, lane, bq);
   load_cls_frags(mK, lane, bk);
@@ -543,14 +591,14 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     mma_cls_t(mK, lane, E0, acc);
     add_row0(sAcc, lane, acc2);
     __syncwarp();                                               // every lane has loaded its V / K fragments of this tile
-    store_acc_rows(Vs, R0, lane, acc, G.scale);
+    store_acc_rows<true>(Vs, R0, lane, acc, G.scale);
     // ---- dK = dS^T Q + dS_cj q_cls (-> K rows) ; dK_cls += ds_.0 Q
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
     mma_rows_t(aQ, R0, lane, dSTa, acc, Rk, acc2);
     mma_cls_t(mQ, lane, Ec, acc);
     add_row0(sAcc + TD, lane, acc2);
-    store_acc_rows(Ks, R0, lane, acc, 1.f);
+    store_acc_rows<false>(Ks, R0, lane, acc);
     // ---- dV = P^T dO + P_cj dO_cls (-> Q rows) ; dV_cls += p_.0 dO
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
@@ -558,13 +606,15 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     mma_cls_t(mD, lane, Epc, acc);
     add_row0(sAcc + 2 * TD, lane, acc2);
     __syncwarp();                                               // every lane is done with the Q rows of this tile
-    store_acc_rows(Qs, R0, lane, acc, 1.f);
+    store_acc_rows<false>(Qs, R0, lane, acc);
   }
   __syncwarp();
   __nv_bfloat16* gbase = G.dqkv + row0 * G.ld_dqkv + h * TD;
-  store_rows_warp(Vs, gbase, G.ld_dqkv, tok, warp, lane);                   // dq (already scaled)
-  store_rows_warp(Ks, gbase + HD3, G.ld_dqkv, tok, warp, lane);             // dk
-  store_rows_warp(Qs, gbase + 2 * HD3, G.ld_dqkv, tok, warp, lane);         // dv
+  {
+    const uint8_t* const arrs[3] = {Vs, Ks, Qs};                            // dq (already scaled), dk, dv
+    __nv_bfloat16* const dsts[3] = {gbase, gbase + HD3, gbase + 2 * HD3};
+    store_rows_warp_n<3>(arrs, dsts, G.ld_dqkv, tok, warp, lane);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * TD; i += kRows) atomicAdd(G.cls_acc + static_cast<long long>(bh) * 3 * TD + i, sAcc[i]);
 }
@@ -597,6 +647,8 @@ static TimeGeom make_time_geom(const oat_attn_args* a) {
   int fp = 1;
   while (fp < a->F) fp <<= 1;
   G.Fp = fp;
+  G.lgFp = 0;
+  while ((1 << G.lgFp) < fp) ++G.lgFp;
   G.gpc = kTimeWarps * (32 / fp);
   G.chunks = (a->n + G.gpc - 1) / G.gpc;
   G.ld_qkv = a->ld_qkv; G.ld_out = a->ld_out; G.ld_dout = a->ld_dout; G.ld_dqkv = a->ld_dqkv;

@@ -101,6 +101,36 @@ def test_layernorm_strided_cls_rows():
     assert torch.allclose(y32, ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B", [5, 32, 40])
+def test_layernorm_bwd_strided_cls_rows(B):
+    """Final-LayerNorm backward on the CLS rows only (row pitch T*D), as the video engine calls it: B = 32 / 40 take the
+    staged kernel, B = 5 the register kernel; rows between the CLS rows must stay untouched."""
+    from oa_transformer_b200 import ops
+    T, D = 7, 768
+    g = gen(6)
+    x = torch.randn(B * T, D, generator=g).cuda()
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).cuda()
+    beta = torch.zeros(D, device="cuda")
+    mean = torch.empty(B, device="cuda")
+    rstd = torch.empty(B, device="cuda")
+    y16 = torch.empty(B, D, device="cuda", dtype=BF)
+    ops.layernorm_fwd(x, gamma, beta, 1e-6, rows=B, ldx=T * D, y_bf16=y16, mean=mean, rstd=rstd)
+    dy16 = torch.randn(B, D, generator=g).to(BF).cuda()
+    dx = torch.full((B * T, D), 3.0, device="cuda")
+    dx16 = torch.full((B * T, D), 3.0, device="cuda", dtype=BF)
+    dgamma, dbeta, dxsum = (torch.zeros(D, device="cuda") for _ in range(3))
+    ops.layernorm_bwd(x, mean, rstd, gamma, dy_bf16=dy16, rows=B, ldx=T * D, dx=dx, dx_bf16=dx16, lddx=T * D, lddxb=T * D,
+                      dgamma=dgamma, dbeta=dbeta, dxsum=dxsum)
+    xr = x.view(B, T, D)[:, 0].clone().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), gr, beta, 1e-6).backward(dy16.float())
+    got = dx.view(B, T, D)
+    assert rel(got[:, 0], xr.grad) < 1e-5
+    assert bool((got[:, 1:] == 3.0).all()) and bool((dx16.view(B, T, D)[:, 1:].float() == 3.0).all())
+    assert rel(dx16.view(B, T, D)[:, 0].float(), xr.grad) < 5e-3
+    assert rel(dgamma, gr.grad) < 1e-4 and rel(dxsum, xr.grad.sum(0)) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _qkv(B, T, H, seed, scale=1.0):
     q = torch.randn(B, T, 3, H, 64, generator=gen(seed)) * scale
