@@ -204,12 +204,23 @@ def test_config_shaped_frames_and_objects_vs_bf16_oracle(frames, tag):
     ((te * ct.to(dev)).sum() + (ve * cv.to(dev)).sum()).backward()
     torch.cuda.synchronize()
     grads = {k: v.grad.detach().cpu() for k, v in params.items() if v.is_floating_point() and v.grad is not None}
-    floor = summarize("noise_floor_%s_linear" % tag, s16, s32, 0.0, 0.0, g16, g32)
-    rep = summarize("%s_depth2_linear_vs_bf16_oracle" % tag, sims, s16, 0.0, 0.0, grads, g16)
+    # video tower (smooth: GELU only): gated on its own bf16-vs-fp32 noise floor. Text tower: the ReLU in front of txt_proj
+    # (oa_model.py:68) makes its gradient discontinuous - a rounding-level difference that flips the sign of a few of the
+    # 768 CLS features changes ~0.5 % of the gradient energy, i.e. ~7 % relative error in every text tensor (seen in the
+    # bf16-vs-fp32 oracle pair itself for one of the two seeds) - so it only gets an absolute gate here; its kernels are
+    # gated tightly in test_ops_gpu.py and, without mask flips, by the cfg1 / golden cases above.
+    def part(d, prefixes):
+        return {k: v for k, v in d.items() if k.startswith(prefixes)}
+    vid = ("video_model.", "vid_proj.")
+    txt = ("text_model.", "txt_proj.")
+    floor = summarize("noise_floor_%s_linear_video" % tag, s16, s32, 0.0, 0.0, part(g16, vid), part(g32, vid))
+    rep = summarize("%s_depth2_linear_video_vs_bf16_oracle" % tag, sims, s16, 0.0, 0.0, part(grads, vid), part(g16, vid))
+    rept = summarize("%s_depth2_linear_text_vs_bf16_oracle" % tag, sims, s16, 0.0, 0.0, part(grads, txt), part(g16, txt))
     assert rep["logit_max_abs_err"] < 1e-3
     assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
     assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
-    assert not rep["missing"]
+    assert rept["grad_rel_err_max"] < 0.15
+    assert not rep["missing"] and not rept["missing"]
 
 
 def test_frozen_in_time_module_surface():
