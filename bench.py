@@ -286,18 +286,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_grads():
-        # what DDP's reducer does (base/base_trainer.py:23): average parameter gradients across ranks
+    # what DDP's reducer does (base/base_trainer.py:23): average parameter gradients across ranks. Each tower's flat
+    # gradient book is all-reduced as soon as that tower's backward has been enqueued (engine.grad_ready_hook): the
+    # text tower finishes first, so its all-reduce runs under the video tower's backward.
+    pending = []
+
+    def start_reduce(book):
         if world > 1:
-            for eng in (model.video_model._engine, model._text_engine):
-                book = getattr(eng, "_gradbook", None)
-                if book is not None:
-                    dist.all_reduce(book.flat, op=dist.ReduceOp.AVG)
+            pending.append(dist.all_reduce(book.flat, op=dist.ReduceOp.AVG, async_op=True))
+
+    def reduce_grads():
+        while pending:
+            pending.pop().wait()
 
     def step(data):
         for p in params:
             p.grad = None
         text_e, video_e = model(data, aug=True)
+        for eng in (model.video_model._engine, model._text_engine):
+            eng.grad_ready_hook = start_reduce
         video_g = AllGatherSlice.apply(video_e, rank, world)
         text_g = AllGatherSlice.apply(text_e, rank, world)
         loss = loss_fn(sim_matrix(text_g, video_g))

@@ -53,6 +53,9 @@ class TowerRunner:
             eng._gradbook, eng._gradbook_key = book, key
         book.zero()
         eng.backward(self.pdict, book, dout.contiguous().float())
+        hook = getattr(eng, "grad_ready_hook", None)
+        if hook is not None:        # e.g. start this tower's gradient all-reduce while the other tower still runs backward
+            hook(book)
         return [book[n] if p.requires_grad else None for n, p in self.named]
 
 
