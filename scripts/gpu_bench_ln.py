@@ -28,3 +28,8 @@ print(json.dumps({"fwd_ms": round(f, 4), "fwd_GBps": round(el * 6 / f / 1e6, 1),
                   "bwd_plain_ms": round(b0, 4), "bwd_plain_GBps": round(el * 12 / b0 / 1e6, 1),
                   "bwd_add1_ms": round(b1, 4), "bwd_add1_GBps": round(el * 16 / b1 / 1e6, 1),
                   "bwd_add2_ms": round(b2, 4), "bwd_add2_GBps": round(el * 20 / b2 / 1e6, 1)}))
+x3 = torch.randn(M, 3 * D, device="cuda").to(BF); x4 = torch.randn(M, 4 * D, device="cuda").to(BF)
+o3 = torch.zeros(3 * D, device="cuda"); o4 = torch.zeros(4 * D, device="cuda")
+c3 = timeit(lambda: ops.colsum_bf16(x3, o3)); c4 = timeit(lambda: ops.colsum_bf16(x4, o4))
+print(json.dumps({"colsum_2304_ms": round(c3, 4), "colsum_2304_GBps": round(M * 3 * D * 2 / c3 / 1e6, 1),
+                  "colsum_3072_ms": round(c4, 4), "colsum_3072_GBps": round(M * 4 * D * 2 / c4 / 1e6, 1)}))
