@@ -207,41 +207,28 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces a 256-row slab; threadIdx.x owns 8 adjacent columns (one
-// 16-byte load per row), threadIdx.y splits the slab's rows (2-8 row groups, so that ~2/3 of the SM's thread slots are
-// filled and enough loads are in flight), partials meet in shared memory and leave as ONE atomic per column and CTA.
-// (64-row slabs were tried instead: 4x the atomics onto the same `cols` addresses made the kernel 1.7x slower in-step.)
-constexpr int kColsumRowsPerCta = 256;
-__global__ void __launch_bounds__(1024) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
-                                                           long long rows, int cols, float* __restrict__ out) {
-  extern __shared__ float colsum_part[];                  // [blockDim.y][blockDim.x * 8]
+// out[c] += sum_r x[r, c]   (bias gradients). Each CTA reduces one slab of rows; a thread owns 8 adjacent columns (one
+// 16-byte load per row). The slab height is chosen so that the number of slabs is a multiple of the SM count (2 per SM
+// at M = 59424): with fixed 256-row slabs 233 CTAs landed 2-1 on the SMs (79 % balance). 64-row slabs were tried too:
+// 4x the atomics onto the same `cols` addresses made the kernel 1.7x slower in the step.
+__global__ void __launch_bounds__(512) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                          long long rows, int cols, float* __restrict__ out,
+                                                          int rows_per_cta) {
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-  const bool active = c < cols;
-  const long long r0 = static_cast<long long>(blockIdx.x) * kColsumRowsPerCta;
-  const long long r1 = min(rows, r0 + kColsumRowsPerCta);
+  if (c >= cols) return;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  if (active) {
-    long long r = r0 + threadIdx.y;
-    const long long step = blockDim.y;
-    for (; r + 3 * step < r1; r += 4 * step) {
-      uint4 v[4];
+  long long r = r0;
+  for (; r + 16 <= r1; r += 16) {
+    uint4 v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (r + u * step) * ld + c);
+    for (int u = 0; u < 16; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (r + u) * ld + c);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[u]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_bf16x2(w[k]);
-          acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
-        }
-      }
-    }
-    for (; r < r1; r += step) {
-      const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+    for (int u = 0; u < 16; ++u) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[u]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = unpack_bf16x2(w[k]);
@@ -249,19 +236,17 @@ __global__ void __launch_bounds__(1024) colsum_bf16_kernel(const __nv_bfloat16* 
       }
     }
   }
-  float* mine = colsum_part + (threadIdx.y * blockDim.x + threadIdx.x) * 8;
+  for (; r < r1; ++r) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + c);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
-  __syncthreads();
-  if (threadIdx.y == 0 && active) {
-    for (int y = 1; y < blockDim.y; ++y) {
-      const float* p = colsum_part + (y * blockDim.x + threadIdx.x) * 8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += p[k];
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(out + c + k, acc[k]);
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(out + c + k, acc[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ text embeddings
@@ -371,15 +356,18 @@ extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int
                                oat_stream_t stream) {
   OAT_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "oat_colsum_bf16: cols and ld must be multiples of 8");
   if (rows <= 0) return OAT_OK;
-  // one block spans all columns when it can (2304 -> 288 threads, 3072 -> 384); the rest of the 1024 threads split rows
+  // one block spans all columns when it can (2304 -> 288 threads, 3072 -> 384): no nearly-empty second column block
   const int want = ((cols / 8 + 31) / 32) * 32;
-  const int tx = want <= 512 ? want : 256;
-  int ty = 1024 / tx;
-  ty = ty > 8 ? 8 : ty;
-  dim3 grid(static_cast<unsigned>((rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta),
-            static_cast<unsigned>((cols / 8 + tx - 1) / tx));
-  colsum_bf16_kernel<<<grid, dim3(tx, ty), static_cast<size_t>(tx) * ty * 8 * sizeof(float), as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, out);
+  const int threads = want <= 512 ? want : 256;
+  // slabs: a multiple of the SM count, about 200-256 rows each
+  const long long sms = num_sms();
+  long long k = (rows + 256 * sms - 1) / (256 * sms);
+  if (k < 1) k = 1;
+  long long rows_per = (rows + k * sms - 1) / (k * sms);
+  if (rows_per < 16) rows_per = 16;
+  dim3 grid(static_cast<unsigned>((rows + rows_per - 1) / rows_per), static_cast<unsigned>((cols / 8 + threads - 1) / threads));
+  colsum_bf16_kernel<<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows,
+                                                             cols, out, static_cast<int>(rows_per));
   return check_launch("colsum_bf16_kernel");
 }
 
