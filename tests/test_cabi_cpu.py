@@ -145,3 +145,37 @@ def test_config_parser_reflection_factory(monkeypatch):
     monkeypatch.setattr("sys.argv", ["prog", "-c", ref_cfg])
     cfg2 = ConfigParser(_parser(), test=True)
     assert cfg2['arch']['args']['video_params']['time_init'] == 'zeros' and cfg2['n_gpu'] == 8
+
+
+def test_fused_adamw_is_what_the_config_factory_resolves_and_has_no_cpu_path():
+    """`optimizer.type = "AdamW"` (the reference's transformers.AdamW, train_dist_multi.py:66) resolves to the fused liboat
+    optimizer; on CPU parameters it refuses to step (there is no CPU fallback anywhere on the path)."""
+    import torch
+    from oa_transformer_b200 import optim
+    assert hasattr(optim, "AdamW")
+    p = torch.nn.Parameter(torch.zeros(8))
+    opt = optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True)
+    assert opt.defaults["correct_bias"] is True and opt.param_groups[0]["lr"] == 1e-3
+    p.grad = torch.ones(8)
+    with pytest.raises(AssertionError):
+        opt.step()
+    with pytest.raises(ValueError):
+        optim.AdamW([p], lr=-1.0)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU port of the reference path, all host threads): exactly one JSON line on stdout
+    with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
