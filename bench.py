@@ -290,10 +290,36 @@ def run_ours(args):
     # gradient book is all-reduced as soon as that tower's backward has been enqueued (engine.grad_ready_hook): the
     # text tower finishes first, so its all-reduce runs under the video tower's backward.
     pending = []
+    layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "0") != "0"     # experiment: all-reduce block by block during backward
+    reduced = set()
+
+    def book_range(book, prefix):
+        """[lo, hi) of the flat book covered by the parameters whose name starts with `prefix` (contiguous by construction)."""
+        spans = [(v.data_ptr(), v.numel()) for n, v in book.views.items() if n.startswith(prefix)]
+        base = book.flat.data_ptr()
+        lo = min(p for p, _ in spans)
+        hi = max(p + 4 * n for p, n in spans)
+        assert sum(n for _, n in spans) * 4 == hi - lo, "parameters of %s are not contiguous in the gradient book" % prefix
+        return (lo - base) // 4, (hi - base) // 4
+
+    def layer_hook(book, prefix):
+        if world > 1 and layer_reduce:
+            lo, hi = book_range(book, prefix)
+            reduced.add((lo, hi))
+            pending.append(dist.all_reduce(book.flat[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
 
     def start_reduce(book):
         if world > 1:
-            pending.append(dist.all_reduce(book.flat, op=dist.ReduceOp.AVG, async_op=True))
+            done = sorted(r for r in reduced if True)
+            if not (layer_reduce and book is getattr(model.video_model._engine, "_gradbook", None)):
+                pending.append(dist.all_reduce(book.flat, op=dist.ReduceOp.AVG, async_op=True))
+            else:                                   # the blocks went out one by one: reduce what lies around them
+                cur = 0
+                for lo, hi in done + [(book.flat.numel(), book.flat.numel())]:
+                    if lo > cur:
+                        pending.append(dist.all_reduce(book.flat[cur:lo], op=dist.ReduceOp.AVG, async_op=True))
+                    cur = max(cur, hi)
+            reduced.clear()
 
     def reduce_grads():
         while pending:
@@ -305,6 +331,7 @@ def run_ours(args):
         text_e, video_e = model(data, aug=True)
         for eng in (model.video_model._engine, model._text_engine):
             eng.grad_ready_hook = start_reduce
+        model.video_model._engine.layer_grad_hook = layer_hook
         video_g = AllGatherSlice.apply(video_e, rank, world)
         text_g = AllGatherSlice.apply(text_e, rank, world)
         loss = loss_fn(sim_matrix(text_g, video_g))

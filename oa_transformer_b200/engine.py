@@ -330,6 +330,9 @@ class VideoEngine:
                 ev = torch.cuda.Event()
                 ev.record(side)
                 side_done[i] = ev
+            hook = getattr(self, "layer_grad_hook", None)
+            if hook is not None:        # every gradient of block i has been enqueued (fc2.bias came from block i+1's LN3)
+                hook(grads, "%sblocks.%d." % (prefix, i))
             dy, dyb = dyb, dy
             dy16 = dy16b
 
