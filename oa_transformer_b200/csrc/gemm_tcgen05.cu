@@ -58,6 +58,7 @@ struct GemmParams {
   float scale;
   float alpha;
   int accumulate;
+  int idle_wait;      // epilogue warps sleep between polls while the k-loop runs (experiment knob OAT_GEMM_IDLE_WAIT)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -310,7 +311,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_arrive_expect_tx(my_in_bar, kBoxBytes);
         tma_load_2d(box_x, &tmap_x, my_in_bar, col0 + half * CW, row0);
       }
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (p.idle_wait) mbar_wait_idle(&tmem_full_bar[acc], acc_phase);
+      else mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < kChunksT; c += 2) {
@@ -670,6 +672,10 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.aux_bf16 = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16); p.ld_aux = a->ld_aux;
   p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
   p.accumulate = a->accumulate;
+  {
+    const char* e = getenv("OAT_GEMM_IDLE_WAIT");
+    p.idle_wait = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
 
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, TWO>;
   static bool attr_set = false;

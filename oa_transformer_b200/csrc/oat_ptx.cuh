@@ -57,6 +57,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait that is expected to be LONG (epilogue warps waiting for a whole k-loop): after a few polls the warp sleeps between
+// polls instead of spinning, which leaves issue slots and power to the warps that are working (the part is power-capped).
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 8) __nanosleep(200);
+    if (spins > (1u << 26)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(desc) : "memory");

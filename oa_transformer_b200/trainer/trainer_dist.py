@@ -142,7 +142,9 @@ class Multi_Trainer_dist(Multi_BaseTrainer_dist):
             nested = {}
             text_embeds = torch.cat(text_arr[dl_idx]).to(self.device)
             vid_embeds = torch.cat(vid_arr[dl_idx]).to(self.device)
-            sims = sim_matrix(text_embeds, vid_embeds).detach().cpu().numpy()
+            # the reference moves the matrix to the host first (trainer_dist.py:255-264); the metric functions here count
+            # the ranks on the device for a CUDA tensor (same numbers, model/metric.py)
+            sims = sim_matrix(text_embeds, vid_embeds).detach()
             for metric in self.metrics:
                 nested[metric.__name__] = {k: float(v) for k, v in metric(sims).items()}
             res[dl_idx] = nested
