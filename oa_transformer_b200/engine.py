@@ -237,7 +237,7 @@ class VideoEngine:
         # Gradient activations they read rotate over two buffer sets (layer parity); the chain waits for the side
         # stream's layer i+2 before overwriting set i%2.
         use_side = SIDE_STREAM and torch.cuda.is_available()
-        main = torch.cuda.current_stream(self.device)
+        main = torch.cuda.current_stream(self.device) if use_side else None
         if use_side:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)

@@ -1,0 +1,89 @@
+"""Host-side schedules of the two towers (engine.VideoEngine / engine.TextEngine) on CPU: the operator layer is replaced,
+for this test only, by the plain-torch stand-in tests/fake_liboat.py, so that buffer management, the frozen-in-time
+residual wiring, operand packing and the hand-written backward bookkeeping (which gradient lands in which tensor, the
+fused bias-gradient reductions, the CLS-row-only final LayerNorm, q/k/v packing of the text tower) are checked against
+the oracle without a GPU. The CUDA kernels themselves are checked on the GPU (tests/test_*_gpu.py)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fake_liboat  # noqa: E402
+
+from oracle import oracle as O  # noqa: E402
+from oracle.weights import fill_seeded, text_tower_spec, video_tower_spec  # noqa: E402
+
+
+def rel(a, b):
+    d, n = float((a.double() - b.double()).norm()), float(b.double().norm())
+    return 0.0 if d <= 1e-9 else d / max(n, 1e-30)
+
+
+@pytest.fixture()
+def engine_on_fake_ops(monkeypatch):
+    from oa_transformer_b200 import engine
+    monkeypatch.setattr(engine, "ops", fake_liboat)
+    monkeypatch.setattr(engine, "SIDE_STREAM", False)
+    return engine
+
+
+@pytest.mark.parametrize("frames,objects", [(2, 3), (3, 0)])
+def test_video_engine_schedule_matches_oracle(engine_on_fake_ops, frames, objects):
+    engine = engine_on_fake_ops
+    dim, heads, depth, B = 128, 2, 2, 2
+    spec = video_tower_spec(depth=depth, dim=dim, frames=frames, grid=2, patch=16, objects=objects > 0)
+    spec["vid_proj.0.weight"], spec["vid_proj.0.bias"] = (32, dim), (32,)
+    w = fill_seeded(spec, 3, 0.05)
+    g = torch.Generator().manual_seed(4)
+    video = torch.randn(B, frames, 3, 32, 32, generator=g)
+    objs = O.synth_objects(B, frames, objects, g) if objects else None
+    coef = torch.randn(B, 32, generator=g)
+
+    p = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = O.compute_video(video, p, O.OracleCfg(heads=heads, bf16=True), objs)
+    (ref * coef).sum().backward()
+
+    eng = engine.VideoEngine(torch.device("cpu"), heads=heads)
+    params = {k: v.clone() for k, v in w.items()}
+    out = eng.forward(params, video, objs)
+    assert rel(out, ref.detach()) < 1e-3
+    named = [(k, torch.nn.Parameter(v)) for k, v in params.items()]
+    book = engine.GradBook(named, torch.device("cpu"))
+    eng.backward(params, book, coef.clone())
+    for name, ref_p in p.items():
+        assert ref_p.grad is not None, name
+        assert rel(book[name], ref_p.grad) < 3e-2, (name, rel(book[name], ref_p.grad))
+
+
+def test_text_engine_schedule_matches_oracle(engine_on_fake_ops):
+    engine = engine_on_fake_ops
+    dim, heads, layers, B, L = 128, 2, 2, 3, 6
+    spec = text_tower_spec(layers=layers, dim=dim, hidden=256, vocab=50, max_pos=16)
+    spec["txt_proj.1.weight"], spec["txt_proj.1.bias"] = (32, dim), (32,)
+    w = fill_seeded(spec, 5, 0.05)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(1, 50, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 4:] = 0
+    mask[2, 3:] = 0
+    coef = torch.randn(B, 32, generator=g)
+
+    p = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = O.compute_text({"input_ids": ids, "attention_mask": mask}, p, O.OracleCfg(heads=heads, bf16=True, text_layers=layers))
+    (ref * coef).sum().backward()
+
+    eng = engine.TextEngine(torch.device("cpu"), heads=heads)
+    params = {k: v.clone() for k, v in w.items()}
+    out = eng.forward(params, ids, mask)
+    assert rel(out, ref.detach()) < 1e-3
+    named = [(k, torch.nn.Parameter(v)) for k, v in params.items()]
+    book = engine.GradBook(named, torch.device("cpu"))
+    eng.backward(params, book, coef.clone())
+    for name, ref_p in p.items():
+        if name.endswith("k_lin.bias"):          # softmax is invariant to the key bias: the gradient is exactly zero
+            continue
+        if ref_p.grad is None:
+            continue
+        assert rel(book[name], ref_p.grad) < 8e-2, (name, rel(book[name], ref_p.grad))
