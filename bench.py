@@ -358,13 +358,13 @@ def run_ours(args):
         loss = step(dev)
     e1.record()
     barrier()
+    launches = (ops.LAUNCHES - launches0) // K
     # diagnostic: host time to enqueue ONE step into an empty stream (no queue back-pressure), not part of any metric
     t_host = time.perf_counter()
     step(dev)
     host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
     barrier()
     ms = e0.elapsed_time(e1) / K
-    launches = (ops.LAUNCHES - launches0) // K
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(loss.detach())
     t = torch.tensor([ms], device=device, dtype=torch.float64)
