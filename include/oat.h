@@ -69,10 +69,13 @@ int oat_gemm_bf16(const oat_gemm_args* args, oat_stream_t stream);
  * row statistics needed by backward. Replaces nn.LayerNorm(eps=1e-6) at video_transformer.py:164,167,174,346 and
  * DistilBERT's LayerNorm(eps=1e-12). Rows may be strided (ldx) so that only the CLS rows are normalised for :351.
  * Backward: dy = dy_bf16 (+ dy_f32); dx = add1 + add2 + LN'(dy); dgamma/dbeta are ACCUMULATED (atomics), and so is
- * dxsum[c] += sum_rows dx[row, c] (optional: the bias gradient of the GEMM that produced the LayerNorm input). */
+ * dxsum[c] += sum_rows dx[row, c] (optional: the bias gradient of the GEMM that produced the LayerNorm input).
+ * y_split (optional, bf16, pitch ldys >= 3*D): rows r with r % split_period == 0 are also written to
+ * y_split[r / split_period] as the split-bf16 operand [hi | hi | lo] (hi = bf16(y), lo = bf16(y - hi)); see
+ * oat_split3_bf16. With split_period = T these are the CLS rows of the video tower. */
 int oat_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t rows,
                       int32_t D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd,
-                      oat_stream_t stream);
+                      void* y_split, int64_t ldys, int64_t split_period, oat_stream_t stream);
 int oat_layernorm_bwd(const void* dy_bf16, int64_t lddyb, const float* dy_f32, int64_t lddyf, const float* x,
                       int64_t ldx, const float* mean, const float* rstd, const float* gamma, int64_t rows, int32_t D,
                       const float* add1, const float* add2, int64_t ldadd, float* dx, int64_t lddx, void* dx_bf16,
@@ -119,9 +122,16 @@ int oat_attn_bwd(const oat_attn_args* args, oat_stream_t stream);
  * oat_text_embed(_bwd): DistilBERT word + position embedding sum and its scatter-add gradient. */
 int oat_cast_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
                   int32_t cols_padded, int32_t relu, oat_stream_t stream);
+/* Split-bf16 operands: the rows the logits depend on directly (the video tower's CLS rows, the text tower, the two
+ * projections of oa_model.py:68-75) take three bf16 MMAs per product instead of one, x.w ~= hi.hi + hi.lo + lo.hi with
+ * hi = bf16(v), lo = bf16(v - hi), as ONE K-concatenated oat_gemm_bf16: activation rows [hi | hi | lo] (this call,
+ * dst pitch ldd >= 3*cols, optional ReLU first) against weight rows [hi | lo | hi] (oat_cast_multi kind 2). */
+int oat_split3_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
+                    int32_t relu, oat_stream_t stream);
 /* Many casts in one launch. table[n][8] (device memory) = {src fp32*, dst*, rows, cols, cols_padded, src pitch,
- * dst pitch, dst_is_f32}; chunk_prefix[n+1] = prefix sum of ceil(rows * cols_padded / 1024). Same element semantics as
- * oat_cast_bf16 (dst_is_f32 rows are plain fp32 copies, used to pack q/k/v biases). */
+ * dst pitch, kind}; chunk_prefix[n+1] = prefix sum of ceil(rows * cols_padded / 1024). kind 0: same element semantics as
+ * oat_cast_bf16; kind 1: plain fp32 copies (used to pack q/k/v biases); kind 2: split-bf16 weight copy, dst row =
+ * [hi | lo | hi] in segments of cols_padded (dst pitch >= 3 * cols_padded). */
 int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,
                    oat_stream_t stream);
 int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,

@@ -41,9 +41,35 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, _
   }
 }
 
+// Split-bf16 activation operand: dst[r] = [hi | hi | lo] (each `cols` wide), hi = bf16(x), lo = bf16(x - hi), optional
+// ReLU first. Against a weight row [hi | lo | hi] one K-concatenated GEMM yields hi.hi + hi.lo + lo.hi.
+__global__ void split3_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                   long long ldd, long long rows, int cols, int relu) {
+  const int vec_per_row = cols >> 2;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const int c = static_cast<int>(idx - r * vec_per_row) << 2;
+    float4 f = *reinterpret_cast<const float4*>(src + r * lds + c);
+    if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+    uint2 hi, lo;
+    hi.x = pack_bf16x2(f.x, f.y);
+    hi.y = pack_bf16x2(f.z, f.w);
+    const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+    lo.x = pack_bf16x2(f.x - h0.x, f.y - h0.y);
+    lo.y = pack_bf16x2(f.z - h1.x, f.w - h1.y);
+    __nv_bfloat16* d = dst + r * ldd + c;
+    *reinterpret_cast<uint2*>(d) = hi;
+    *reinterpret_cast<uint2*>(d + cols) = hi;
+    *reinterpret_cast<uint2*>(d + 2 * cols) = lo;
+  }
+}
+
 // Many casts in one launch (the bf16 operand copies of every weight of a tower, re-packed each step): a device table
-// row = {src, dst, rows, cols, cols_padded, src pitch, dst pitch, dst_is_f32}, chunk_prefix = prefix sum of the
-// 1024-element chunks of each tensor's padded (rows x cols_padded) extent. dst_is_f32 rows are plain copies (bias packing).
+// row = {src, dst, rows, cols, cols_padded, src pitch, dst pitch, kind}, chunk_prefix = prefix sum of the
+// 1024-element chunks of each tensor's padded (rows x cols_padded) extent. kind 0: bf16 copy; 1: plain fp32 copy (bias
+// packing); 2: split-bf16 weight copy, dst row = [hi | lo | hi] with segments cols_padded wide (pitch >= 3 * cols_padded).
 __global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __restrict__ table,
                                                         const long long* __restrict__ chunk_prefix, int n,
                                                         long long total_chunks) {
@@ -69,10 +95,21 @@ __global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __rest
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = (c + k < cols) ? sp[k] : 0.f;
     }
-    if (t[7] != 0) {
+    if (t[7] == 1) {
       float* d = reinterpret_cast<float*>(t[1]) + r * ldd + c;
 #pragma unroll
       for (int k = 0; k < 4; ++k) d[k] = v[k];
+    } else if (t[7] == 2) {
+      uint2 hi, lo;
+      hi.x = pack_bf16x2(v[0], v[1]);
+      hi.y = pack_bf16x2(v[2], v[3]);
+      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+      lo.x = pack_bf16x2(v[0] - h0.x, v[1] - h0.y);
+      lo.y = pack_bf16x2(v[2] - h1.x, v[3] - h1.y);
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(t[1]) + r * ldd + c;
+      *reinterpret_cast<uint2*>(d) = hi;
+      *reinterpret_cast<uint2*>(d + colsp) = lo;
+      *reinterpret_cast<uint2*>(d + 2 * colsp) = hi;
     } else {
       uint2 pk;
       pk.x = pack_bf16x2(v[0], v[1]);
@@ -303,6 +340,20 @@ extern "C" int oat_cast_bf16(const float* src, int64_t lds, void* dst, int64_t l
   cast_bf16_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
       src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded, relu);
   return check_launch("cast_bf16_kernel");
+}
+
+extern "C" int oat_split3_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols,
+                               int32_t relu, oat_stream_t stream) {
+  OAT_REQUIRE(cols > 0 && cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldd >= 3LL * cols,
+              "oat_split3_bf16: cols=%d lds=%lld ldd=%lld (multiples of 4, ldd >= 3*cols)", cols, (long long)lds,
+              (long long)ldd);
+  OAT_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+              "oat_split3_bf16: src must be 16-byte and dst 8-byte aligned");
+  if (rows <= 0) return OAT_OK;
+  const long long total = rows * (cols / 4);
+  split3_bf16_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, relu);
+  return check_launch("split3_bf16_kernel");
 }
 
 extern "C" int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,

@@ -17,11 +17,14 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, long long rows, __nv_bfloat16* __restrict__ y_bf16,
                      long long ldy, float* __restrict__ y_f32, long long ldyf, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out) {
+                     float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y_split, long long ldys,
+                     long long split_period) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
+  // split-bf16 copy [hi | hi | lo] of every split_period-th row (the CLS rows of the video tower, period = T)
+  __nv_bfloat16* ys = (y_split != nullptr && row % split_period == 0) ? y_split + (row / split_period) * ldys : nullptr;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   float4 v[NV];
   float s = 0.f;
@@ -57,6 +60,17 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
       pk.x = pack_bf16x2(o.x, o.y);
       pk.y = pack_bf16x2(o.z, o.w);
       reinterpret_cast<uint2*>(y_bf16 + row * ldy)[i * 32 + lane] = pk;
+    }
+    if (ys != nullptr) {
+      uint2 hi, lo;
+      hi.x = pack_bf16x2(o.x, o.y);
+      hi.y = pack_bf16x2(o.z, o.w);
+      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+      lo.x = pack_bf16x2(o.x - h0.x, o.y - h0.y);
+      lo.y = pack_bf16x2(o.z - h1.x, o.w - h1.y);
+      reinterpret_cast<uint2*>(ys)[i * 32 + lane] = hi;
+      reinterpret_cast<uint2*>(ys + D)[i * 32 + lane] = hi;
+      reinterpret_cast<uint2*>(ys + 2 * D)[i * 32 + lane] = lo;
     }
   }
 }
@@ -293,11 +307,12 @@ layernorm_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long
 template <int NV>
 static int launch_ln_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                          long long rows, void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean,
-                         float* rstd, cudaStream_t s) {
+                         float* rstd, void* y_split, long long ldys, long long split_period, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
   layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(x, ldx, gamma, beta, eps, rows,
                                                           reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, y_f32, ldyf,
-                                                          mean, rstd);
+                                                          mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_split), ldys,
+                                                          split_period);
   return check_launch("layernorm_fwd_kernel");
 }
 
@@ -340,18 +355,22 @@ static int launch_ln_bwd(const void* dyb, long long lddyb, const float* dyf, lon
 
 extern "C" int oat_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                                  int64_t rows, int32_t D, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf,
-                                 float* mean, float* rstd, oat_stream_t stream) {
+                                 float* mean, float* rstd, void* y_split, int64_t ldys, int64_t split_period,
+                                 oat_stream_t stream) {
   using namespace oat;
   OAT_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024, "oat_layernorm_fwd: D=%d must be a multiple of 128, <= 1024", D);
   OAT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldyf % 4 == 0, "oat_layernorm_fwd: leading dims must be multiples of 4");
+  OAT_REQUIRE(y_split == nullptr || (split_period >= 1 && ldys % 4 == 0 && ldys >= 3 * D),
+              "oat_layernorm_fwd: y_split needs split_period >= 1 and a pitch >= 3*D that is a multiple of 4");
+  if (y_split == nullptr) split_period = 1;
   if (rows == 0) return OAT_OK;
   cudaStream_t s = as_stream(stream);
   switch (D / 128) {
-    case 1: return launch_ln_fwd<1>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
-    case 2: return launch_ln_fwd<2>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
-    case 4: return launch_ln_fwd<4>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
-    case 6: return launch_ln_fwd<6>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
-    case 8: return launch_ln_fwd<8>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, s);
+    case 1: return launch_ln_fwd<1>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, y_split, ldys, split_period, s);
+    case 2: return launch_ln_fwd<2>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, y_split, ldys, split_period, s);
+    case 4: return launch_ln_fwd<4>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, y_split, ldys, split_period, s);
+    case 6: return launch_ln_fwd<6>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, y_split, ldys, split_period, s);
+    case 8: return launch_ln_fwd<8>(x, ldx, gamma, beta, eps, rows, y_bf16, ldy, y_f32, ldyf, mean, rstd, y_split, ldys, split_period, s);
     default: return set_error(OAT_ERR_ARG, "oat_layernorm_fwd: unsupported D=%d (128, 256, 512, 768, 1024)", D);
   }
 }

@@ -9,6 +9,14 @@ follow the reference modules line by line:
 Arithmetic contract (mirrored by oracle/oracle.py in bf16 mode): GEMM / attention operands are bf16, accumulation
 fp32; residual stream, LayerNorm, softmax, logits, loss and every parameter gradient are fp32; activation gradients
 that feed a GEMM are bf16.
+
+Split-bf16 rows (forward only, OAT_SPLIT=0 turns it off): the logits depend DIRECTLY on the CLS row of the video
+tower, on the (tiny) text tower and on the two projections; operand rounding there (2^-9 per product) is what moves
+bf16 logits by ~1e-3 at the benchmark geometry, while the other F*n token rows only reach the CLS row through
+attention averages over hundreds of keys. Those rows therefore take three bf16 MMAs per product instead of one:
+x = hi + lo, w = hi + lo, x.w ~= hi.hi + hi.lo + lo.hi, laid out so that ONE K-concatenated GEMM does it
+(activation rows [hi | hi | lo], weight rows [hi | lo | hi]); where the plain GEMM already produced hi.hi (+ bias +
+residual) in fp32, only the correction [hi | lo] x [lo | hi] is accumulated on top. Cost: ~1 % of the step.
 """
 import os
 
@@ -23,6 +31,7 @@ Q_SCALE = HEAD_DIM ** -0.5
 OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py:593-650)
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
+SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
 
 
 class _Buffers:
@@ -45,18 +54,40 @@ class _Buffers:
         return t
 
 
-def _w16(bufs, name, w, rows=None, cols=None, pitch=None, plan=None):
+def _w16(bufs, name, w, rows=None, cols=None, pitch=None, plan=None, split=False):
     """bf16 operand copy of an fp32 weight (re-packed every step: the optimizer owns the fp32 master). With a CastPlan
-    the copy is only registered; plan.run() performs every registered copy of the tower in one launch."""
+    the copy is only registered; plan.run() performs every registered copy of the tower in one launch.
+    split=True: the copy is [rows, 3*cols] = [hi | lo | hi] (hi = bf16(w), lo = bf16(w - hi)); its first `cols`
+    columns are the ordinary bf16 operand."""
     w2 = w.detach().reshape(w.shape[0], -1)
     rows = w2.shape[0] if rows is None else rows
     cols = w2.shape[1] if cols is None else cols
+    if split:
+        assert plan is not None and pitch is None
+        dst = bufs.get(name, (rows, 3 * cols), BF)
+        plan.add(w2, dst, rows=rows, cols=cols, split=True)
+        return dst
     dst = bufs.get(name, (rows, pitch or cols), BF)
     if plan is not None:
         plan.add(w2, dst, rows=rows, cols=cols)
     else:
         ops.cast_bf16(w2, dst, rows=rows, cols=cols)
     return dst
+
+
+def _hi(w3):
+    """[N, K] bf16 operand inside a split weight copy [N, 3K] = [hi | lo | hi]."""
+    return w3[:, :w3.shape[1] // 3]
+
+
+def _lo(w3):
+    k = w3.shape[1] // 3
+    return w3[:, k:2 * k]
+
+
+def _lohi(w3):
+    """[lo | hi]: against activation columns [hi | lo] this is the correction hi.lo + lo.hi."""
+    return w3[:, w3.shape[1] // 3:]
 
 
 class GradBook:
@@ -118,19 +149,33 @@ class VideoEngine:
 
         # --- bf16 operand copies of every weight of the tower: one launch
         plan = self._plan
-        W = {"patch": _w16(bufs, "w.patch", p[prefix + "patch_embed.proj.weight"], plan=plan)}
+        split = SPLIT
+        W, W3 = {}, {}          # W: ordinary bf16 operands; W3: split copies [hi | lo | hi] (W[key] is then a view of W3[key])
+
+        def weight(key, name, param):
+            if split:
+                W3[key] = _w16(bufs, name + ".s3", param, plan=plan, split=True)
+                W[key] = _hi(W3[key])
+            else:
+                W[key] = _w16(bufs, name, param, plan=plan)
+
+        W["patch"] = _w16(bufs, "w.patch", p[prefix + "patch_embed.proj.weight"], plan=plan)
         if O > 0:
             W["object"] = _w16(bufs, "w.object", p[prefix + "object_embed.weight"], pitch=OBJ_PITCH, plan=plan)
         for i in range(depth):
             b = "%sblocks.%d." % (prefix, i)
             for tag, aname in (("t", "timeattn"), ("s", "attn")):
-                W[(i, tag, "qkv")] = _w16(bufs, "w.%s.qkv.%d" % (tag, i), p[b + aname + ".qkv.weight"], plan=plan)
-                W[(i, tag, "proj")] = _w16(bufs, "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"], plan=plan)
-            W[(i, "fc1")] = _w16(bufs, "w.fc1.%d" % i, p[b + "mlp.fc1.weight"], plan=plan)
-            W[(i, "fc2")] = _w16(bufs, "w.fc2.%d" % i, p[b + "mlp.fc2.weight"], plan=plan)
+                weight((i, tag, "qkv"), "w.%s.qkv.%d" % (tag, i), p[b + aname + ".qkv.weight"])
+                weight((i, tag, "proj"), "w.%s.proj.%d" % (tag, i), p[b + aname + ".proj.weight"])
+            weight((i, "fc1"), "w.fc1.%d" % i, p[b + "mlp.fc1.weight"])
+            weight((i, "fc2"), "w.fc2.%d" % i, p[b + "mlp.fc2.weight"])
         if proj is not None:
-            W["vid_proj"] = _w16(bufs, "w.vid_proj", p[proj[0]], plan=plan)
+            weight("vid_proj", "w.vid_proj", p[proj[0]])
         plan.run()
+
+        def cls(t):
+            """The B CLS rows (token 0 of every video) of an [M, w] token buffer, as a strided [B, w] view."""
+            return t.view(B, T * t.shape[1])[:, :t.shape[1]]
 
         # --- patch / object embedding + token assembly (video_transformer.py:71-76, 303-325)
         K0 = C * ps * ps
@@ -159,17 +204,22 @@ class VideoEngine:
             x = xs[i]
 
             def ln(tag, src, wname):
+                """LayerNorm of every token row -> bf16 GEMM operand; the CLS rows also leave as [hi | hi | lo]."""
                 h = bufs.get("h%s.%d" % (tag, i), (M, D), BF)
                 mean = bufs.get("mean%s.%d" % (tag, i), (M,), F32)
                 rstd = bufs.get("rstd%s.%d" % (tag, i), (M,), F32)
+                c3 = bufs.get("c3." + tag, (B, 3 * D), BF) if split else None
                 ops.layernorm_fwd(src, p[b + wname + ".weight"], p[b + wname + ".bias"], self.eps, y_bf16=h,
-                                  mean=mean, rstd=rstd)
-                return h, mean, rstd
+                                  mean=mean, rstd=rstd, y_split=c3, split_period=T)
+                return h, mean, rstd, c3
 
-            def attention(tag, mode, h, aname, resid, out):
+            def attention(tag, mode, h, c3, aname, resid, out):
                 wqkv = W[(i, tag, "qkv")]
                 qkv = bufs.get("qkv%s.%d" % (tag, i), (M, 3 * D), BF)
                 ops.gemm(h, wqkv, bias=p[b + aname + ".qkv.bias"], scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
+                if split:       # CLS rows again, three-term product
+                    ops.gemm(c3, W3[(i, tag, "qkv")], bias=p[b + aname + ".qkv.bias"], scale_cols=D, scale=Q_SCALE,
+                             out_bf16=cls(qkv))
                 a = bufs.get("a%s.%d" % (tag, i), (M, D), BF)
                 lse = bufs.get("lse%s.%d" % (tag, i), (B * H * T,), F32)
                 ws = bufs.get("attn_ws", (max(1, ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, Fr, n),
@@ -177,26 +227,37 @@ class VideoEngine:
                 ops.attn_fwd(mode, B, T, H, Fr, n, qkv, a, lse, cls_ws=ws)
                 wproj = W[(i, tag, "proj")]
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
+                if split:       # the attention output is bf16 already (lo = 0): add a . w_lo on the CLS rows
+                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True)
                 return wqkv, wproj, qkv, a, lse
 
             # time attention on norm3(x); residual from x                    (video_transformer.py:164-165)
-            L["h3"], L["m3"], L["r3"] = ln("3", x, "norm3")
+            L["h3"], L["m3"], L["r3"], c3 = ln("3", x, "norm3")
             tr = bufs.get("tr.%d" % i, (M, D), F32)
-            L["wqkv_t"], L["wproj_t"], L["qkv_t"], L["a_t"], L["lse_t"] = attention("t", ops.MODE_TIME, L["h3"],
+            L["wqkv_t"], L["wproj_t"], L["qkv_t"], L["a_t"], L["lse_t"] = attention("t", ops.MODE_TIME, L["h3"], c3,
                                                                                     "timeattn", x, tr)
             # space attention on norm1(time_residual); residual from x again  (:167-170)
-            L["h1"], L["m1"], L["r1"] = ln("1", tr, "norm1")
+            L["h1"], L["m1"], L["r1"], c3 = ln("1", tr, "norm1")
             sr = bufs.get("sr.%d" % i, (M, D), F32)
-            L["wqkv_s"], L["wproj_s"], L["qkv_s"], L["a_s"], L["lse_s"] = attention("s", ops.MODE_SPACE, L["h1"],
+            L["wqkv_s"], L["wproj_s"], L["qkv_s"], L["a_s"], L["lse_s"] = attention("s", ops.MODE_SPACE, L["h1"], c3,
                                                                                     "attn", x, sr)
             # MLP on norm2(space_residual)                                   (:174, Mlp :45-51)
-            L["h2"], L["m2"], L["r2"] = ln("2", sr, "norm2")
+            L["h2"], L["m2"], L["r2"], c3 = ln("2", sr, "norm2")
             L["w1"] = W[(i, "fc1")]
             L["w2"] = W[(i, "fc2")]
             u = bufs.get("u.%d" % i, (M, 4 * D), BF)
             g = bufs.get("g.%d" % i, (M, 4 * D), BF)
             ops.gemm(L["h2"], L["w1"], bias=p[b + "mlp.fc1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
+            g3 = None
+            if split:           # CLS rows: three-term fc1, GELU kept in fp32 and split for fc2
+                g32 = bufs.get("g32", (B, 4 * D), F32)
+                ops.gemm(c3, W3[(i, "fc1")], bias=p[b + "mlp.fc1.bias"], act=ops.ACT_GELU, out_f32=g32,
+                         out_bf16=cls(g), out2_bf16=cls(u))
+                g3 = bufs.get("g3", (B, 12 * D), BF)
+                ops.split3_bf16(g32, g3)
             ops.gemm(g, L["w2"], bias=p[b + "mlp.fc2.bias"], residual=sr, out_f32=xs[i + 1])
+            if split:           # + g_hi . w_lo + g_lo . w_hi on the CLS rows
+                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True)
             L["tr"], L["sr"], L["u"], L["g"] = tr, sr, u, g
             layers.append(L)
 
@@ -205,15 +266,19 @@ class VideoEngine:
         cls16 = bufs.get("cls16", (B, D), BF)
         mf = bufs.get("meanf", (B,), F32)
         rf = bufs.get("rstdf", (B,), F32)
+        cls3 = bufs.get("cls3", (B, 3 * D), BF) if (split and proj is not None) else None
         ops.layernorm_fwd(xs[depth], p[prefix + "norm.weight"], p[prefix + "norm.bias"], self.eps, rows=B, ldx=T * D,
-                          y_bf16=cls16, y_f32=cls32, mean=mf, rstd=rf)
+                          y_bf16=cls16, y_f32=cls32, mean=mf, rstd=rf, y_split=cls3, split_period=1)
         out = cls32.clone() if proj is None else None
         wv = None
         if proj is not None:
             wv = W["vid_proj"]
             P = p[proj[0]].shape[0]
             out = torch.empty((B, P), dtype=F32, device=self.device)
-            ops.gemm(cls16, wv, bias=p[proj[1]], out_f32=out)
+            if split:
+                ops.gemm(cls3, W3["vid_proj"], bias=p[proj[1]], out_f32=out)
+            else:
+                ops.gemm(cls16, wv, bias=p[proj[1]], out_f32=out)
         if save:
             self.saved = dict(B=B, Fr=Fr, N=N, O=O, n=n, T=T, M=M, D=D, depth=depth, xs=xs, layers=layers, cols=cols,
                               obj16=obj16, cls16=cls16, mf=mf, rf=rf, wv=wv, proj=proj, prefix=prefix,
@@ -385,71 +450,97 @@ class TextEngine:
             key_mask = attention_mask.to(torch.int32).contiguous().view(-1)
 
         # --- bf16 operand copies of every weight (q / k / v packed into one [3D, D] operand, biases likewise): one launch
+        # With SPLIT every weight copy is [hi | lo | hi] and every activation operand [hi | hi | lo]: the whole (tiny)
+        # text tower runs its forward products in three-term split-bf16 arithmetic (module docstring).
         plan = self._plan
+        split = SPLIT
+        S3 = 3 if split else 1
         W = {}
         for i in range(layers_n):
             b = "%stransformer.layer.%d." % (prefix, i)
-            wqkv = bufs.get("w.qkv.%d" % i, (3 * D, D), BF)
+            wqkv = bufs.get("w.qkv.%d.%d" % (i, S3), (3 * D, S3 * D), BF)
             bqkv = bufs.get("b.qkv.%d" % i, (3 * D,), F32)
             for j, nm in enumerate(("q_lin", "k_lin", "v_lin")):
-                plan.add(p[b + "attention.%s.weight" % nm], wqkv[j * D:(j + 1) * D])
+                plan.add(p[b + "attention.%s.weight" % nm], wqkv[j * D:(j + 1) * D], split=split)
                 plan.add(p[b + "attention.%s.bias" % nm].detach().view(1, D), bqkv[j * D:(j + 1) * D].view(1, D))
             W[(i, "qkv")], W[(i, "bqkv")] = wqkv, bqkv
-            W[(i, "o")] = _w16(bufs, "w.o.%d" % i, p[b + "attention.out_lin.weight"], plan=plan)
-            W[(i, "l1")] = _w16(bufs, "w.l1.%d" % i, p[b + "ffn.lin1.weight"], plan=plan)
-            W[(i, "l2")] = _w16(bufs, "w.l2.%d" % i, p[b + "ffn.lin2.weight"], plan=plan)
+            W[(i, "o")] = _w16(bufs, "w.o.%d" % i, p[b + "attention.out_lin.weight"], plan=plan, split=split)
+            W[(i, "l1")] = _w16(bufs, "w.l1.%d" % i, p[b + "ffn.lin1.weight"], plan=plan, split=split)
+            W[(i, "l2")] = _w16(bufs, "w.l2.%d" % i, p[b + "ffn.lin2.weight"], plan=plan, split=split)
         if proj is not None:
-            W["txt_proj"] = _w16(bufs, "w.txt_proj", p[proj[0]], plan=plan)
+            W["txt_proj"] = _w16(bufs, "w.txt_proj", p[proj[0]], plan=plan, split=split)
         plan.run()
+        hi = _hi if split else (lambda w: w)
 
         emb = bufs.get("emb", (M, D), F32)
         ops.text_embed(ids, word, pos, emb, Lq)
 
         def ln(tag, src, wname):
-            y16 = bufs.get("y16." + tag, (M, D), BF)
+            """-> (GEMM operand [M, S3*D], its plain bf16 part [M, D], fp32 value, mean, rstd)"""
             y32 = bufs.get("y32." + tag, (M, D), F32)
             mean = bufs.get("mean." + tag, (M,), F32)
             rstd = bufs.get("rstd." + tag, (M,), F32)
+            if split:
+                y3 = bufs.get("y3." + tag, (M, 3 * D), BF)
+                ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_f32=y32, mean=mean,
+                                  rstd=rstd, y_split=y3, split_period=1)
+                return y3, y3[:, :D], y32, mean, rstd
+            y16 = bufs.get("y16." + tag, (M, D), BF)
             ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_bf16=y16, y_f32=y32,
                               mean=mean, rstd=rstd)
-            return y16, y32, mean, rstd
+            return y16, y16, y32, mean, rstd
 
-        x16, x32, m0, r0 = ln("emb", emb, prefix + "embeddings.LayerNorm")
+        xop, x16, x32, m0, r0 = ln("emb", emb, prefix + "embeddings.LayerNorm")
         layers = []
         for i in range(layers_n):
             b = "%stransformer.layer.%d." % (prefix, i)
             L = {"x16": x16, "x32": x32}
             wqkv, bqkv = W[(i, "qkv")], W[(i, "bqkv")]
             qkv = bufs.get("qkv.%d" % i, (M, 3 * D), BF)
-            ops.gemm(x16, wqkv, bias=bqkv, scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
+            ops.gemm(xop, wqkv, bias=bqkv, scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
             ctx = bufs.get("ctx.%d" % i, (M, D), BF)
             lse = bufs.get("lse.%d" % i, (B * H * Lq,), F32)
             ops.attn_fwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, qkv, ctx, lse, key_mask)
             wo = W[(i, "o")]
             sa_sum = bufs.get("sa_sum.%d" % i, (M, D), F32)
-            ops.gemm(ctx, wo, bias=p[b + "attention.out_lin.bias"], residual=x32, out_f32=sa_sum)
-            y16, y32, m1, r1 = ln("sa.%d" % i, sa_sum, b + "sa_layer_norm")
+            ops.gemm(ctx, hi(wo), bias=p[b + "attention.out_lin.bias"], residual=x32, out_f32=sa_sum)
+            if split:           # ctx is bf16 already: + ctx . w_lo
+                ops.gemm(ctx, _lo(wo), out_f32=sa_sum, accumulate=True)
+            yop, y16, y32, m1, r1 = ln("sa.%d" % i, sa_sum, b + "sa_layer_norm")
             w1, w2 = W[(i, "l1")], W[(i, "l2")]
             Hd = w1.shape[0]
             u = bufs.get("u.%d" % i, (M, Hd), BF)
             g = bufs.get("g.%d" % i, (M, Hd), BF)
-            ops.gemm(y16, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
             ffn_sum = bufs.get("ffn_sum.%d" % i, (M, D), F32)
-            ops.gemm(g, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
-            x16, x32, m2, r2 = ln("out.%d" % i, ffn_sum, b + "output_layer_norm")
-            L.update(wqkv=wqkv, qkv=qkv, ctx=ctx, lse=lse, wo=wo, sa_sum=sa_sum, y16=y16, m1=m1, r1=r1, w1=w1, w2=w2,
-                     u=u, g=g, ffn_sum=ffn_sum, m2=m2, r2=r2)
+            if split:
+                g32 = bufs.get("g32", (M, Hd), F32)
+                ops.gemm(yop, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_f32=g32, out_bf16=g, out2_bf16=u)
+                g3 = bufs.get("g3", (M, 3 * Hd), BF)
+                ops.split3_bf16(g32, g3)
+                ops.gemm(g3, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
+            else:
+                ops.gemm(y16, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
+                ops.gemm(g, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
+            xop, x16, x32, m2, r2 = ln("out.%d" % i, ffn_sum, b + "output_layer_norm")
+            L.update(wqkv=hi(wqkv), qkv=qkv, ctx=ctx, lse=lse, wo=hi(wo), sa_sum=sa_sum, y16=y16, m1=m1, r1=r1,
+                     w1=hi(w1), w2=hi(w2), u=u, g=g, ffn_sum=ffn_sum, m2=m2, r2=r2)
             layers.append(L)
 
         # last_hidden_state[:, 0] -> ReLU -> Linear (oa_model.py:113-121, 68-69)
         out = x32.view(B, Lq, D)[:, 0].clone() if proj is None else None
         r16 = wt = None
         if proj is not None:
-            r16 = bufs.get("relu16", (B, D), BF)
-            ops.cast_bf16(x32, r16, rows=B, cols=D, lds=Lq * D, relu=True)
-            wt = W["txt_proj"]
+            wt = hi(W["txt_proj"])
             out = torch.empty((B, p[proj[0]].shape[0]), dtype=F32, device=self.device)
-            ops.gemm(r16, wt, bias=p[proj[1]], out_f32=out)
+            if split:
+                r3 = bufs.get("relu3", (B, 3 * D), BF)
+                ops.split3_bf16(x32, r3, rows=B, cols=D, lds=Lq * D, relu=True)
+                r16 = r3[:, :D]
+                ops.gemm(r3, W["txt_proj"], bias=p[proj[1]], out_f32=out)
+            else:
+                r16 = bufs.get("relu16", (B, D), BF)
+                ops.cast_bf16(x32, r16, rows=B, cols=D, lds=Lq * D, relu=True)
+                ops.gemm(r16, wt, bias=p[proj[1]], out_f32=out)
         if save:
             self.saved = dict(B=B, Lq=Lq, M=M, D=D, ids=ids, key_mask=key_mask, emb=emb, m0=m0, r0=r0, layers=layers,
                               last32=x32, r16=r16, wt=wt, proj=proj, prefix=prefix)

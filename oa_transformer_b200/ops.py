@@ -97,17 +97,23 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
 _i64, _i32, _f32, _vp, _sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f32=None, mean=None, rstd=None):
-    """Row LayerNorm of fp32 x (rows x D, row pitch ldx) -> bf16 and/or fp32 outputs, plus mean / rstd."""
+def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f32=None, mean=None, rstd=None,
+                  y_split=None, split_period=1):
+    """Row LayerNorm of fp32 x (rows x D, row pitch ldx) -> bf16 and/or fp32 outputs, plus mean / rstd.
+    y_split (bf16 [ceil(rows / split_period), 3*D]): split-bf16 copy [hi | hi | lo] of every split_period-th row."""
     D = gamma.numel()
     rows = x.shape[0] if rows is None else rows
     ldx = x.stride(0) if ldx is None else ldx
+    if y_split is not None:
+        assert y_split.dtype == torch.bfloat16 and y_split.shape[1] == 3 * D
+        assert y_split.shape[0] * split_period >= rows
     _count(1)
     check(lib().oat_layernorm_fwd(
         ptr(x), _i64(ldx), ptr(gamma), ptr(beta), _f32(eps), _i64(rows), _i32(D),
         ptr(y_bf16), _i64(y_bf16.stride(0) if y_bf16 is not None else 0),
         ptr(y_f32), _i64(y_f32.stride(0) if y_f32 is not None else 0),
-        ptr(mean), ptr(rstd), stream_ptr()), "oat_layernorm_fwd")
+        ptr(mean), ptr(rstd), ptr(y_split), _i64(y_split.stride(0) if y_split is not None else 0),
+        _i64(split_period), stream_ptr()), "oat_layernorm_fwd")
 
 
 def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None, ldx=None, lddyf=None, add1=None,
@@ -214,6 +220,17 @@ def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
                               _i32(dst.shape[1]), _i32(1 if relu else 0), stream_ptr()), "oat_cast_bf16")
 
 
+def split3_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
+    """dst (bf16 [rows, 3*cols]) <- split-bf16 activation operand [hi | hi | lo] of src (fp32), optional ReLU first."""
+    rows = dst.shape[0] if rows is None else rows
+    cols = src.shape[-1] if cols is None else cols
+    lds = (src.stride(0) if src.dim() == 2 else cols) if lds is None else lds
+    assert dst.dtype == torch.bfloat16 and dst.shape[1] == 3 * cols and src.dtype == torch.float32
+    _count(1)
+    check(lib().oat_split3_bf16(ptr(src), _i64(lds), ptr(dst), _i64(dst.stride(0)), _i64(rows), _i32(cols),
+                                _i32(1 if relu else 0), stream_ptr()), "oat_split3_bf16")
+
+
 class CastPlan:
     """A set of fp32 -> bf16 (or fp32 -> fp32) 2-D copies executed by ONE launch (oat_cast_multi). The device table is
     built once and re-used for as long as the source / destination pointers stay the same."""
@@ -223,26 +240,29 @@ class CastPlan:
         self._key = None
         self._dev = None
 
-    def add(self, src, dst, rows=None, cols=None):
-        """dst[:rows, :] <- src (2-D view, last dim contiguous); columns [cols, dst.shape[1]) are zero-filled."""
+    def add(self, src, dst, rows=None, cols=None, split=False):
+        """dst[:rows, :] <- src (2-D view, last dim contiguous); columns [cols, dst.shape[1]) are zero-filled.
+        split=True: dst is [rows, 3*w] and receives the split-bf16 weight copy [hi | lo | hi] (segments w wide)."""
         src2 = src.detach()
         src2 = src2.reshape(src2.shape[0], -1) if src2.dim() != 2 else src2
         rows = src2.shape[0] if rows is None else rows
         cols = src2.shape[1] if cols is None else cols
         assert src2.dtype == torch.float32 and src2.stride(1) == 1 and dst.dim() == 2 and dst.stride(1) == 1
-        assert dst.shape[1] % 4 == 0 and dst.stride(0) % 4 == 0 and dst.shape[1] >= cols
-        self.items.append((src2, dst, rows, cols))
+        width = dst.shape[1] // 3 if split else dst.shape[1]
+        assert (not split) or (dst.shape[1] % 3 == 0 and dst.dtype == torch.bfloat16)
+        assert width % 4 == 0 and dst.stride(0) % 4 == 0 and width >= cols
+        self.items.append((src2, dst, rows, cols, split))
 
     def run(self):
         if not self.items:
             return
-        key = tuple((s.data_ptr(), d.data_ptr(), r, c) for s, d, r, c in self.items)
+        key = tuple((s.data_ptr(), d.data_ptr(), r, c, sp) for s, d, r, c, sp in self.items)
         if key != self._key:
             rows_, prefix = [], [0]
-            for s, d, r, c in self.items:
-                colsp = d.shape[1]
+            for s, d, r, c, sp in self.items:
+                colsp = d.shape[1] // 3 if sp else d.shape[1]
                 rows_.append([s.data_ptr(), d.data_ptr(), r, c, colsp, s.stride(0), d.stride(0),
-                              1 if d.dtype == torch.float32 else 0])
+                              2 if sp else (1 if d.dtype == torch.float32 else 0)])
                 prefix.append(prefix[-1] + (r * colsp + 1023) // 1024)
             dev = self.items[0][1].device
             self._dev = (torch.tensor(rows_, dtype=torch.int64, device=dev),

@@ -21,6 +21,12 @@ Two arithmetic modes:
   cfg.bf16 = True  : every matrix-product OPERAND is rounded to bf16 (fp32 accumulate); residual stream, LayerNorm,
                      softmax, loss stay fp32; dgrad results are rounded to bf16. This mirrors the storage points of
                      the CUDA path exactly, so it isolates accumulation-order differences (gate 1e-3).
+  cfg.split = True : (with bf16) the rows the logits depend on DIRECTLY - the CLS row of every video-tower linear, every
+                     text-tower linear, both projections - use split-bf16 operands in the forward pass: x = hi + lo
+                     with hi = bf16(x), lo = bf16(x - hi), same for w, product = hi.hi + hi.lo + lo.hi (three bf16
+                     MMAs, fp32 accumulate; relative error ~2^-17 instead of 2^-9). The other F*n token rows reach
+                     the CLS row only through attention averages over hundreds of keys, where operand rounding noise
+                     averages out. The backward pass is the plain bf16 one. This is the CUDA path's contract.
 """
 import math
 from dataclasses import dataclass
@@ -34,6 +40,7 @@ import torch.nn.functional as F
 class OracleCfg:
     heads: int = 12
     bf16: bool = False
+    split: bool = True              # split-bf16 (3-term) forward products on the CLS / text / projection rows (bf16 mode)
     ln_eps_video: float = 1e-6      # video_transformer.py:228
     ln_eps_text: float = 1e-12      # HF DistilBERT Embeddings / TransformerBlock LayerNorm
     text_layers: int = 6
@@ -82,10 +89,32 @@ class _LinearBF16(torch.autograd.Function):
         return dx, dw, db
 
 
-def linear(x, w, b, cfg):
+class _LinearSplit(torch.autograd.Function):
+    """Forward with split-bf16 operands: (x_hi + x_lo)(w_hi + w_lo)^T without the lo.lo term; backward as _LinearBF16."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xh, wh = _r(x), _r(w)
+        xl, wl = _r(x - xh), _r(w - wh)
+        ctx.save_for_backward(xh, wh)
+        ctx.has_bias = b is not None
+        y = xh @ wh.t() + (xh @ wl.t() + xl @ wh.t())
+        return y + b if b is not None else y
+
+    backward = staticmethod(_LinearBF16.backward)
+
+
+def linear(x, w, b, cfg, split=False):
     if cfg.bf16:
-        return _LinearBF16.apply(x, w, b)
+        return (_LinearSplit if (split and cfg.split) else _LinearBF16).apply(x, w, b)
     return F.linear(x, w, b)
+
+
+def linear_cls(x, w, b, cfg):
+    """Linear over (B, T, D) tokens whose CLS row (token 0) takes the split-bf16 product (see the module docstring)."""
+    if not (cfg.bf16 and cfg.split):
+        return linear(x, w, b, cfg)
+    return torch.cat([linear(x[:, :1], w, b, cfg, split=True), linear(x[:, 1:], w, b, cfg)], dim=1)
 
 
 def _ste(x, cfg):
@@ -195,16 +224,16 @@ def divided_attention(x, p, pre, mode, Fr, n, cfg):
     B, T, D = x.shape
     h = cfg.heads
     d = D // h
-    qkv = linear(x, p[pre + "qkv.weight"], p[pre + "qkv.bias"], cfg).reshape(B, T, 3, h, d)
+    qkv = linear_cls(x, p[pre + "qkv.weight"], p[pre + "qkv.bias"], cfg).reshape(B, T, 3, h, d)
     q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))        # (B, h, T, d)
     out = divided_attention_core(q * (d ** -0.5), k, v, mode, Fr, n, cfg)
-    return linear(out, p[pre + "proj.weight"], p[pre + "proj.bias"], cfg)
+    return linear_cls(_ste(out, cfg), p[pre + "proj.weight"], p[pre + "proj.bias"], cfg)   # attention output is stored bf16
 
 
 def mlp(x, p, pre, cfg):
     """Mlp.forward (video_transformer.py:45-51), dropout p=0."""
-    u = linear(x, p[pre + "fc1.weight"], p[pre + "fc1.bias"], cfg)
-    return linear(gelu(u, cfg), p[pre + "fc2.weight"], p[pre + "fc2.bias"], cfg)
+    u = linear_cls(x, p[pre + "fc1.weight"], p[pre + "fc1.bias"], cfg)
+    return linear_cls(gelu(u, cfg), p[pre + "fc2.weight"], p[pre + "fc2.bias"], cfg)
 
 
 def space_time_block(x, p, pre, Fr, n, cfg):
@@ -257,14 +286,14 @@ def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model."):
         def heads(t):
             return t.reshape(B, L, h, d).permute(0, 2, 1, 3)
 
-        q = heads(linear(x, p[pre + "attention.q_lin.weight"], p[pre + "attention.q_lin.bias"], cfg)) * (d ** -0.5)
-        k = heads(linear(x, p[pre + "attention.k_lin.weight"], p[pre + "attention.k_lin.bias"], cfg))
-        v = heads(linear(x, p[pre + "attention.v_lin.weight"], p[pre + "attention.v_lin.bias"], cfg))
-        ctx = _softmax_attention(q, k, v, cfg, add_mask).permute(0, 2, 1, 3).reshape(B, L, D)
-        sa = linear(ctx, p[pre + "attention.out_lin.weight"], p[pre + "attention.out_lin.bias"], cfg)
+        q = heads(linear(x, p[pre + "attention.q_lin.weight"], p[pre + "attention.q_lin.bias"], cfg, True)) * (d ** -0.5)
+        k = heads(linear(x, p[pre + "attention.k_lin.weight"], p[pre + "attention.k_lin.bias"], cfg, True))
+        v = heads(linear(x, p[pre + "attention.v_lin.weight"], p[pre + "attention.v_lin.bias"], cfg, True))
+        ctx = _ste(_softmax_attention(q, k, v, cfg, add_mask).permute(0, 2, 1, 3).reshape(B, L, D), cfg)  # stored bf16
+        sa = linear(ctx, p[pre + "attention.out_lin.weight"], p[pre + "attention.out_lin.bias"], cfg, True)
         x = layer_norm(sa + x, p[pre + "sa_layer_norm.weight"], p[pre + "sa_layer_norm.bias"], e)
-        f = linear(gelu(linear(x, p[pre + "ffn.lin1.weight"], p[pre + "ffn.lin1.bias"], cfg), cfg),
-                   p[pre + "ffn.lin2.weight"], p[pre + "ffn.lin2.bias"], cfg)
+        f = linear(gelu(linear(x, p[pre + "ffn.lin1.weight"], p[pre + "ffn.lin1.bias"], cfg, True), cfg),
+                   p[pre + "ffn.lin2.weight"], p[pre + "ffn.lin2.bias"], cfg, True)
         x = layer_norm(f + x, p[pre + "output_layer_norm.weight"], p[pre + "output_layer_norm.bias"], e)
     return x
 
@@ -275,12 +304,12 @@ def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model."):
 def compute_text(text, p, cfg):
     """FrozenInTime.compute_text (oa_model.py:106-123): last_hidden_state[:, 0] -> ReLU -> Linear(768, 256)."""
     hid = distilbert(text["input_ids"], text.get("attention_mask"), p, cfg)[:, 0]
-    return linear(F.relu(hid.float()), p["txt_proj.1.weight"], p["txt_proj.1.bias"], cfg)
+    return linear(F.relu(hid.float()), p["txt_proj.1.weight"], p["txt_proj.1.bias"], cfg, True)
 
 
 def compute_video(video, p, cfg, objects=None):
     """FrozenInTime.compute_video (oa_model.py:129-133): CLS feature -> Linear(768, 256)."""
-    return linear(video_tower(video, p, cfg, objects), p["vid_proj.0.weight"], p["vid_proj.0.bias"], cfg)
+    return linear(video_tower(video, p, cfg, objects), p["vid_proj.0.weight"], p["vid_proj.0.bias"], cfg, True)
 
 
 def dual_encoder(data, p, cfg):

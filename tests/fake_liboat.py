@@ -30,17 +30,37 @@ class CastPlan:
     def __init__(self):
         self.items = []
 
-    def add(self, src, dst, rows=None, cols=None):
+    def add(self, src, dst, rows=None, cols=None, split=False):
         src2 = src.detach()
         src2 = src2.reshape(src2.shape[0], -1) if src2.dim() != 2 else src2
-        self.items.append((src2, dst, src2.shape[0] if rows is None else rows, src2.shape[1] if cols is None else cols))
+        self.items.append((src2, dst, src2.shape[0] if rows is None else rows, src2.shape[1] if cols is None else cols,
+                           split))
 
     def run(self):
-        for s, d, r, c in self.items:
+        for s, d, r, c, split in self.items:
             d[:r].zero_()
-            d[:r, :c] = s[:r, :c].to(d.dtype)
+            if split:                       # weight layout [hi | lo | hi], each segment dst.shape[1] // 3 wide
+                seg = d.shape[1] // 3
+                hi = s[:r, :c].to(BF)
+                lo = (s[:r, :c] - hi.float()).to(BF)
+                d[:r, :c], d[:r, seg:seg + c], d[:r, 2 * seg:2 * seg + c] = hi, lo, hi
+            else:
+                d[:r, :c] = s[:r, :c].to(d.dtype)
         self.items = []
         _count(1)
+
+
+def split3_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
+    """activation layout [hi | hi | lo]"""
+    rows = dst.shape[0] if rows is None else rows
+    cols = src.shape[-1] if cols is None else cols
+    lds = (src.stride(0) if src.dim() == 2 else cols) if lds is None else lds
+    v = _rows(src.detach(), rows, lds, cols).float()
+    if relu:
+        v = v.clamp_min(0)
+    hi = v.to(BF)
+    dst[:rows, :cols], dst[:rows, cols:2 * cols], dst[:rows, 2 * cols:3 * cols] = hi, hi, (v - hi.float()).to(BF)
+    _count(1)
 
 
 def cast_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
@@ -93,7 +113,8 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
     _count(1)
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f32=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f32=None, mean=None, rstd=None,
+                  y_split=None, split_period=1):
     D = gamma.numel()
     rows = x.shape[0] if rows is None else rows
     ldx = x.stride(0) if ldx is None else ldx
@@ -110,6 +131,11 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, y_bf16=None, y_f3
         mean[:rows].copy_(mu)
     if rstd is not None:
         rstd[:rows].copy_(rs)
+    if y_split is not None:                 # rows r with r % split_period == 0 -> y_split[r // split_period] = [hi | hi | lo]
+        ys = y[::split_period]
+        hi = ys.to(BF)
+        k = ys.shape[0]
+        y_split[:k, :D], y_split[:k, D:2 * D], y_split[:k, 2 * D:] = hi, hi, (ys - hi.float()).to(BF)
     _count(1)
 
 

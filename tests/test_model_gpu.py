@@ -3,11 +3,11 @@
   * against the pinned oracle in bf16-operand mode on the same inputs.
 
 Tolerances (BASELINE.json north_star: 1e-3 on bf16 logits/grads):
-  LOGIT_TOL = 2e-3 absolute on cosine logits in [-1, 1]. Rounding matmul operands to bf16 (which north_star itself
-    prescribes) moves the logits of a 12-block network by ~6e-4 max even with exact accumulation (oracle bf16 mode vs
-    oracle fp32, measured in test_cfg1: `noise_floor`); two different accumulation orders therefore differ by about
-    sqrt(2) times that. The measured CUDA-vs-oracle error is reported in gpurun_out/parity_*.json and DESIGN.md
-    (2e-4 .. 1.3e-3); it is below 1e-3 on the 224x224 cases and marginally above on the 33-token cfg1 case.
+  LOGIT_TOL = 1e-3 absolute on cosine logits in [-1, 1], against the REFERENCE's fp32 outputs and against the oracle.
+    Plain bf16 operands everywhere cannot guarantee that (oracle bf16 mode without split rows vs oracle fp32: 7.6e-4
+    on cfg1, 1.5e-3 on the small fixture, 1.3e-3 at the benchmark geometry), so the rows the logits depend on
+    directly - CLS rows, text tower, projections - take split-bf16 (three-term) products in the forward pass
+    (engine.py docstring; oracle cfg.split mirrors it): 3.9e-4 / 6.5e-4 / 1.4e-4 on the same cases.
   Gradients: the loss divides logits by T = 0.05, so a 6e-4 logit perturbation changes dL/dlogits by ~1.2 % before a
     single backward kernel has run. The gate is therefore relative to that measured floor: the CUDA path must be as
     close to the bf16 oracle as the bf16 oracle is to fp32 (factor 2), per tensor in the median and in the worst
@@ -33,7 +33,7 @@ def rel(a, b, floor=1e-6):
     return 0.0 if d <= floor else d / max(n, 1e-30)
 
 
-LOGIT_TOL = 2e-3
+LOGIT_TOL = 1e-3
 
 
 def cuda_dual(p_cpu, video, ids, mask, heads, objects=None, want_grads=True, temperature=0.05):
@@ -221,6 +221,36 @@ def test_config_shaped_frames_and_objects_vs_bf16_oracle(frames, tag):
     assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
     assert rept["grad_rel_err_max"] < 0.15
     assert not rep["missing"] and not rept["missing"]
+
+
+def test_cfg4_benchmark_geometry_full_depth_vs_oracles():
+    """The configuration bench.py times (BASELINE configs[3] per-GPU shard: 8 frames of 224x224, 36 object regions per
+    frame, 32-token text, ViT-B/16 space-time with all 12 blocks + DistilBERT-base, InfoNCE at T = 0.05) at batch 4:
+    logits within 1e-3 of the fp32 oracle (= what the reference computes) and of the bf16 oracle; every parameter
+    gradient compared per tensor with both oracles, gated on the measured operand-rounding floor (bf16 oracle vs fp32
+    oracle on the same inputs)."""
+    spec = dual_encoder_spec(frames=8, objects=True)
+    w = fill_seeded(spec, 0, 0.02)
+    g = torch.Generator().manual_seed(1234)
+    B, Fr, Oo, L = 4, 8, 36, 32
+    video = torch.randn(B, Fr, 3, 224, 224, generator=g)
+    objects = O.synth_objects(B, Fr, Oo, g)
+    text = O.synth_text(B, L, g)
+    te, ve, sims, loss, grads = cuda_dual(w, video, text["input_ids"], text["attention_mask"], heads=12, objects=objects)
+    torch.cuda.empty_cache()
+    (s16, l16, g16), floor = noise_floor(w, video, text["input_ids"], text["attention_mask"], O.OracleCfg(bf16=True),
+                                         O.OracleCfg(), objects=objects, tag="cfg4_")
+    _, _, s32, l32, g32 = oracle_dual(w, video, text["input_ids"], text["attention_mask"], O.OracleCfg(), objects)
+    rep16 = summarize("cfg4_vs_bf16_oracle", sims, s16, loss, l16, grads, g16)
+    rep32 = summarize("cfg4_vs_fp32_oracle", sims, s32, loss, l32, grads, g32)
+    assert not rep16["missing"]
+    assert rep16["logit_max_abs_err"] < LOGIT_TOL and rep32["logit_max_abs_err"] < LOGIT_TOL
+    assert abs(loss - l32) < 2e-3 * max(1.0, abs(l32))
+    # gradients: the CUDA path may be no further from the fp32 truth than the bf16 oracle is (1x the floor; 10 % slack
+    # on the median over ~330 tensors, the single worst tensor is a noisier statistic)
+    assert rep32["grad_rel_err_median"] < 1.1 * floor["grad_rel_err_median"] + 1e-3
+    assert rep32["grad_rel_err_max"] < 1.5 * floor["grad_rel_err_max"] + 1e-3
+    assert rep16["grad_rel_err_median"] < 1.1 * floor["grad_rel_err_median"] + 1e-3
 
 
 def test_frozen_in_time_module_surface():

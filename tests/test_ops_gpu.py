@@ -57,6 +57,65 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     assert rel(dxsum, dx.sum(0)) < 1e-4
 
 
+def _split_ref(v):
+    hi = v.to(BF)
+    return hi, (v - hi.float()).to(BF)
+
+
+def test_split_bf16_operands_bit_exact_and_three_term_gemm():
+    """Split-bf16 operands (include/oat.h, oat_split3_bf16 / oat_cast_multi kind 2 / oat_layernorm_fwd y_split): the
+    packing is pure rounding bookkeeping -> bit-exact against torch; the K-concatenated GEMM [hi|hi|lo] x [hi|lo|hi]
+    must agree with the fp64 product far below one bf16 ulp (2^-9), which a single bf16 GEMM cannot."""
+    from oa_transformer_b200 import ops
+    g = gen(11)
+    rows, K, N, T = 24, 768, 256, 5
+    x = torch.randn(rows * T, K, generator=g).cuda()
+    w = (0.05 * torch.randn(N, K, generator=g)).cuda()
+    # activation layout from the strided rows 0, T, 2T, ... (the CLS rows), with ReLU
+    a3 = torch.empty(rows, 3 * K, device="cuda", dtype=BF)
+    ops.split3_bf16(x, a3, rows=rows, cols=K, lds=T * K, relu=True)
+    hi, lo = _split_ref(x[::T].clamp_min(0))
+    assert torch.equal(a3[:, :K], hi) and torch.equal(a3[:, K:2 * K], hi) and torch.equal(a3[:, 2 * K:], lo)
+    # weight layout through the one-launch cast plan
+    w3 = torch.zeros(N, 3 * K, device="cuda", dtype=BF)
+    plan = ops.CastPlan()
+    plan.add(w, w3, split=True)
+    plan.run()
+    whi, wlo = _split_ref(w)
+    assert torch.equal(w3[:, :K], whi) and torch.equal(w3[:, K:2 * K], wlo) and torch.equal(w3[:, 2 * K:], whi)
+    # LayerNorm forward emitting the split copy of every T-th row
+    gamma = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    y32 = torch.empty(rows * T, K, device="cuda")
+    y16 = torch.empty(rows * T, K, device="cuda", dtype=BF)
+    c3 = torch.empty(rows, 3 * K, device="cuda", dtype=BF)
+    ops.layernorm_fwd(x, gamma, beta, 1e-6, y_bf16=y16, y_f32=y32, y_split=c3, split_period=T)
+    hi, lo = _split_ref(y32[::T])
+    assert torch.equal(c3[:, :K], hi) and torch.equal(c3[:, K:2 * K], hi) and torch.equal(c3[:, 2 * K:], lo)
+    assert torch.equal(y16[::T], hi)
+    # three-term product vs fp64, and the correction form  hi.hi (plain GEMM) + [hi|lo] x [lo|hi] (accumulated)
+    xr = x[::T].clamp_min(0)
+    exact = (xr.double() @ w.double().t()).float()
+    out3 = torch.empty(rows, N, device="cuda")
+    ops.gemm(a3, w3, out_f32=out3)
+    out1 = torch.empty(rows, N, device="cuda")
+    ops.gemm(a3[:, :K], w3[:, :K], out_f32=out1)
+    assert rel(out3, exact) < 3e-5 and rel(out1, exact) > 1e-3
+    ops.gemm(a3[:, K:], w3[:, K:], out_f32=out1, accumulate=True)
+    assert rel(out1, exact) < 3e-5
+    # strided output rows (the CLS rows of a token buffer) for both the overwrite and the accumulate form
+    big = torch.zeros(rows * T, N, device="cuda")
+    cls_rows = big.view(rows, T * N)[:, :N]
+    ops.gemm(a3, w3, out_f32=cls_rows)
+    assert rel(big[::T], exact) < 3e-5 and float(big[1::T].abs().max()) == 0.0
+    big16 = torch.zeros(rows * T, N, device="cuda", dtype=BF)
+    ops.gemm(a3, w3, out_bf16=big16.view(rows, T * N)[:, :N])
+    assert rel(big16[::T].float(), exact) < 4e-3 and float(big16[1::T].float().abs().max()) == 0.0
+    ops.gemm(a3[:, K:], w3[:, K:], out_f32=cls_rows, accumulate=True)
+    torch.cuda.synchronize()
+    assert float(big[1::T].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("variant", ["adds", "add1", "plain", "text"])
 @pytest.mark.parametrize("rows,D", [(5000, 768), (8 * 148 + 3, 768), (100, 256)])
 def test_layernorm_bwd_staged_variants(rows, D, variant):
