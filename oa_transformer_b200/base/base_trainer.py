@@ -64,6 +64,11 @@ class Multi_BaseTrainer_dist:
                 for key, value in log.items():
                     self.logger.info('    {:15s}: {}'.format(str(key), value))
             best = False
+            if self.mnt_mode != 'off' and self.args.rank == 0 and self.mnt_metric not in log:
+                # base_trainer.py:117-121: a monitor that names no logged scalar switches monitoring off, loudly
+                self.logger.warning("Warning: Metric '{}' is not found. Model performance monitoring is disabled."
+                                    .format(self.mnt_metric))
+                self.mnt_mode = 'off'
             if self.mnt_mode != 'off' and self.mnt_metric in log:
                 improved = (self.mnt_mode == 'min' and log[self.mnt_metric] <= self.mnt_best) or \
                            (self.mnt_mode == 'max' and log[self.mnt_metric] >= self.mnt_best)
@@ -92,7 +97,9 @@ class Multi_BaseTrainer_dist:
             torch.save(state, str(self.checkpoint_dir / 'model_best.pth'))
 
     def _resume_checkpoint(self, resume_path):
-        checkpoint = torch.load(str(resume_path), map_location="cpu")
+        # weights_only=False: reference-produced checkpoints pickle the config dictionary next to the tensors
+        # (base_trainer.py:163-175); checkpoints are trusted local files here, exactly as in the reference
+        checkpoint = torch.load(str(resume_path), map_location="cpu", weights_only=False)
         self.start_epoch = checkpoint['epoch'] + 1
         self.mnt_best = checkpoint['monitor_best']
         state_dict = state_dict_data_parallel_fix(checkpoint['state_dict'], self.model.state_dict())

@@ -35,21 +35,26 @@ SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forwa
 
 
 class _Buffers:
-    """Shape-keyed cache of device buffers so that a training loop re-uses its activation storage every step."""
+    """Name-keyed cache of device buffers so that a training loop re-uses its activation storage every step. A buffer
+    is re-allocated only when a request needs more elements than it holds and is otherwise viewed to the requested
+    shape, so varying batch sizes / padded text lengths (tokenizer padding=True, trainer_dist.py:152) do not pile up
+    one activation set per distinct shape."""
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
 
     def get(self, name, shape, dtype, zero=False):
-        key = (name, tuple(shape), dtype)
-        t = self.bufs.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
-            self.bufs[key] = t
-            if zero:
-                t.zero_()
-        elif zero:
+        key = (name, dtype)
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        flat = self.bufs.get(key)
+        if flat is None or flat.numel() < numel:
+            flat = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self.bufs[key] = flat
+        t = flat[:numel].view(tuple(shape))
+        if zero:
             t.zero_()
         return t
 
@@ -83,6 +88,13 @@ def _hi(w3):
 def _lo(w3):
     k = w3.shape[1] // 3
     return w3[:, k:2 * k]
+
+
+def _spread(N, K, sms=148):
+    """split-K factor that spreads a skinny (few-row) accumulate GEMM over the whole chip: its cost is streaming the
+    [N, K] weight, which a handful of output tiles cannot do fast."""
+    tiles = max(1, (N + 255) // 256)
+    return max(1, min((K + 63) // 64, sms // tiles))
 
 
 def _lohi(w3):
@@ -126,9 +138,14 @@ class VideoEngine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
-                save=True):
+                save=True, tokens=None, region_layer=6):
         """p: dict name -> fp32 parameter tensor. video fp32 (B,F,3,H,W); objects fp32 (B,F,O,2054) or None.
-        Returns projected CLS embeddings fp32 (B, P)."""
+        Returns projected CLS embeddings fp32 (B, P).
+        tokens="final": also returns the final LayerNorm of EVERY token row, fp32 (B, T, D) - forward_features'
+          second result is its [:, 1:] (video_transformer.py:346-351).
+        tokens="region": also returns region_norm(x) after `region_layer` blocks, fp32 (B, T, D)
+          (oa_video_transformer_region.py:364-376: K = 6, region_feature = region_norm(x)[:, 1:])."""
+        assert tokens in (None, "final", "region")
         bufs = self.bufs
         B, Fr, C, Hh, Ww = video.shape
         ps = self.patch
@@ -228,7 +245,8 @@ class VideoEngine:
                 wproj = W[(i, tag, "proj")]
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
                 if split:       # the attention output is bf16 already (lo = 0): add a . w_lo on the CLS rows
-                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True)
+                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True,
+                             split_k=_spread(D, D))
                 return wqkv, wproj, qkv, a, lse
 
             # time attention on norm3(x); residual from x                    (video_transformer.py:164-165)
@@ -257,9 +275,17 @@ class VideoEngine:
                 ops.split3_bf16(g32, g3)
             ops.gemm(g, L["w2"], bias=p[b + "mlp.fc2.bias"], residual=sr, out_f32=xs[i + 1])
             if split:           # + g_hi . w_lo + g_lo . w_hi on the CLS rows
-                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True)
+                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True,
+                         split_k=_spread(D, 8 * D))
             L["tr"], L["sr"], L["u"], L["g"] = tr, sr, u, g
             layers.append(L)
+            if tokens == "region" and i + 1 == region_layer:
+                tok32, tmean, trstd = self._token_norm(p, prefix + "region_norm", xs[i + 1], M, D)
+
+        if tokens == "region":
+            assert 1 <= region_layer <= depth, "region_layer %d outside the %d blocks" % (region_layer, depth)
+        if tokens == "final":
+            tok32, tmean, trstd = self._token_norm(p, prefix + "norm", xs[depth], M, D)
 
         # final LayerNorm: only the CLS row is consumed (:346-351), then vid_proj (oa_model.py:131)
         cls32 = bufs.get("cls32", (B, D), F32)
@@ -282,13 +308,25 @@ class VideoEngine:
         if save:
             self.saved = dict(B=B, Fr=Fr, N=N, O=O, n=n, T=T, M=M, D=D, depth=depth, xs=xs, layers=layers, cols=cols,
                               obj16=obj16, cls16=cls16, mf=mf, rf=rf, wv=wv, proj=proj, prefix=prefix,
-                              has_type=type_embed is not None)
+                              has_type=type_embed is not None, tokens=tokens, region_layer=region_layer,
+                              tmean=tmean if tokens else None, trstd=trstd if tokens else None)
+        if tokens is not None:
+            return out, tok32.view(B, T, D)
         return out
 
+    def _token_norm(self, p, wname, x, M, D):
+        """LayerNorm of every token row (fp32 result): the patch / region features the variant heads consume."""
+        tok32 = torch.empty((M, D), dtype=F32, device=self.device)      # returned to autograd: not a recycled buffer
+        mean = self.bufs.get("tok.mean", (M,), F32)
+        rstd = self.bufs.get("tok.rstd", (M,), F32)
+        ops.layernorm_fwd(x, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_f32=tok32, mean=mean, rstd=rstd)
+        return tok32, mean, rstd
+
     # ------------------------------------------------------------------ backward
-    def backward(self, p, grads, dout):
-        """dout: fp32 (B, P) gradient of the projected embeddings. Fills `grads` (GradBook-like: name -> fp32 view,
-        pre-zeroed) with every parameter gradient."""
+    def backward(self, p, grads, dout, dtokens=None):
+        """dout: fp32 (B, P) gradient of the projected embeddings; dtokens: fp32 (B, T, D) gradient of the token
+        features returned with tokens="final" / "region" (None: unused). Fills `grads` (GradBook-like: name -> fp32
+        view, pre-zeroed) with every parameter gradient."""
         S = self.saved
         assert S is not None, "backward without a saved forward"
         bufs = self.bufs
@@ -339,10 +377,22 @@ class VideoEngine:
             ops.colsum_bf16(d16, grads[bname])
         else:
             ops.cast_bf16(dout.contiguous(), dcls16)
+        # LayerNorm backward is linear in dy, so the gradient arriving through the token features is a second pass over
+        # ALL rows (final norm, or region_norm when it sits on the last block) added onto the CLS-row pass; only the
+        # last pass accumulates the column sums of the finished dx (= fc2 bias gradient of the last block).
+        tok_mode = S["tokens"] if dtokens is not None else None
+        region_at = S["region_layer"] if tok_mode == "region" else -1
+        tok_here = tok_mode == "final" or region_at == depth
+        fc2b_last = grads["%sblocks.%d.mlp.fc2.bias" % (prefix, depth - 1)] if depth > 0 else None
         ops.layernorm_bwd(xs[depth], S["mf"], S["rf"], p[prefix + "norm.weight"], dy_bf16=dcls16, rows=B, ldx=T * D,
                           dx=dy, dx_bf16=dy16, lddx=T * D, lddxb=T * D, dgamma=grads[prefix + "norm.weight"],
-                          dbeta=grads[prefix + "norm.bias"],
-                          dxsum=grads["%sblocks.%d.mlp.fc2.bias" % (prefix, depth - 1)] if depth > 0 else None)
+                          dbeta=grads[prefix + "norm.bias"], dxsum=None if tok_here else fc2b_last)
+        if dtokens is not None:
+            dtokens = dtokens.contiguous().view(M, D)
+        if tok_here:
+            wn = prefix + ("norm" if tok_mode == "final" else "region_norm")
+            ops.layernorm_bwd(xs[depth], S["tmean"], S["trstd"], p[wn + ".weight"], dy_f32=dtokens, add1=dy, dx=dy,
+                              dx_bf16=dy16, dgamma=grads[wn + ".weight"], dbeta=grads[wn + ".bias"], dxsum=fc2b_last)
 
         nset = 2 if use_side else 1
         du = [bufs.get("du.%d" % k, (M, 4 * D), BF) for k in range(nset)]
@@ -387,6 +437,10 @@ class VideoEngine:
             ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc)
             ops.gemm(dqkv_t[k], L["wqkv_t"], b_major=1, out_bf16=dh)
             wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv")
+            if i == region_at:      # x_i also fed region_norm: dsr += region_norm'(dtokens), in place, before the sum below
+                wn = prefix + "region_norm"
+                ops.layernorm_bwd(xs[i], S["tmean"], S["trstd"], p[wn + ".weight"], dy_f32=dtokens, add1=dsr, dx=dsr,
+                                  dgamma=grads[wn + ".weight"], dbeta=grads[wn + ".bias"])
             # ---- dx = dsr (space skip) + dtr (time skip) + norm3'(dh)
             ops.layernorm_bwd(xs[i], L["m3"], L["r3"], p[b + "norm3.weight"], dy_bf16=dh, add1=dsr, add2=dtr, dx=dyb,
                               dx_bf16=dy16b, dgamma=grads[b + "norm3.weight"], dbeta=grads[b + "norm3.bias"],

@@ -25,11 +25,12 @@ class _TowerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, *params):
         ctx.runner = runner
-        return runner.fwd()
+        ctx.set_materialize_grads(False)
+        return runner.fwd()          # embeddings, or (embeddings, token features) when the engine was asked for tokens
 
     @staticmethod
-    def backward(ctx, dout):
-        grads = ctx.runner.bwd(dout)
+    def backward(ctx, dout, dtokens=None):
+        grads = ctx.runner.bwd(dout, dtokens)
         return (None,) + tuple(grads)
 
 
@@ -42,17 +43,24 @@ class TowerRunner:
         self._book = None
 
     def fwd(self):
-        return self.engine.forward(self.pdict, **self.kw)
+        out = self.engine.forward(self.pdict, **self.kw)
+        self.out_shape = tuple((out[0] if isinstance(out, tuple) else out).shape)
+        return out
 
-    def bwd(self, dout):
+    def bwd(self, dout, dtokens=None):
         eng = self.engine
         key = tuple((n, tuple(p.shape)) for n, p in self.named)
         book = getattr(eng, "_gradbook", None)
         if book is None or getattr(eng, "_gradbook_key", None) != key:
-            book = GradBook(self.named, dout.device)
+            book = GradBook(self.named, (dout if dout is not None else dtokens).device)
             eng._gradbook, eng._gradbook_key = book, key
         book.zero()
-        eng.backward(self.pdict, book, dout.contiguous().float())
+        if dout is None:                # only the token features were used downstream
+            dout = torch.zeros(self.out_shape, dtype=torch.float32, device=dtokens.device)
+        if dtokens is not None:
+            eng.backward(self.pdict, book, dout.contiguous().float(), dtokens.contiguous().float())
+        else:
+            eng.backward(self.pdict, book, dout.contiguous().float())
         hook = getattr(eng, "grad_ready_hook", None)
         if hook is not None:        # e.g. start this tower's gradient all-reduce while the other tower still runs backward
             hook(book)

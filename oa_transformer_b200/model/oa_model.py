@@ -25,6 +25,9 @@ from .model import sim_matrix as _unused  # noqa: F401  (kept importable from he
 from .video_transformer import SpaceTimeTransformer
 
 
+MAX_TEXT_TOKENS = 256      # oat_attn_fwd mode 2 keeps one caption's keys in shared memory
+
+
 class FrozenInTime(BaseModel):
     def __init__(self,
                  video_params,
@@ -62,7 +65,8 @@ class FrozenInTime(BaseModel):
             modality_token = video_params.get('modality_token', False)
             if arch_config == 'base_patch16_224':
                 vit_path = video_params.get('vit_checkpoint', "pretrained/jx_vit_base_p16_224-80ecf9dd.pth")
-                vit_model = torch.load(vit_path, map_location="cpu") if vit_path and os.path.exists(vit_path) else None
+                vit_model = torch.load(vit_path, map_location="cpu", weights_only=False) \
+                    if vit_path and os.path.exists(vit_path) else None
                 if vit_model is None and not video_params.get('allow_missing_vit', False):
                     raise FileNotFoundError(vit_path)
                 model = SpaceTimeTransformer(num_frames=num_frames, time_init=time_init,
@@ -96,7 +100,8 @@ class FrozenInTime(BaseModel):
             self.vid_proj = vid_proj
 
         if load_checkpoint not in ["", None]:
-            checkpoint = torch.load(load_checkpoint, map_location="cpu")
+            # weights_only=False: reference checkpoints pickle their config next to the tensors (base_trainer.py:163-175)
+            checkpoint = torch.load(load_checkpoint, map_location="cpu", weights_only=False)
             state_dict = checkpoint['state_dict']
             new_state_dict = state_dict_data_parallel_fix(state_dict, self.state_dict())
             new_state_dict = self._inflate_positional_embeds(new_state_dict)
@@ -127,6 +132,9 @@ class FrozenInTime(BaseModel):
         if not self.text_params['model'].split('/')[-1].startswith('distilbert'):
             raise NotImplementedError
         ids = text_data['input_ids']
+        if ids.shape[1] > MAX_TEXT_TOKENS:
+            raise ValueError("the CUDA text-attention kernel handles up to %d tokens per caption, got %d: tokenize with "
+                             "truncation=True, max_length=%d" % (MAX_TEXT_TOKENS, ids.shape[1], MAX_TEXT_TOKENS))
         if self._text_engine is None or self._text_engine.device != ids.device:
             self._text_engine = TextEngine(ids.device, heads=self.text_model.config.n_heads)
         return run_tower(self._text_engine, self._text_named(), input_ids=ids,

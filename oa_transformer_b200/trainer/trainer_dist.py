@@ -59,7 +59,9 @@ class Multi_Trainer_dist(Multi_BaseTrainer_dist):
 
     def _to_device(self, data):
         if self.tokenizer is not None and not isinstance(data['text'], dict):
-            data['text'] = self.tokenizer(data['text'], return_tensors='pt', padding=True, truncation=True)
+            # trainer_dist.py:152 (padding=True, truncation=True); the CUDA text attention takes at most 256 tokens
+            data['text'] = self.tokenizer(data['text'], return_tensors='pt', padding=True, truncation=True,
+                                          max_length=min(getattr(self.tokenizer, "model_max_length", 256), 256))
         data['text'] = {k: v.to(self.device) for k, v in data['text'].items()}
         data['video'] = data['video'].to(self.device)
         if 'object' in data:
@@ -137,17 +139,17 @@ class Multi_Trainer_dist(Multi_BaseTrainer_dist):
                     text_arr[dl_idx].append(t_all.cpu())
                     vid_arr[dl_idx].append(v_all.cpu())
                     total_val_loss[dl_idx] += self.loss(sim_matrix(t_all, v_all)).item()
-        res = {}
+        # nested_metrics[dl_idx][metric_name] = {R1, R5, ...} exactly as trainer_dist.py:251-279, so that
+        # Multi_BaseTrainer_dist.train flattens it to the scalar keys val_{dl}_{metric}_{R1,...} a monitor can name
+        nested_metrics = {i: {} for i in range(n_dl)}
         for dl_idx in range(n_dl):
-            nested = {}
             text_embeds = torch.cat(text_arr[dl_idx]).to(self.device)
             vid_embeds = torch.cat(vid_arr[dl_idx]).to(self.device)
             # the reference moves the matrix to the host first (trainer_dist.py:255-264); the metric functions here count
             # the ranks on the device for a CUDA tensor (same numbers, model/metric.py)
             sims = sim_matrix(text_embeds, vid_embeds).detach()
             for metric in self.metrics:
-                nested[metric.__name__] = {k: float(v) for k, v in metric(sims).items()}
-            res[dl_idx] = nested
+                nested_metrics[dl_idx][metric.__name__] = {k: float(v) for k, v in metric(sims).items()}
         log = {f'val_loss_{i}': total_val_loss[i] / max(1, len(self.valid_data_loader[i])) for i in range(n_dl)}
-        log['nested_val_metrics'] = {i: {"synthetic": res[i]} for i in range(n_dl)}
+        log['nested_val_metrics'] = nested_metrics
         return log

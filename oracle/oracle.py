@@ -249,15 +249,23 @@ def space_time_block(x, p, pre, Fr, n, cfg):
     return s_res + mlp(layer_norm(s_res, p[pre + "norm2.weight"], p[pre + "norm2.bias"], e), p, pre + "mlp.", cfg)
 
 
-def video_tower(video, p, cfg, objects=None, prefix="video_model.", depth=None, return_tokens=False):
-    """SpaceTimeTransformer.forward_features (video_transformer.py:303-351): tokens -> blocks -> final LN -> CLS."""
+def video_tower(video, p, cfg, objects=None, prefix="video_model.", depth=None, return_tokens=False, region_layer=None):
+    """SpaceTimeTransformer.forward_features (video_transformer.py:303-351): tokens -> blocks -> final LN -> CLS;
+    return_tokens: (x[:, 0], x[:, 1:]) as :351 returns. region_layer=K: the region variant
+    (oa_video_transformer_region.py:364-376) returns (norm(x)[:, 0], region_norm(x after K blocks)[:, 1:]), K = 6."""
     x, n = video_tokens(video, p, cfg, objects, prefix)
     Fr = video.shape[1]
     if depth is None:
         depth = 1 + max(int(k[len(prefix) + 7:].split(".")[0]) for k in p if k.startswith(prefix + "blocks."))
+    region = None
     for i in range(depth):
         x = space_time_block(x, p, "%sblocks.%d." % (prefix, i), Fr, n, cfg)
+        if region_layer is not None and i + 1 == region_layer:
+            region = layer_norm(x, p[prefix + "region_norm.weight"], p[prefix + "region_norm.bias"],
+                                cfg.ln_eps_video)[:, 1:]
     x = layer_norm(x, p[prefix + "norm.weight"], p[prefix + "norm.bias"], cfg.ln_eps_video)
+    if region_layer is not None:
+        return x[:, 0], region
     return (x[:, 0], x[:, 1:]) if return_tokens else x[:, 0]
 
 

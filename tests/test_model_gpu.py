@@ -8,11 +8,15 @@ Tolerances (BASELINE.json north_star: 1e-3 on bf16 logits/grads):
     on cfg1, 1.5e-3 on the small fixture, 1.3e-3 at the benchmark geometry), so the rows the logits depend on
     directly - CLS rows, text tower, projections - take split-bf16 (three-term) products in the forward pass
     (engine.py docstring; oracle cfg.split mirrors it): 3.9e-4 / 6.5e-4 / 1.4e-4 on the same cases.
-  Gradients: the loss divides logits by T = 0.05, so a 6e-4 logit perturbation changes dL/dlogits by ~1.2 % before a
-    single backward kernel has run. The gate is therefore relative to that measured floor: the CUDA path must be as
-    close to the bf16 oracle as the bf16 oracle is to fp32 (factor 2), per tensor in the median and in the worst
-    case; and with T = 1 (no amplification) per-tensor gradient error must be below 1e-2 (median below 4e-3).
-    Mathematically-zero gradients (softmax is invariant to the key bias: *.k_lin.bias) are excluded.
+  Gradients (gate_grads): bf16 operands put a floor under per-tensor gradient error that no kernel can beat - the
+    distance between the oracle in bf16-operand mode and the fp32 oracle on the same inputs (`noise_floor`, measured
+    in every test; 1-4 % per tensor for InfoNCE at T = 0.05 on random-init towers, whose embeddings are nearly
+    identical across samples so that dL/dembedding is a difference of almost equal terms; 0.5-0.7 % under a linear
+    loss). The CUDA path must be no further from the fp32 truth (the reference's outputs, or the fp32 oracle) than
+    the bf16 oracle is: 1x the floor, with 10 % slack on the median over tensors and 1.5x on the single worst
+    tensor. Against the bf16 oracle itself the expected distance is sqrt(2) x the floor (two independent roundings
+    of the same computation: the kernels round unnormalised softmax weights, the oracle normalised ones), gated at
+    1.5x / 2x. Mathematically-zero gradients (softmax is invariant to the key bias: *.k_lin.bias) are excluded.
 """
 import json
 import os
@@ -86,6 +90,16 @@ def summarize(tag, sims, sims_ref, loss, loss_ref, grads, grads_ref):
     return rep
 
 
+def gate_grads(floor, vs_truth=None, vs_bf16_oracle=None):
+    """See the module docstring: 1x the measured floor against the fp32 truth, sqrt(2)x against the bf16 oracle."""
+    if vs_truth is not None:
+        assert vs_truth["grad_rel_err_median"] < 1.1 * floor["grad_rel_err_median"] + 1e-3, (vs_truth, floor)
+        assert vs_truth["grad_rel_err_max"] < 1.5 * floor["grad_rel_err_max"] + 1e-2, (vs_truth, floor)
+    if vs_bf16_oracle is not None:
+        assert vs_bf16_oracle["grad_rel_err_median"] < 1.5 * floor["grad_rel_err_median"] + 1e-3, (vs_bf16_oracle, floor)
+        assert vs_bf16_oracle["grad_rel_err_max"] < 2.0 * floor["grad_rel_err_max"] + 1e-2, (vs_bf16_oracle, floor)
+
+
 def noise_floor(w, video, ids, mask, cfg16, cfg32, objects=None, temperature=0.05, tag=""):
     """bf16-operand oracle vs fp32 oracle on the same inputs: the error that operand rounding alone introduces."""
     _, _, s16, l16, g16 = oracle_dual(w, video, ids, mask, cfg16, objects, temperature)
@@ -100,17 +114,15 @@ def test_small_dual_encoder_vs_reference_golden_and_bf16_oracle():
     te, ve, sims, loss, grads = cuda_dual(w, g["video"], g["input_ids"], g["attention_mask"], heads=2)
     (osims, oloss, ograds), floor = noise_floor(w, g["video"], g["input_ids"], g["attention_mask"],
                                                 O.OracleCfg(heads=2, text_layers=2, bf16=True),
-                                                O.OracleCfg(heads=2, text_layers=2))
+                                                O.OracleCfg(heads=2, text_layers=2), tag="small_")
     # (1) vs the reference's fp32 outputs
     rep = summarize("small_vs_reference", sims, g["sims"], loss, float(g["loss"]), grads, g["grads"])
     assert rep["logit_max_abs_err"] < LOGIT_TOL and not rep["missing"]
     assert abs(loss - float(g["loss"])) < 1e-2
-    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
     # (2) vs the pinned oracle in bf16-operand mode
-    rep = summarize("small_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
-    assert rep["logit_max_abs_err"] < LOGIT_TOL
-    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
-    assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
+    rep16 = summarize("small_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep16["logit_max_abs_err"] < LOGIT_TOL
+    gate_grads(floor, vs_truth=rep, vs_bf16_oracle=rep16)
 
 
 def test_cfg1_full_size_vs_reference_golden_and_bf16_oracle():
@@ -122,12 +134,16 @@ def test_cfg1_full_size_vs_reference_golden_and_bf16_oracle():
     assert rep["logit_max_abs_err"] < LOGIT_TOL
     assert abs(loss - float(g["loss"])) < 1e-2
     (osims, oloss, ograds), floor = noise_floor(w, g["video"], g["input_ids"], g["attention_mask"],
-                                                O.OracleCfg(bf16=True), O.OracleCfg())
-    rep = summarize("cfg1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
-    assert rep["logit_max_abs_err"] < LOGIT_TOL
+                                                O.OracleCfg(bf16=True), O.OracleCfg(), tag="cfg1_")
+    rep16 = summarize("cfg1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep16["logit_max_abs_err"] < LOGIT_TOL
     assert abs(loss - oloss) < 2e-3 * max(1.0, abs(oloss))
-    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
-    assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
+    # the fixture keeps the reference's gradients for a subset of tensors only: the floor is taken over the same subset
+    sub = {k: v for k, v in ograds.items() if k in g["grads_subset"]}
+    _, _, s32, l32, g32 = oracle_dual(w, g["video"], g["input_ids"], g["attention_mask"], O.OracleCfg())
+    floor_sub = summarize("noise_floor_cfg1_subset", osims, s32, oloss, l32, sub, g32)
+    gate_grads(floor_sub, vs_truth=rep)
+    gate_grads(floor, vs_bf16_oracle=rep16)
 
 
 def test_cfg1_gradients_without_temperature_amplification():
@@ -138,11 +154,13 @@ def test_cfg1_gradients_without_temperature_amplification():
     w = fill_seeded(g["shapes"], g["weight_seed"], g["weight_scale"])
     te, ve, sims, loss, grads = cuda_dual(w, g["video"], g["input_ids"], g["attention_mask"], heads=12, temperature=1.0)
     (osims, oloss, ograds), floor = noise_floor(w, g["video"], g["input_ids"], g["attention_mask"],
-                                                O.OracleCfg(bf16=True), O.OracleCfg(), temperature=1.0)
-    rep = summarize("cfg1_T1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+                                                O.OracleCfg(bf16=True), O.OracleCfg(), temperature=1.0, tag="cfg1_")
+    _, _, s32, l32, g32 = oracle_dual(w, g["video"], g["input_ids"], g["attention_mask"], O.OracleCfg(),
+                                      temperature=1.0)
+    rep32 = summarize("cfg1_T1_vs_fp32_oracle", sims, s32, loss, l32, grads, g32)
+    rep16 = summarize("cfg1_T1_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
     assert abs(loss - oloss) < 1e-3 * max(1.0, abs(oloss))
-    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
-    assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
+    gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
 
 
 def test_object_tokens_224_vs_bf16_oracle():
@@ -156,11 +174,13 @@ def test_object_tokens_224_vs_bf16_oracle():
     text = O.synth_text(B, L, g, ragged=True)
     te, ve, sims, loss, grads = cuda_dual(w, video, text["input_ids"], text["attention_mask"], heads=12,
                                           objects=objects)
-    cfg = O.OracleCfg(bf16=True)
-    _, _, osims, oloss, ograds = oracle_dual(w, video, text["input_ids"], text["attention_mask"], cfg, objects=objects)
-    rep = summarize("objects_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
-    assert rep["logit_max_abs_err"] < 1e-3
-    assert rep["grad_rel_err_median"] < 8e-2 and rep["grad_rel_err_max"] < 0.4
+    (osims, oloss, ograds), floor = noise_floor(w, video, text["input_ids"], text["attention_mask"],
+                                                O.OracleCfg(bf16=True), O.OracleCfg(), objects=objects, tag="objects_")
+    _, _, s32, l32, g32 = oracle_dual(w, video, text["input_ids"], text["attention_mask"], O.OracleCfg(), objects)
+    rep32 = summarize("objects_vs_fp32_oracle", sims, s32, loss, l32, grads, g32)
+    rep16 = summarize("objects_vs_bf16_oracle", sims, osims, loss, oloss, grads, ograds)
+    assert rep16["logit_max_abs_err"] < LOGIT_TOL and rep32["logit_max_abs_err"] < LOGIT_TOL
+    gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
     assert "video_model.object_embed.weight" in grads
 
 
@@ -214,12 +234,14 @@ def test_config_shaped_frames_and_objects_vs_bf16_oracle(frames, tag):
     vid = ("video_model.", "vid_proj.")
     txt = ("text_model.", "txt_proj.")
     floor = summarize("noise_floor_%s_linear_video" % tag, s16, s32, 0.0, 0.0, part(g16, vid), part(g32, vid))
+    floort = summarize("noise_floor_%s_linear_text" % tag, s16, s32, 0.0, 0.0, part(g16, txt), part(g32, txt))
+    rep32 = summarize("%s_depth2_linear_video_vs_fp32_oracle" % tag, sims, s32, 0.0, 0.0, part(grads, vid), part(g32, vid))
     rep = summarize("%s_depth2_linear_video_vs_bf16_oracle" % tag, sims, s16, 0.0, 0.0, part(grads, vid), part(g16, vid))
+    rept32 = summarize("%s_depth2_linear_text_vs_fp32_oracle" % tag, sims, s32, 0.0, 0.0, part(grads, txt), part(g32, txt))
     rept = summarize("%s_depth2_linear_text_vs_bf16_oracle" % tag, sims, s16, 0.0, 0.0, part(grads, txt), part(g16, txt))
-    assert rep["logit_max_abs_err"] < 1e-3
-    assert rep["grad_rel_err_median"] < 2 * floor["grad_rel_err_median"] + 1e-3
-    assert rep["grad_rel_err_max"] < 2 * floor["grad_rel_err_max"] + 1e-2
-    assert rept["grad_rel_err_max"] < 0.15
+    assert rep["logit_max_abs_err"] < LOGIT_TOL and rep32["logit_max_abs_err"] < LOGIT_TOL
+    gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep)
+    gate_grads(floort, vs_truth=rept32, vs_bf16_oracle=rept)
     assert not rep["missing"] and not rept["missing"]
 
 
@@ -246,11 +268,7 @@ def test_cfg4_benchmark_geometry_full_depth_vs_oracles():
     assert not rep16["missing"]
     assert rep16["logit_max_abs_err"] < LOGIT_TOL and rep32["logit_max_abs_err"] < LOGIT_TOL
     assert abs(loss - l32) < 2e-3 * max(1.0, abs(l32))
-    # gradients: the CUDA path may be no further from the fp32 truth than the bf16 oracle is (1x the floor; 10 % slack
-    # on the median over ~330 tensors, the single worst tensor is a noisier statistic)
-    assert rep32["grad_rel_err_median"] < 1.1 * floor["grad_rel_err_median"] + 1e-3
-    assert rep32["grad_rel_err_max"] < 1.5 * floor["grad_rel_err_max"] + 1e-3
-    assert rep16["grad_rel_err_median"] < 1.1 * floor["grad_rel_err_median"] + 1e-3
+    gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
 
 
 def test_frozen_in_time_module_surface():
