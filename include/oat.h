@@ -180,6 +180,30 @@ int oat_object_patch_attn(const float* q, const float* k, const float* v, const 
                           oat_stream_t stream);
 int oat_patch_masks_from_bbox(const double* boxes, int32_t stride, float* masks, int32_t n, int32_t grid,
                               oat_stream_t stream);
+/* Backward of oat_object_patch_attn. weights = what the forward returned (the masks for mode 0); dweights (B,O,L)
+ * and/or dout (B,O,Cv) are the incoming gradients (either may be NULL); dq (B,O,C), dk (B,L,C), dv (B,L,Cv) are
+ * written (any may be NULL); ds_scratch: fp32 (B,O,L), needed for modes 1/2. Mode 0 propagates to v only (the masks
+ * are data). Replaces autograd through oa_model_global_local.py:178 / oa_model_region_mem.py:147-151. */
+int oat_object_patch_attn_bwd(const float* q, const float* k, const float* v, const float* weights,
+                              const float* dweights, const float* dout, float* dq, float* dk, float* dv,
+                              float* ds_scratch, int32_t B, int32_t O, int32_t L, int32_t C, int32_t Cv, int32_t mode,
+                              oat_stream_t stream);
+
+/* ---- variant heads ----------------------------------------------------------------------------------
+ * oat_token_pool: out[b] = a * cls[b] + bcoef * mean_l tok[b, l]  (cls may be NULL); token row (b, l) starts at
+ *   tok + b * ld_batch + l * ld_tok, so a [:, 1:] slice of a (B, T, P) tensor is passed without a copy.
+ *   `video_embeddings = (video_embeddings + mean(video_region_feature, 1)) / 2` (oa_model_region_mem.py:119) is
+ *   a = bcoef = 0.5; `torch.mean(region_feat, dim=1)` (trainer/trainer_global_local.py:207) is cls = NULL, bcoef = 1.
+ * oat_token_pool_bwd: dcls = a * dout (optional), dtok[b, l] = bcoef / L * dout[b].
+ * oat_bce_sum: loss[0] = scale * BCELoss(reduction='sum')(p, target) and dp = d loss / d p (optional), with
+ *   torch's clamps (log at -100, gradient denominator at 1e-12): the region loss `0.1 * BCE_sum / rows`
+ *   (trainer/trainer_region_mem.py:97,161-167) is scale = 0.1 / rows. One CTA, fixed summation order. */
+int oat_token_pool(const float* cls, int64_t ld_cls, const float* tok, int64_t ld_batch, int64_t ld_tok, float* out,
+                   int32_t B, int32_t L, int32_t P, float a, float bcoef, oat_stream_t stream);
+int oat_token_pool_bwd(const float* dout, float* dcls, float* dtok, int64_t ld_batch, int64_t ld_tok, int32_t B,
+                       int32_t L, int32_t P, float a, float bcoef, oat_stream_t stream);
+int oat_bce_sum(const float* p, const float* target, int64_t n, float scale, float* loss, float* dp,
+                oat_stream_t stream);
 
 /* ---- retrieval ranks on a square similarity matrix (rows = text queries, columns = videos) ------------------------------
  * t2v_rank[i] = #{j : sims[i][j] > sims[i][i]}                       ties broken optimistically (model/metric.py:62-69)

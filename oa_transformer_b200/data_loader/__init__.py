@@ -15,7 +15,8 @@ class _Sampler:
 class SyntheticTextObjectVideoDataLoader:
     def __init__(self, dataset_name="synthetic", text_params=None, video_params=None, object_params=None,
                  data_dir="", object_dir="", batch_size=16, split="train", num_workers=0, shuffle=True, n_samples=64,
-                 num_objects=0, text_len=32, pre_tokenized=True, args=None, **_unused):
+                 num_objects=0, text_len=32, pre_tokenized=True, args=None, region_mem=False, num_regions=5,
+                 **_unused):
         video_params = video_params or {}
         self.dataset_name, self.split = dataset_name, split
         self.batch_size = batch_size
@@ -23,6 +24,7 @@ class SyntheticTextObjectVideoDataLoader:
         self.frames = video_params.get("num_frames", 4)
         self.res = video_params.get("input_res", 224)
         self.num_objects, self.text_len, self.pre_tokenized = num_objects, text_len, pre_tokenized
+        self.region_mem, self.num_regions = region_mem, num_regions
         self.rank = getattr(args, "rank", 0) if args is not None else 0
         self.train_sampler = _Sampler()
 
@@ -37,6 +39,13 @@ class SyntheticTextObjectVideoDataLoader:
                     "meta": {"dataset": [self.dataset_name] * B, "paths": ["synthetic/%d" % (i * B + j) for j in range(B)]}}
             if self.num_objects:
                 data["object"] = synth_objects(B, self.frames, self.num_objects, g)
+            if self.region_mem:
+                # the region-sensitive loaders (base/base_dataset_region_mem.py) return the anchor frame(s) first and
+                # the clip after them, CLIP text-region embeddings (B, 5, 512) and bbox patch masks (B, 1, 5, 196)
+                data["video"] = torch.randn(B, 2 * self.frames, 3, self.res, self.res, generator=g)
+                data["text_region_embedding"] = torch.randn(B, self.num_regions, 512, generator=g)
+                grid = (self.res // 16) ** 2
+                data["patch_masks"] = (torch.rand(B, 1, self.num_regions, self.frames * grid, generator=g) > 0.7).double()
             if self.pre_tokenized:
                 data["text"] = synth_text(B, self.text_len, g)
             else:

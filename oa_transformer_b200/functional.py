@@ -142,3 +142,128 @@ class AllGatherSlice(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         return grad[ctx.bs * ctx.rank: ctx.bs * (ctx.rank + 1)], None, None
+
+
+# ---------------------------------------------------------------------------------------------- variant heads
+class _LinearFn(torch.autograd.Function):
+    """y = [relu](x) @ w^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate): the projections the variant heads
+    apply to token features (vid_proj over every patch token, oa_model_region_mem.py:142-145) and to the CLIP text-region
+    embeddings (txt_proj_2 = ReLU -> Linear(512, 256), ibid. :70-72,118). x (rows, K) fp32, w (N, K), b (N)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        rows, K = x.shape
+        N = w.shape[0]
+        x = x.contiguous().float()
+        x16 = torch.empty(rows, K, dtype=torch.bfloat16, device=x.device)
+        ops.cast_bf16(x, x16, relu=relu)
+        w16 = torch.empty(N, K, dtype=torch.bfloat16, device=x.device)
+        ops.cast_bf16(w.detach().contiguous().float(), w16)
+        y = torch.empty(rows, N, dtype=torch.float32, device=x.device)
+        ops.gemm(x16, w16, bias=None if b is None else b.detach().contiguous().float(), out_f32=y)
+        ctx.save_for_backward(x if relu else None, x16, w16)
+        ctx.relu, ctx.has_bias = relu, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x16, w16 = ctx.saved_tensors
+        rows, K = x16.shape
+        N = w16.shape[0]
+        dy16 = torch.empty(rows, N, dtype=torch.bfloat16, device=dy.device)
+        ops.cast_bf16(dy.contiguous().float(), dy16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if ctx.relu:
+                dx16 = torch.empty(rows, K, dtype=torch.bfloat16, device=dy.device)
+                ops.gemm(dy16, w16, b_major=1, out_bf16=dx16)
+                dx = torch.empty(rows, K, dtype=torch.float32, device=dy.device)
+                ops.relu_bwd(x, dx16, dx, rows=rows, cols=K, ldx=K)
+            else:
+                dx = torch.empty(rows, K, dtype=torch.float32, device=dy.device)
+                ops.gemm(dy16, w16, b_major=1, out_f32=dx)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
+            ops.gemm(dy16, x16, a_major=1, b_major=1, out_f32=dw, accumulate=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(N, dtype=torch.float32, device=dy.device)
+            ops.colsum_bf16(dy16, db)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, relu=False):
+    """(..., K) -> (..., N): nn.Linear (optionally behind a ReLU) on liboat, differentiable."""
+    lead = x.shape[:-1]
+    y = _LinearFn.apply(x.reshape(-1, x.shape[-1]), w, b, relu)
+    return y.view(*lead, w.shape[0])
+
+
+class _ObjectPatchAttnFn(torch.autograd.Function):
+    """oat_object_patch_attn / _bwd: returns (weights (B,O,L), out (B,O,Cv))."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, masks, mode):
+        cf = lambda t: None if t is None else t.contiguous().float()
+        q, k, v, masks = cf(q), cf(k), cf(v), cf(masks)
+        weights, out = ops.object_patch_attention(q, k, v, mode=mode, masks=masks)
+        ctx.mode = mode
+        ctx.save_for_backward(q, k, v, weights)
+        ctx.set_materialize_grads(False)
+        return weights, out
+
+    @staticmethod
+    def backward(ctx, dweights, dout):
+        q, k, v, weights = ctx.saved_tensors
+        cf = lambda t: None if t is None else t.contiguous().float()
+        if dweights is None and dout is None:
+            return None, None, None, None, None
+        if ctx.mode == "mask":
+            dweights = None           # the masks are data
+            if dout is None:
+                return None, None, None, None, None
+        dq, dk, dv = ops.object_patch_attention_bwd(q, k, v, weights, ctx.mode, dweights=cf(dweights), dout=cf(dout))
+        return dq, dk, dv, None, None
+
+
+def object_patch_attention(q, k, v=None, mode="softmax", masks=None):
+    """Differentiable object -> patch attention: 'mask' pooling (oa_model_global_local.py:178), 'sigmoid' region
+    similarity (oa_model_region_mem.py:147-151), 'softmax'. q (B,O,C), k (B,L,C), v (B,L,Cv), masks (B,O,L)."""
+    return _ObjectPatchAttnFn.apply(q, k, v, masks, mode)
+
+
+class _TokenPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls, tok, a, b):
+        ctx.dims = tuple(tok.shape) + (a, b, cls is not None)
+        return ops.token_pool(None if cls is None else cls.float(), tok.float(), a, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, P, a, b, has_cls = ctx.dims
+        dcls, dtok = ops.token_pool_bwd(dout.contiguous().float(), B, L, P, a, b, need_cls=has_cls)
+        return dcls, dtok, None, None
+
+
+def token_pool(cls, tok, a=0.5, b=0.5):
+    """a * cls + b * mean(tok, dim=1): `(video_embeddings + torch.mean(video_region_feature, dim=1)) / 2`
+    (oa_model_region_mem.py:119); cls=None, b=1 is `torch.mean(region_feat, dim=1)` (trainer_global_local.py:207)."""
+    return _TokenPoolFn.apply(cls, tok, a, b)
+
+
+class _BceSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, target, scale):
+        loss, dp = ops.bce_sum(p.contiguous().float(), target.contiguous().float(), scale)
+        ctx.save_for_backward(dp)
+        ctx.shape = p.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return (dp * g).view(ctx.shape), None, None
+
+
+def bce_sum(p, target, scale=1.0):
+    """scale * nn.BCELoss(reduction='sum')(p, target) (trainer/trainer_region_mem.py:97,166)."""
+    return _BceSumFn.apply(p, target, scale)

@@ -9,7 +9,9 @@ Extensions selected by config keys that old configs do not carry (so they still 
   video_params['model'] == 'SpaceTimeObjectTransformer' or object_params['input_objects'] truthy: per-frame
   object-region tokens are appended to each frame's patch tokens (data['object'], fp32 (B, F, O, 2054) or (B, O, 2054)
   for single-frame loaders) - SURVEY.md section 8a rows X1-X3.
-  text_params['random_init'] / video_params['vit_checkpoint']: build without the pretrained files (benchmarks).
+  text_params['random_init'] (+ 'config': DistilBertConfig overrides) / video_params['vit_checkpoint'] /
+  video_params['depth' | 'embed_dim' | 'num_heads' | 'patch_size' | 'img_size']: build without the pretrained files and
+  at other sizes (benchmarks, fixtures).
 """
 import os
 
@@ -29,6 +31,8 @@ MAX_TEXT_TOKENS = 256      # oat_attn_fwd mode 2 keeps one caption's keys in sha
 
 
 class FrozenInTime(BaseModel):
+    VIDEO_TOWER = SpaceTimeTransformer       # variants swap the tower class (model/oa_model_region_mem.py)
+
     def __init__(self,
                  video_params,
                  object_params,
@@ -48,7 +52,7 @@ class FrozenInTime(BaseModel):
         from transformers import AutoModel
         if text_params.get('random_init', False):
             from transformers import DistilBertConfig, DistilBertModel
-            self.text_model = DistilBertModel(DistilBertConfig())
+            self.text_model = DistilBertModel(DistilBertConfig(**text_params.get('config', {})))
         else:
             self.text_model = AutoModel.from_pretrained(text_params['model'])
         self.text_model.train()
@@ -69,10 +73,12 @@ class FrozenInTime(BaseModel):
                     if vit_path and os.path.exists(vit_path) else None
                 if vit_model is None and not video_params.get('allow_missing_vit', False):
                     raise FileNotFoundError(vit_path)
-                model = SpaceTimeTransformer(num_frames=num_frames, time_init=time_init,
-                                             attention_style=attention_style, object_tokens=self.use_objects,
-                                             modality_token=modality_token,
-                                             img_size=video_params.get('img_size', 224))
+                model = self.VIDEO_TOWER(num_frames=num_frames, time_init=time_init,
+                                         attention_style=attention_style, object_tokens=self.use_objects,
+                                         modality_token=modality_token,
+                                         img_size=video_params.get('img_size', 224),
+                                         **{k: video_params[k] for k in ('depth', 'embed_dim', 'num_heads', 'patch_size')
+                                            if k in video_params})
             else:
                 raise NotImplementedError
             model.head = nn.Identity()
@@ -99,14 +105,17 @@ class FrozenInTime(BaseModel):
         if video_params['model'] != "":
             self.vid_proj = vid_proj
 
-        if load_checkpoint not in ["", None]:
-            # weights_only=False: reference checkpoints pickle their config next to the tensors (base_trainer.py:163-175)
-            checkpoint = torch.load(load_checkpoint, map_location="cpu", weights_only=False)
-            state_dict = checkpoint['state_dict']
-            new_state_dict = state_dict_data_parallel_fix(state_dict, self.state_dict())
-            new_state_dict = self._inflate_positional_embeds(new_state_dict)
-            self.load_state_dict(new_state_dict, strict=False)
         self._text_engine = None
+        if load_checkpoint not in ["", None]:
+            self._load_checkpoint(load_checkpoint)
+
+    def _load_checkpoint(self, load_checkpoint):
+        # weights_only=False: reference checkpoints pickle their config next to the tensors (base_trainer.py:163-175)
+        checkpoint = torch.load(load_checkpoint, map_location="cpu", weights_only=False)
+        state_dict = checkpoint['state_dict']
+        new_state_dict = state_dict_data_parallel_fix(state_dict, self.state_dict())
+        new_state_dict = self._inflate_positional_embeds(new_state_dict)
+        self.load_state_dict(new_state_dict, strict=False)
 
     def set_device(self, device):
         self.device = device

@@ -413,6 +413,63 @@ def object_patch_attention(q, k, v=None, mode="softmax", masks=None, want_weight
     return weights, out
 
 
+def object_patch_attention_bwd(q, k, v, weights, mode, dweights=None, dout=None, need_q=True, need_k=True,
+                               need_v=True):
+    """Gradients of object_patch_attention: returns (dq, dk, dv), each None when not applicable / not requested."""
+    m = {"mask": XATTN_MASK, "sigmoid": XATTN_SIGMOID, "softmax": XATTN_SOFTMAX}[mode]
+    B, O, L = weights.shape
+    dev = weights.device
+    for t in (q, k, v, weights, dweights, dout):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    C = 0 if m == XATTN_MASK else q.shape[2]
+    Cv = v.shape[2] if v is not None else 0
+    dq = torch.empty_like(q) if (m != XATTN_MASK and need_q) else None
+    dk = torch.empty_like(k) if (m != XATTN_MASK and need_k) else None
+    dv = torch.empty_like(v) if (v is not None and dout is not None and need_v) else None
+    ds = torch.empty(B, O, L, dtype=torch.float32, device=dev) if m != XATTN_MASK else None
+    _count(2 if m != XATTN_MASK else 1)
+    check(lib().oat_object_patch_attn_bwd(ptr(q), ptr(k), ptr(v), ptr(weights), ptr(dweights), ptr(dout), ptr(dq),
+                                          ptr(dk), ptr(dv), ptr(ds), _i32(B), _i32(O), _i32(L), _i32(C), _i32(Cv),
+                                          _i32(m), stream_ptr()), "oat_object_patch_attn_bwd")
+    return dq, dk, dv
+
+
+def token_pool(cls, tok, a, b):
+    """out (B, P) = a * cls + b * mean over tokens of tok (B, L, P); tok may be a [:, 1:] style slice (any batch / token
+    pitch, unit inner stride); cls (B, P) or None."""
+    B, L, P = tok.shape
+    assert tok.dtype == torch.float32 and tok.stride(2) == 1
+    assert cls is None or (cls.dtype == torch.float32 and cls.shape == (B, P) and cls.stride(1) == 1)
+    out = torch.empty(B, P, dtype=torch.float32, device=tok.device)
+    _count(1)
+    check(lib().oat_token_pool(ptr(cls), _i64(cls.stride(0) if cls is not None else 0), ptr(tok), _i64(tok.stride(0)),
+                               _i64(tok.stride(1)), ptr(out), _i32(B), _i32(L), _i32(P), _f32(a), _f32(b),
+                               stream_ptr()), "oat_token_pool")
+    return out
+
+
+def token_pool_bwd(dout, B, L, P, a, b, need_cls=True):
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.shape == (B, P)
+    dcls = torch.empty(B, P, dtype=torch.float32, device=dout.device) if need_cls else None
+    dtok = torch.empty(B, L, P, dtype=torch.float32, device=dout.device)
+    _count(1)
+    check(lib().oat_token_pool_bwd(ptr(dout), ptr(dcls), ptr(dtok), _i64(L * P), _i64(P), _i32(B), _i32(L), _i32(P),
+                                   _f32(a), _f32(b), stream_ptr()), "oat_token_pool_bwd")
+    return dcls, dtok
+
+
+def bce_sum(p, target, scale, want_grad=True):
+    """scale * BCELoss(reduction='sum')(p, target) -> (loss[1], dp or None); torch's clamps."""
+    assert p.dtype == torch.float32 and target.dtype == torch.float32 and p.is_contiguous() and target.is_contiguous()
+    assert p.numel() == target.numel()
+    loss = torch.empty(1, dtype=torch.float32, device=p.device)
+    dp = torch.empty_like(p) if want_grad else None
+    _count(1)
+    check(lib().oat_bce_sum(ptr(p), ptr(target), _i64(p.numel()), _f32(scale), ptr(loss), ptr(dp), stream_ptr()),
+          "oat_bce_sum")
+    return loss, dp
+
+
 def patch_masks_from_bbox(boxes, patch_rows=14):
     """boxes: fp64 CUDA tensor [n, >=4] with (x1, y1, x2, y2) in [0,1] -> fp32 masks [n, patch_rows^2] (bit-exact
     with base/base_dataset_global_local.py:348-356)."""

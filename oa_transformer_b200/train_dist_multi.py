@@ -36,7 +36,10 @@ def init_dataloaders(config, module):
     return train, valid
 
 
-def run(config, args):
+def run(config, args, arch_module=None, trainer_cls=None):
+    """arch_module / trainer_cls: the variant entry points swap them (train_dist_region_mem.py)."""
+    module_arch_ = arch_module or module_arch
+    trainer_cls = trainer_cls or Multi_Trainer_dist
     logger = config.get_logger('train')
     os.environ['TOKENIZERS_PARALLELISM'] = "false"
     torch.cuda.set_device(args.local_rank)
@@ -49,7 +52,7 @@ def run(config, args):
         import transformers
         tokenizer = transformers.AutoTokenizer.from_pretrained(text_model)
     data_loader, valid_data_loader = init_dataloaders(config, module_data)
-    model = config.initialize('arch', module_arch)
+    model = config.initialize('arch', module_arch_)
     if args.local_rank == 0:
         logger.info(model)
     loss = config.initialize(name="loss", module=module_loss)
@@ -62,7 +65,7 @@ def run(config, args):
     opt_module = oat_optim if hasattr(oat_optim, config['optimizer']['type']) else (
         transformers if hasattr(transformers, config['optimizer']['type']) else torch.optim)
     optimizer = config.initialize('optimizer', opt_module, trainable)
-    trainer = Multi_Trainer_dist(args, model, loss, metrics, optimizer, config=config, data_loader=data_loader,
+    trainer = trainer_cls(args, model, loss, metrics, optimizer, config=config, data_loader=data_loader,
                                  valid_data_loader=valid_data_loader, tokenizer=tokenizer,
                                  max_samples_per_epoch=config['trainer']['max_samples_per_epoch'])
     trainer.train()
@@ -70,7 +73,7 @@ def run(config, args):
         torch.distributed.destroy_process_group()
 
 
-def main(argv=None):
+def main(argv=None, arch_module=None, trainer_cls=None):
     ap = argparse.ArgumentParser(description='OA-Transformer dual-encoder training (B200 path)')
     ap.add_argument('-c', '--config', default=None, type=str)
     ap.add_argument('-r', '--resume', default=None, type=str)
@@ -91,7 +94,7 @@ def main(argv=None):
         import sys
         sys.argv = [sys.argv[0]] + list(argv)
     config = ConfigParser(ap, options)
-    run(config, config.args)
+    run(config, config.args, arch_module=arch_module, trainer_cls=trainer_cls)
 
 
 if __name__ == '__main__':

@@ -10,6 +10,9 @@ Reference entry points exercised (paths relative to /root/reference/OATrans):
   trainer/trainer_dist.py:AllGather_multi (2-rank gloo)      -> allgather2.pt
   base/base_dataset_global_local.py:patch_all_masks_from_bbox-> patch_masks.pt
   model/metric.py:t2v_metrics / v2t_metrics                  -> metrics.pt
+  model/oa_model_region_mem.py:FrozenInTime over model/oa_video_transformer_region.py:SpaceTimeTransformer,
+  trainer/trainer_region_mem.py:157-167 (region BCE loss)    -> region_small.pt
+  trainer/trainer_global_local.py:187-208 (3-term loss), model/oa_model_global_local.py:178 -> global_local_loss.pt
 """
 import os
 import sys
@@ -251,6 +254,108 @@ def make_metrics():
         out[name] = {"sims": torch.from_numpy(sims), "t2v": t2v, "v2t": v2t}
     torch.save(out, os.path.join(GOLD, "metrics.pt"))
     print("metrics ok", out["n50"]["t2v"])
+
+
+def make_region_small():
+    """The region-sensitive variant end to end through the reference: model/oa_model_region_mem.py:FrozenInTime.forward
+    (:105-123: anchor/video clip split, vid_proj on CLS and region features, txt_proj_2, mean-pool blend, region_sim)
+    over model/oa_video_transformer_region.py:SpaceTimeTransformer (region_norm at layer 6), then the loss of
+    trainer/trainer_region_mem.py:157-167 (NormSoftmaxLoss + 0.1 * BCELoss(sum) / rows)."""
+    from transformers import DistilBertConfig, DistilBertModel
+    if not hasattr(nn.init, "xavier_uniform"):            # deprecated alias the reference still calls (:13)
+        nn.init.xavier_uniform = nn.init.xavier_uniform_
+    from OATrans.model.oa_model_region_mem import FrozenInTime
+    from OATrans.model.oa_video_transformer_region import SpaceTimeTransformer
+    from OATrans.model.model import sim_matrix
+    from OATrans.model.loss import NormSoftmaxLoss
+    d = ref_shim.scratch_cwd(6)
+    torch.manual_seed(6)
+    DistilBertModel(DistilBertConfig(dim=128, hidden_dim=256, n_heads=2, n_layers=2, vocab_size=200,
+                                     max_position_embeddings=16)).save_pretrained(
+        os.path.join(d, "pretrained", "distilbert-base-uncased"))
+    m = FrozenInTime(
+        video_params={"model": "SpaceTimeTransformer", "arch_config": "base_patch16_224", "num_frames": 1,
+                      "pretrained": True, "time_init": "zeros"},
+        object_params={"model": "", "input_objects": False},
+        text_params={"model": "pretrained/distilbert-base-uncased", "pretrained": True, "input": "text"},
+        projection_dim=256, projection="minimal")
+    vm = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=128, depth=6, num_heads=2, num_frames=1,
+                              time_init="rand")
+    vm.head = nn.Identity()
+    vm.pre_logits = nn.Identity()
+    vm.fc = nn.Identity()
+    m.video_model = vm
+    m.vid_proj = nn.Sequential(nn.Linear(128, 256))
+    m.eval()
+    sd = seeded_weights(m.state_dict(), seed=81, scale=0.08)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(82)
+    B, K, L = 4, 5, 4
+    video = torch.randn(B, 2, 3, 32, 32, generator=g)          # frame 0 = anchor image, frame 1 = the (1-frame) clip
+    ids = torch.randint(5, 200, (B, 8), generator=g)
+    mask = torch.ones(B, 8, dtype=torch.long)
+    mask[2, 6:] = 0
+    ids = ids * mask
+    tre = torch.randn(B, K, 512, generator=g)
+    patch_masks = (torch.rand(B, 1, K, L, generator=g) > 0.5).double()     # float64-from-numpy in the loaders
+    data = {"video": video, "text": {"input_ids": ids, "attention_mask": mask}, "text_region_embedding": tre,
+            "patch_masks": patch_masks}
+    text_e, video_e, region_sim = m(data, aug=True)
+    output = sim_matrix(text_e, video_e)
+    loss = NormSoftmaxLoss(0.05)(output)
+    pm = patch_masks.squeeze(1).float()
+    rs, pmv = region_sim.view(-1, region_sim.size(-1)), pm.view(-1, pm.size(-1))
+    r_loss = 0.1 * nn.BCELoss(reduction="sum")(rs, pmv) / rs.size(0)
+    total = loss + r_loss
+    grads = grads_of(m, total)
+    # weights are regenerated from the seed by name (oracle/weights.py); every 1-D gradient and a spread of matrices
+    # are kept, the norm of every gradient beside them
+    keep2d = ("vid_proj.0.weight", "txt_proj.1.weight", "txt_proj_2.1.weight", "video_model.blocks.0.attn.qkv.weight",
+              "video_model.blocks.5.timeattn.proj.weight", "video_model.blocks.3.mlp.fc1.weight",
+              "video_model.patch_embed.proj.weight", "video_model.pos_embed", "video_model.cls_token",
+              "text_model.transformer.layer.0.attention.q_lin.weight", "text_model.embeddings.word_embeddings.weight")
+    small = {k: v for k, v in grads.items() if v.dim() == 1 or k in keep2d}
+    torch.save({"weight_seed": 81, "weight_scale": 0.08, "shapes": {k: tuple(v.shape) for k, v in sd.items()},
+                "video": video, "input_ids": ids, "attention_mask": mask, "text_region_embedding": tre,
+                "patch_masks": patch_masks, "text_embeds": text_e.detach(), "video_embeds": video_e.detach(),
+                "region_sim": region_sim.detach(), "loss": total.detach(), "t2v_loss": loss.detach(),
+                "region_loss": r_loss.detach(), "grads_subset": small,
+                "grad_norms": {k: float(v.norm()) for k, v in grads.items()},
+                "cfg": {"heads": 2, "text_layers": 2}}, os.path.join(GOLD, "region_small.pt"))
+    print("region_small ok loss", float(total), "region", float(r_loss), "grads", len(grads))
+
+
+def make_global_local_loss():
+    """The loss arithmetic of trainer/trainer_global_local.py:187-208 (the trainer's model cannot be constructed - SURVEY
+    fact 3 - so the three terms are evaluated with the reference's sim_matrix / NormSoftmaxLoss on seeded features),
+    plus the mask pooling einsum of model/oa_model_global_local.py:178."""
+    from OATrans.model.model import sim_matrix
+    from OATrans.model.loss import NormSoftmaxLoss
+    g = torch.Generator().manual_seed(91)
+    B, R, P, L = 4, 8, 256, 196
+    names = ("text_embeds", "pad_text_embeds", "video_embeds")
+    t = {k: torch.randn(B, P, generator=g, requires_grad=True) for k in names}
+    region_feat = torch.randn(B, R, P, generator=g, requires_grad=True)
+    tags_feat = torch.randn(B, R, P, generator=g, requires_grad=True)
+    loss_fn = NormSoftmaxLoss(0.05)
+    st2sv = loss_fn(sim_matrix(t["text_embeds"], t["video_embeds"]))
+    lt2sv = loss_fn(sim_matrix(t["pad_text_embeds"], t["video_embeds"]))
+    fine = loss_fn(sim_matrix(torch.mean(region_feat, dim=1), torch.mean(tags_feat, dim=1)))
+    loss = st2sv + lt2sv + fine
+    gs = torch.autograd.grad(loss, [t[k] for k in names] + [region_feat, tags_feat])
+    out = {k: v.detach() for k, v in t.items()}
+    out.update(region_feat=region_feat.detach(), tags_feat=tags_feat.detach(), loss=loss.detach(),
+               terms={"st2sv": st2sv.detach(), "lt2sv": lt2sv.detach(), "fine_grained": fine.detach()},
+               grads={k: gv for k, gv in zip(names + ("region_feat", "tags_feat"), gs)})
+    patch_masks = (torch.rand(B, R, L, generator=g) > 0.8).float()
+    patch_feats = torch.randn(B, L, P, generator=g, requires_grad=True)
+    pooled = torch.einsum('b o l, b l c -> b o c', patch_masks, patch_feats)
+    probe = torch.randn(B, R, P, generator=g)
+    (gp,) = torch.autograd.grad((pooled * probe).sum(), [patch_feats])
+    out.update(patch_masks=patch_masks, patch_feats=patch_feats.detach(), pooled=pooled.detach(), pool_probe=probe,
+               pool_grad=gp)
+    torch.save(out, os.path.join(GOLD, "global_local_loss.pt"))
+    print("global_local_loss ok", float(loss))
 
 
 if __name__ == "__main__":

@@ -325,6 +325,42 @@ def dual_encoder(data, p, cfg):
     return compute_text(data["text"], p, cfg), compute_video(data["video"], p, cfg, data.get("object"))
 
 
+def region_mem_forward(data, p, cfg, region_layer=6):
+    """FrozenInTime.forward of the region-sensitive variant (model/oa_model_region_mem.py:105-123):
+    data['video'] (B, 2F, 3, H, W) viewed as 2B clips (even = anchor frames, odd = video, :111-117); the region tower
+    returns (norm(x)[:, 0], region_norm(x after 6 blocks)[:, 1:]) (oa_video_transformer_region.py:364-376); vid_proj on
+    both (:140-145); video_embeddings = (vid_proj(cls) + mean(vid_proj(regions), 1)) / 2 of the video clips (:119);
+    region_sim = sigmoid(einsum('b k f, b n f -> b k n', txt_proj_2(text_region_embedding), anchor regions)) (:118,147-151).
+    Returns (text_embeddings, video_embeddings, region_sim)."""
+    text_e = compute_text(data["text"], p, cfg)
+    v = data["video"]
+    v = v.reshape(v.shape[0] * 2, -1, v.shape[2], v.shape[3], v.shape[4])
+    cls, region = video_tower(v, p, cfg, region_layer=region_layer)
+    cls_p = linear(cls, p["vid_proj.0.weight"], p["vid_proj.0.bias"], cfg, True)
+    reg_p = linear(region, p["vid_proj.0.weight"], p["vid_proj.0.bias"], cfg)
+    obj_region = reg_p[0::2]
+    video_e, video_region = cls_p[1::2], reg_p[1::2]
+    tre = linear(F.relu(data["text_region_embedding"].float()), p["txt_proj_2.1.weight"], p["txt_proj_2.1.bias"], cfg)
+    video_e = (video_e + video_region.mean(dim=1)) / 2
+    region_sim = torch.sigmoid(torch.einsum("bkf,bnf->bkn", tre, obj_region))
+    return text_e, video_e, region_sim
+
+
+def region_loss(region_sim, patch_mask, weight=0.1):
+    """trainer/trainer_region_mem.py:161-167: 0.1 * BCELoss(reduction='sum')(region_sim rows, mask rows) / rows."""
+    rs = region_sim.reshape(-1, region_sim.shape[-1])
+    pm = patch_mask.reshape(-1, patch_mask.shape[-1]).to(rs.dtype)
+    return weight * F.binary_cross_entropy(rs, pm, reduction="sum") / rs.shape[0]
+
+
+def global_local_loss(text, pad_text, video, region_feat, tags_feat, temperature=0.05):
+    """trainer/trainer_global_local.py:187-208: short-text and tag-padded-text InfoNCE against the video embeddings plus
+    the fine-grained InfoNCE between mean-pooled region and tag features."""
+    return norm_softmax_loss(sim_matrix(text, video), temperature) + \
+        norm_softmax_loss(sim_matrix(pad_text, video), temperature) + \
+        norm_softmax_loss(sim_matrix(region_feat.mean(dim=1), tags_feat.mean(dim=1)), temperature)
+
+
 def sim_matrix(a, b, eps=1e-8):
     """model/model.py:164-172: rows L2-normalised with the norm clamped at eps, then a_n @ b_n^T."""
     an = a / a.norm(dim=1, keepdim=True).clamp_min(eps)
@@ -369,7 +405,7 @@ def object_patch_attention(q, k, v=None, mode="softmax", masks=None):
       'softmax' : weights = softmax(q k^T * C^-0.5)                      (Visualization/.../visualize.py:155-168)
     q (B,O,C), k (B,L,C), v (B,L,Cv). Returns (weights (B,O,L), out (B,O,Cv) or None)."""
     if mode == "mask":
-        w = masks.to(k.dtype)
+        w = masks.to(v.dtype if v is not None else masks.dtype)
     else:
         s = torch.einsum("bkf,bnf->bkn", q, k)
         w = torch.sigmoid(s) if mode == "sigmoid" else (s * q.shape[-1] ** -0.5).softmax(dim=-1)

@@ -271,6 +271,106 @@ def test_cfg4_benchmark_geometry_full_depth_vs_oracles():
     gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
 
 
+def _region_model(g):
+    from oa_transformer_b200.model.oa_model_region_mem import FrozenInTime
+    m = FrozenInTime({"model": "SpaceTimeTransformer", "arch_config": "base_patch16_224", "num_frames": 1,
+                      "pretrained": True, "time_init": "rand", "allow_missing_vit": True, "img_size": 32, "depth": 6,
+                      "embed_dim": 128, "num_heads": 2},
+                     {"model": "", "input_objects": False},
+                     {"model": "distilbert-base-uncased", "pretrained": True, "random_init": True,
+                      "config": dict(dim=128, hidden_dim=256, n_heads=2, n_layers=2, vocab_size=200,
+                                     max_position_embeddings=16)})
+    w = fill_seeded(g["shapes"], g["weight_seed"], g["weight_scale"])
+    missing, unexpected = m.load_state_dict(w, strict=False)
+    assert not unexpected and all(k.startswith("video_model.head.") for k in missing), (missing, unexpected)
+    return m.cuda(), w
+
+
+def test_region_variant_vs_reference_golden():
+    """the region-sensitive variant through the plugin surface (model.oa_model_region_mem.FrozenInTime,
+    trainer.trainer_region_mem.region_loss) against OUTPUTS OF THE REFERENCE (tests/golden/region_small.pt: embeddings,
+    region_sim, both loss terms, gradients), and against the oracle in bf16 mode for the floor."""
+    from oa_transformer_b200.model import NormSoftmaxLoss, sim_matrix
+    from oa_transformer_b200.trainer.trainer_region_mem import region_loss
+    g = torch.load(os.path.join(GOLD, "region_small.pt"), map_location="cpu", weights_only=False)
+    m, w = _region_model(g)
+    m.train()
+    data = {"video": g["video"].cuda(), "text": {"input_ids": g["input_ids"].cuda(),
+                                                  "attention_mask": g["attention_mask"].cuda()},
+            "text_region_embedding": g["text_region_embedding"].cuda(), "patch_masks": g["patch_masks"].cuda()}
+    te, ve, rs = m(data, aug=True)
+    t2v = NormSoftmaxLoss(0.05)(sim_matrix(te, ve))
+    rl = region_loss(rs, data["patch_masks"].squeeze(1).float())
+    (t2v + rl).backward()
+    torch.cuda.synchronize()
+    grads = {k: v.grad.detach().cpu() for k, v in m.named_parameters() if v.grad is not None}
+    assert float((rs.detach().cpu() - g["region_sim"]).abs().max()) < 1e-3
+    assert abs(float(rl) - float(g["region_loss"])) < 1e-3 * float(g["region_loss"])
+    sims = sim_matrix(te, ve).detach().cpu()
+    from oracle import oracle as OO
+    ref_sims = OO.sim_matrix(g["text_embeds"], g["video_embeds"])
+    rep = summarize("region_vs_reference", sims, ref_sims, float(t2v + rl), float(g["loss"]), grads, g["grads_subset"])
+    assert rep["logit_max_abs_err"] < LOGIT_TOL and not rep["missing"]
+    # floor: the oracle in bf16 mode vs the reference on the same tensors
+    p = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    odata = {"video": g["video"], "text": {"input_ids": g["input_ids"], "attention_mask": g["attention_mask"]},
+             "text_region_embedding": g["text_region_embedding"]}
+    ote, ove, ors = OO.region_mem_forward(odata, p, OO.OracleCfg(heads=2, text_layers=2, bf16=True))
+    (OO.norm_softmax_loss(OO.sim_matrix(ote, ove)) + OO.region_loss(ors, g["patch_masks"].squeeze(1).float())).backward()
+    og = {k: v.grad for k, v in p.items() if v.grad is not None and k in g["grads_subset"]}
+    floor = summarize("noise_floor_region", OO.sim_matrix(ote, ove).detach(), ref_sims, 0.0, 0.0, og, g["grads_subset"])
+    gate_grads(floor, vs_truth=rep)
+    # the unused parameters of the reference's forward stay without gradient contributions
+    assert "video_model.region_norm.weight" in grads and "txt_proj_2.1.weight" in grads
+
+
+def test_global_local_loss_head_vs_reference_golden():
+    """trainer/trainer_global_local.py:187-208 (3-term InfoNCE with the mean-pooled fine-grained term) and the mask
+    pooling einsum of model/oa_model_global_local.py:178, forward and backward, vs the reference-generated fixture."""
+    from oa_transformer_b200.model import NormSoftmaxLoss
+    from oa_transformer_b200.trainer.trainer_global_local import global_local_loss, pooled_region_features
+    g = torch.load(os.path.join(GOLD, "global_local_loss.pt"), map_location="cpu", weights_only=False)
+    names = ("text_embeds", "pad_text_embeds", "video_embeds", "region_feat", "tags_feat")
+    t = {k: g[k].cuda().requires_grad_(True) for k in names}
+    loss, terms = global_local_loss(NormSoftmaxLoss(0.05), t["text_embeds"], t["pad_text_embeds"], t["video_embeds"],
+                                    t["region_feat"], t["tags_feat"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+    for k in ("st2sv", "lt2sv", "fine_grained"):
+        assert abs(float(terms[k]) - float(g["terms"][k])) < 1e-4 * abs(float(g["terms"][k])), k
+    for k in names:
+        assert rel(t[k].grad.cpu(), g["grads"][k]) < 1e-3, (k, rel(t[k].grad.cpu(), g["grads"][k]))
+    pf = g["patch_feats"].cuda().requires_grad_(True)
+    pooled = pooled_region_features(g["patch_masks"].cuda(), pf)
+    (pooled * g["pool_probe"].cuda()).sum().backward()
+    assert rel(pooled.detach().cpu(), g["pooled"]) < 1e-5 and rel(pf.grad.cpu(), g["pool_grad"]) < 1e-5
+
+
+def test_train_dist_region_mem_entry_point_synthetic(tmp_path, monkeypatch):
+    """The region variant's entry point (train_dist_region_mem.py wiring: oa_model_region_mem + trainer_region_mem) for
+    one tiny epoch with validation and a checkpoint."""
+    import json as _json
+    from oa_transformer_b200 import train_dist_region_mem
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = _json.load(open(os.path.join(root, "oa_transformer_b200", "configs", "pt", "cc3m_webvid",
+                                       "synthetic-region-mem.json")))
+    cfg["trainer"]["save_dir"] = str(tmp_path)
+    cfg["trainer"]["save_period"] = 1
+    cfg["data_loader"][0]["args"].update({"batch_size": 2, "n_samples": 4})
+    cfg["arch"]["args"]["video_params"]["depth"] = 6
+    cfg["trainer"]["max_samples_per_epoch"] = 4
+    p = tmp_path / "cfg.json"
+    p.write_text(_json.dumps(cfg))
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    train_dist_region_mem.main(["-c", str(p)])
+    ckpts = list(tmp_path.rglob("checkpoint-epoch1.pth"))
+    assert len(ckpts) == 1
+    ck = torch.load(str(ckpts[0]), map_location="cpu", weights_only=False)
+    assert "txt_proj_2.1.weight" in ck["state_dict"] and "video_model.region_norm.weight" in ck["state_dict"]
+
+
 def test_frozen_in_time_module_surface():
     """The nn.Module mirror: constructor, forward(data) -> (text, video) embeddings, backward into .grad."""
     from oa_transformer_b200.model import FrozenInTime, NormSoftmaxLoss, sim_matrix

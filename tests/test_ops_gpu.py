@@ -217,7 +217,9 @@ def _run_attn(mode, B, F, n, H, qkv16, dout16, key_mask=None, fwd_ws=True):
                                           ("time", 1, 8, 40, 2), ("time", 1, 16, 9, 1), ("space", 1, 2, 196, 12),
                                           ("time", 1, 4, 232, 12), ("space", 4, 4, 232, 12), ("space", 1, 2, 128, 2),
                                           ("space", 1, 3, 255, 2), ("time", 2, 8, 232, 12), ("time", 1, 6, 19, 2),
-                                          ("time", 3, 4, 7, 1), ("time", 1, 16, 232, 2), ("time", 2, 3, 33, 3)])
+                                          ("time", 3, 4, 7, 1), ("time", 1, 16, 232, 2), ("time", 2, 3, 33, 3),
+                                          ("time", 2, 1, 4, 2), ("space", 2, 1, 4, 2), ("time", 2, 1, 196, 12),
+                                          ("space", 2, 1, 196, 12)])
 def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     from oa_transformer_b200 import ops
     T = 1 + F * n
@@ -417,6 +419,84 @@ def test_object_patch_attention_modes(mode, C, Ob):
                                       v.cuda(), mode, None if masks is None else masks.cuda().contiguous())
     assert rel(w.cpu(), w_ref) < 1e-5
     assert rel(o.cpu(), o_ref) < 1e-5
+
+
+@pytest.mark.parametrize("mode,C,Ob,L,with_v", [("sigmoid", 256, 5, 196, False), ("sigmoid", 256, 5, 196, True),
+                                                   ("softmax", 768, 36, 196, True), ("softmax", 256, 20, 50, False),
+                                                   ("mask", 0, 20, 196, True)])
+def test_object_patch_attention_backward(mode, C, Ob, L, with_v):
+    """X4 on the fwd/bwd path: gradients of the three score -> weight modes w.r.t. q, k, v through the autograd wrapper
+    (functional.object_patch_attention) vs torch autograd of the oracle (fp32 both sides)."""
+    from oa_transformer_b200.functional import object_patch_attention
+    g = gen(31)
+    B, Cv = 3, 128
+    q = (0.2 * torch.randn(B, Ob, C, generator=g)) if C else None
+    k = (0.2 * torch.randn(B, L, C, generator=g)) if C else None
+    v = torch.randn(B, L, Cv, generator=g) if with_v else None
+    masks = (torch.rand(B, Ob, L, generator=g) > 0.7).float() if mode == "mask" else None
+    pw, po = torch.randn(B, Ob, L, generator=g), torch.randn(B, Ob, Cv, generator=g)
+
+    def run(fn, dev):
+        t = [None if x is None else x.to(dev).clone().requires_grad_(True) for x in (q, k, v)]
+        w, o = fn(t[0], t[1], t[2], mode=mode, masks=None if masks is None else masks.to(dev))
+        loss = (w * pw.to(dev)).sum() if mode != "mask" else 0.0
+        if o is not None:
+            loss = loss + (o * po.to(dev)).sum()
+        loss.backward()
+        return w.detach().cpu(), None if o is None else o.detach().cpu(), [None if x is None else x.grad.cpu() for x in t]
+
+    w_ref, o_ref, g_ref = run(O.object_patch_attention, "cpu")
+    w_out, o_out, g_out = run(object_patch_attention, "cuda")
+    assert rel(w_out, w_ref) < 1e-5 and (o_ref is None or rel(o_out, o_ref) < 1e-5)
+    for a, b, name in zip(g_out, g_ref, "qkv"):
+        assert (a is None) == (b is None), name
+        if b is not None:
+            assert rel(a, b) < 2e-5, (name, rel(a, b))
+
+
+def test_token_pool_bce_and_linear_heads_vs_torch():
+    """The small head ops of the region / global-local variants vs torch: (cls + mean(tokens)) / 2 on a [:, 1:] slice
+    of strided clips, scale * BCELoss(sum) with its gradient, and the differentiable bf16 linear (ReLU -> Linear)."""
+    from oa_transformer_b200 import functional as OF
+    g = gen(33)
+    B2, T, P = 6, 9, 256
+    tok = torch.randn(B2, T, P, generator=g)
+    cls = torch.randn(B2, P, generator=g)
+    probe = torch.randn(B2 // 2, P, generator=g)
+    tr, cr = tok.clone().requires_grad_(True), cls.clone().requires_grad_(True)
+    ref = (cr[1::2] + tr[1::2, 1:].mean(dim=1)) / 2
+    (ref * probe).sum().backward()
+    tc, cc = tok.cuda().requires_grad_(True), cls.cuda().requires_grad_(True)
+    out = OF.token_pool(cc[1::2], tc[1::2, 1:], 0.5, 0.5)
+    (out * probe.cuda()).sum().backward()
+    assert rel(out.detach().cpu(), ref.detach()) < 1e-6
+    assert rel(tc.grad.cpu(), tr.grad) < 1e-6 and rel(cc.grad.cpu(), cr.grad) < 1e-6
+    # BCE(sum): probabilities incl. saturated ones (torch clamps the logs at -100 and the gradient denominator at 1e-12)
+    p = torch.rand(40, 196, generator=g)
+    p[0, :4] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7])
+    t = (torch.rand(40, 196, generator=g) > 0.5).float()
+    pr = p.clone().requires_grad_(True)
+    lref = 0.1 * torch.nn.BCELoss(reduction="sum")(pr, t) / 40
+    lref.backward()
+    pc = p.cuda().requires_grad_(True)
+    lout = OF.bce_sum(pc, t.cuda(), 0.1 / 40)
+    lout.backward()
+    assert abs(float(lout) - float(lref)) < 1e-5 * abs(float(lref))
+    assert torch.allclose(pc.grad.cpu(), pr.grad, rtol=1e-5, atol=1e-9)
+    # ReLU -> Linear(512, 256) (txt_proj_2) vs the bf16-operand oracle
+    x = torch.randn(20, 512, generator=g)
+    w = 0.05 * torch.randn(256, 512, generator=g)
+    b = 0.1 * torch.randn(256, generator=g)
+    probe = torch.randn(20, 256, generator=g)
+    xr, wr, br = (z.clone().requires_grad_(True) for z in (x, w, b))
+    yref = O.linear(torch.relu(xr), wr, br, O.OracleCfg(bf16=True))
+    (yref * probe).sum().backward()
+    xc, wc, bc = (z.cuda().requires_grad_(True) for z in (x, w, b))
+    y = OF.linear(xc, wc, bc, relu=True)
+    (y * probe.cuda()).sum().backward()
+    assert rel(y.detach().cpu(), yref.detach()) < 1e-5
+    for a, r_, name in ((xc, xr, "x"), (wc, wr, "w"), (bc, br, "b")):
+        assert rel(a.grad.cpu(), r_.grad) < 6e-3, (name, rel(a.grad.cpu(), r_.grad))
 
 
 def test_device_prefetcher_stages_batches_in_order():
