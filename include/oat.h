@@ -180,6 +180,24 @@ int oat_object_patch_attn(const float* q, const float* k, const float* v, const 
                           oat_stream_t stream);
 int oat_patch_masks_from_bbox(const double* boxes, int32_t stride, float* masks, int32_t n, int32_t grid,
                               oat_stream_t stream);
+/* The other bookkeeping in front of the path, bit-exact with the reference:
+ * oat_patch_masks_same_class: base/base_dataset_region_mem.py:233-247 - masks[j] = union over every box i with
+ *   classes[i] == classes[sel[j]] of the box's patch rectangle (boxes fp64 [n, stride], scaled by `grid` and cut with
+ *   int() / ceil() as above); sel[para] are the indices random.sample drew on the host.
+ * oat_object_tags_masks: base/base_dataset_global_local.py:395-405 - ends[i] = running sum of int(token_lens[indices[i]])
+ *   (token_lens fp64 as np.loadtxt reads them), total[0] = the sum.
+ * oat_region_features_topk: base/base_dataset.py:593-650 after np.load - rows by descending confidence, v = 2 keeps the
+ *   first region of every object class (np.unique order), np.pad(..., 'edge') to top_k rows - which also pads the
+ *   columns, so with m < top_k regions the row is feat_dim + (top_k - m) + 6 wide, as the reference produces it -
+ *   then [x1/W, y1/H, x1/W + w/W, y1/H + h/H, w/W, h/H]. out: fp32 [top_k, ld_out], ld_out >= feat_dim + top_k + 6;
+ *   m_out[0] = number of regions before padding. n <= 128. */
+int oat_patch_masks_same_class(const double* boxes, int32_t stride, const int32_t* classes, const int32_t* sel,
+                               float* masks, int32_t n, int32_t para, int32_t grid, oat_stream_t stream);
+int oat_object_tags_masks(const double* token_lens, const int64_t* indices, float* ends, int32_t* total, int32_t k,
+                          oat_stream_t stream);
+int oat_region_features_topk(const float* x, const float* bbox, const float* conf, const int64_t* ids, int32_t n,
+                             int32_t feat_dim, int32_t top_k, int32_t v, int32_t image_w, int32_t image_h, float* out,
+                             int64_t ld_out, int32_t* m_out, oat_stream_t stream);
 /* Backward of oat_object_patch_attn. weights = what the forward returned (the masks for mode 0); dweights (B,O,L)
  * and/or dout (B,O,Cv) are the incoming gradients (either may be NULL); dq (B,O,C), dk (B,L,C), dv (B,L,Cv) are
  * written (any may be NULL); ds_scratch: fp32 (B,O,L), needed for modes 1/2. Mode 0 propagates to v only (the masks

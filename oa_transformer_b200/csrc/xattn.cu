@@ -94,9 +94,127 @@ __global__ void patch_masks_kernel(const double* __restrict__ boxes, int stride,
   masks[idx] = (r >= rs && r < re && c >= cs && c < ce) ? 1.0f : 0.0f;
 }
 
+// base/base_dataset_region_mem.py:233-247: for each of the `para` selected boxes, the union of the masks of EVERY box
+// of the same object class; boxes are scaled by the grid size first (fp64, like numpy) and cut with int() / ceil().
+__global__ void patch_masks_same_class_kernel(const double* __restrict__ boxes, int stride, const int* __restrict__ classes,
+                                              const int* __restrict__ sel, float* __restrict__ masks, int n, int para,
+                                              int g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= para * g * g) return;
+  const int j = idx / (g * g), cell = idx - j * g * g, r = cell / g, c = cell - r * g;
+  const int cls = classes[sel[j]];
+  auto norm = [g](long long i) { return i < 0 ? (i + g < 0 ? 0LL : i + g) : (i > g ? static_cast<long long>(g) : i); };
+  float v = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    if (classes[i] != cls) continue;
+    const double* bx = boxes + static_cast<long long>(i) * stride;
+    const double x1 = bx[0] * g, y1 = bx[1] * g, x2 = bx[2] * g, y2 = bx[3] * g;
+    const long long rs = norm(static_cast<long long>(y1)), re = norm(static_cast<long long>(ceil(y2)));
+    const long long cs = norm(static_cast<long long>(x1)), ce = norm(static_cast<long long>(ceil(x2)));
+    if (r >= rs && r < re && c >= cs && c < ce) v = 1.0f;
+  }
+  masks[idx] = v;
+}
+
+// base/base_dataset_global_local.py:395-405: ends[i] = running sum of int(token_len[indices[i]]); total = the sum.
+__global__ void object_tags_masks_kernel(const double* __restrict__ lens, const long long* __restrict__ indices,
+                                         float* __restrict__ ends, int* __restrict__ total, int k) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long end = 0;
+  for (int i = 0; i < k; ++i) {
+    end += static_cast<long long>(lens[indices[i]]);      // int() truncates toward zero
+    ends[i] = static_cast<float>(end);
+  }
+  total[0] = static_cast<int>(end);
+}
+
+// base/base_dataset.py:593-650 (read_object_from_disk after np.load): confidence order, optional class de-duplication
+// (v = 2), numpy 'edge' padding to top_k - which pads BOTH axes, so with m < top_k regions the feature part is
+// 2048 + (top_k - m) wide (reproduced as the reference computes it) - and box geometry scaled by the image size.
+// One CTA per output row; n is small (<= 100 regions), so the order is found by counting.
+__global__ void __launch_bounds__(256)
+region_features_topk_kernel(const float* __restrict__ x, const float* __restrict__ bbox, const float* __restrict__ conf,
+                            const long long* __restrict__ ids, int n, int fdim, int top_k, int v, float image_w,
+                            float image_h, float* __restrict__ out, long long ld_out, int* __restrict__ m_out) {
+  __shared__ int order[128];        // order[r]: index of the r-th most confident region (np.argsort(conf)[::-1])
+  __shared__ int uniq[128];         // v = 2: np.unique(ids, return_index=True)[1] - first index of each class, by class id
+  __shared__ int m_sh;
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) m_sh = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int pos = 0;
+    for (int j = 0; j < n; ++j) pos += (conf[j] > conf[i] || (conf[j] == conf[i] && j > i)) ? 1 : 0;
+    order[pos] = i;
+    if (v == 2) {
+      bool first = true;
+      for (int j = 0; j < i; ++j) first = first && ids[j] != ids[i];
+      if (first) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          bool jf = ids[j] < ids[i];
+          for (int q = 0; jf && q < j; ++q) jf = ids[q] != ids[j];
+          rank += jf ? 1 : 0;
+        }
+        uniq[rank] = i;
+        atomicAdd(&m_sh, 1);
+      }
+    }
+  }
+  __syncthreads();
+  const int m = v == 2 ? m_sh : n;
+  const int res = top_k > m ? top_k - m : 0;
+  if (r == 0 && threadIdx.x == 0) m_out[0] = m;
+  const int rr = r < m ? r : m - 1;                        // 'edge' rows
+  const int src = v == 2 ? order[uniq[rr]] : order[rr];
+  const int fw = fdim + res;                               // 'edge' columns of the feature block
+  for (int c = threadIdx.x; c < fw; c += blockDim.x) out[r * ld_out + c] = x[static_cast<long long>(src) * fdim + (c < fdim ? c : fdim - 1)];
+  if (threadIdx.x == 0) {
+    const float* b = bbox + static_cast<long long>(src) * 4;
+    const float bw = b[2] - b[0], bh = b[3] - b[1];
+    const float sw = __fdiv_rn(bw, image_w), sh = __fdiv_rn(bh, image_h);
+    const float sx = __fdiv_rn(b[0], image_w), sy = __fdiv_rn(b[1], image_h);
+    float* o = out + r * ld_out + fw;
+    o[0] = sx; o[1] = sy; o[2] = __fadd_rn(sx, sw); o[3] = __fadd_rn(sy, sh); o[4] = sw; o[5] = sh;
+  }
+}
+
 }  // namespace oat
 
 using namespace oat;
+
+extern "C" int oat_patch_masks_same_class(const double* boxes, int32_t stride, const int32_t* classes,
+                                          const int32_t* sel, float* masks, int32_t n, int32_t para, int32_t grid,
+                                          oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && para > 0 && grid > 0 && stride >= 4 && boxes != nullptr && classes != nullptr && sel != nullptr,
+              "oat_patch_masks_same_class: bad arguments");
+  const int total = para * grid * grid;
+  patch_masks_same_class_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(boxes, stride, classes, sel, masks, n,
+                                                                                   para, grid);
+  return check_launch("patch_masks_same_class_kernel");
+}
+
+extern "C" int oat_object_tags_masks(const double* token_lens, const int64_t* indices, float* ends, int32_t* total,
+                                     int32_t k, oat_stream_t stream) {
+  OAT_REQUIRE(k > 0 && token_lens != nullptr && indices != nullptr && ends != nullptr && total != nullptr,
+              "oat_object_tags_masks: bad arguments");
+  object_tags_masks_kernel<<<1, 32, 0, as_stream(stream)>>>(token_lens, reinterpret_cast<const long long*>(indices), ends,
+                                                          total, k);
+  return check_launch("object_tags_masks_kernel");
+}
+
+extern "C" int oat_region_features_topk(const float* x, const float* bbox, const float* conf, const int64_t* ids,
+                                        int32_t n, int32_t feat_dim, int32_t top_k, int32_t v, int32_t image_w,
+                                        int32_t image_h, float* out, int64_t ld_out, int32_t* m_out,
+                                        oat_stream_t stream) {
+  OAT_REQUIRE(n > 0 && n <= 128 && top_k > 0 && feat_dim > 0 && (v == 1 || v == 2), "oat_region_features_topk: bad arguments (n <= 128)");
+  OAT_REQUIRE(ld_out >= feat_dim + top_k + 6, "oat_region_features_topk: ld_out must hold feat_dim + top_k + 6 columns");
+  OAT_REQUIRE(v == 1 || ids != nullptr, "oat_region_features_topk: v = 2 needs the object class ids");
+  region_features_topk_kernel<<<top_k, 256, 0, as_stream(stream)>>>(x, bbox, conf, reinterpret_cast<const long long*>(ids),
+                                                                  n, feat_dim, top_k, v, static_cast<float>(image_w),
+                                                                  static_cast<float>(image_h), out, ld_out, m_out);
+  return check_launch("region_features_topk_kernel");
+}
 
 extern "C" int oat_object_patch_attn(const float* q, const float* k, const float* v, const float* masks,
                                      float* weights, float* out, int32_t B, int32_t O, int32_t L, int32_t C,

@@ -480,3 +480,47 @@ def patch_masks_from_bbox(boxes, patch_rows=14):
     check(lib().oat_patch_masks_from_bbox(ptr(boxes), _i32(boxes.shape[1]), ptr(masks), _i32(n), _i32(patch_rows),
                                           stream_ptr()), "oat_patch_masks_from_bbox")
     return masks
+
+
+def patch_masks_same_class(boxes, classes, sel, patch_rows=14):
+    """base/base_dataset_region_mem.py:233-247 on the device: boxes fp64 [n, >=4] in [0,1], classes int32 [n], sel int32
+    [para] (the indices random.sample drew) -> fp32 masks [para, patch_rows^2], each the union over the boxes of the
+    selected box's class. Bit-exact."""
+    assert boxes.dtype == torch.float64 and boxes.dim() == 2 and boxes.is_contiguous()
+    assert classes.dtype == torch.int32 and sel.dtype == torch.int32 and classes.numel() == boxes.shape[0]
+    para = sel.numel()
+    masks = torch.empty(para, patch_rows * patch_rows, dtype=torch.float32, device=boxes.device)
+    _count(1)
+    check(lib().oat_patch_masks_same_class(ptr(boxes), _i32(boxes.shape[1]), ptr(classes), ptr(sel), ptr(masks),
+                                           _i32(boxes.shape[0]), _i32(para), _i32(patch_rows), stream_ptr()),
+          "oat_patch_masks_same_class")
+    return masks
+
+
+def object_tags_masks(token_lens, indices):
+    """base/base_dataset_global_local.py:395-405: (ends fp32 [k] = running end offset of each tag's tokens, total)."""
+    assert token_lens.dtype == torch.float64 and indices.dtype == torch.int64
+    k = indices.numel()
+    ends = torch.empty(k, dtype=torch.float32, device=indices.device)
+    total = torch.empty(1, dtype=torch.int32, device=indices.device)
+    _count(1)
+    check(lib().oat_object_tags_masks(ptr(token_lens), ptr(indices), ptr(ends), ptr(total), _i32(k), stream_ptr()),
+          "oat_object_tags_masks")
+    return ends, int(total.item())
+
+
+def region_features_topk(x, bbox, conf, ids, image_w, image_h, top_k=10, v=1):
+    """base/base_dataset.py:593-650 (read_object_from_disk after np.load) on the device -> fp32 [top_k, 2054 (+ pad)]."""
+    n, fdim = x.shape
+    for t in (x, bbox, conf):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert ids is None or (ids.dtype == torch.int64 and ids.numel() == n)
+    ld = fdim + top_k + 6
+    out = torch.zeros(top_k, ld, dtype=torch.float32, device=x.device)
+    m = torch.empty(1, dtype=torch.int32, device=x.device)
+    _count(1)
+    check(lib().oat_region_features_topk(ptr(x), ptr(bbox), ptr(conf), ptr(ids), _i32(n), _i32(fdim), _i32(top_k),
+                                         _i32(v), _i32(int(image_w)), _i32(int(image_h)), ptr(out), _i64(ld), ptr(m),
+                                         stream_ptr()), "oat_region_features_topk")
+    res = max(0, top_k - int(m.item()))
+    return out[:, :fdim + res + 6].contiguous()

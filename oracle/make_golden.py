@@ -13,6 +13,8 @@ Reference entry points exercised (paths relative to /root/reference/OATrans):
   model/oa_model_region_mem.py:FrozenInTime over model/oa_video_transformer_region.py:SpaceTimeTransformer,
   trainer/trainer_region_mem.py:157-167 (region BCE loss)    -> region_small.pt
   trainer/trainer_global_local.py:187-208 (3-term loss), model/oa_model_global_local.py:178 -> global_local_loss.pt
+  base/base_dataset_region_mem.py:233-247, base/base_dataset_global_local.py:395-405,
+  base/base_dataset.py:593-650 (bbox / tag / region-feature bookkeeping)                    -> bookkeeping.pt
 """
 import os
 import sys
@@ -356,6 +358,85 @@ def make_global_local_loss():
                pool_grad=gp)
     torch.save(out, os.path.join(GOLD, "global_local_loss.pt"))
     print("global_local_loss ok", float(loss))
+
+
+def make_bookkeeping():
+    """Integer / index bookkeeping in front of the path, outputs of the reference's own functions:
+      base/base_dataset_region_mem.py:233-247  patch_all_masks_from_bbox (random pick of 5 boxes, same-class union)
+      base/base_dataset_global_local.py:395-405 object_tags_masks (running end offsets of the tag tokens)
+      base/base_dataset.py:593-650              read_object_from_disk (confidence order, v=2 class de-duplication,
+                                                'edge' padding to top_k, box geometry scaled to [0, 1])"""
+    import importlib
+    import random
+    import tempfile
+    from types import SimpleNamespace
+    out = {}
+    # ---- region_mem masks
+    mod = importlib.import_module("OATrans.base.base_dataset_region_mem")
+    fn = None
+    for name in dir(mod):
+        obj = getattr(mod, name)
+        if isinstance(obj, type) and "patch_all_masks_from_bbox" in obj.__dict__:
+            fn = obj.__dict__["patch_all_masks_from_bbox"]
+            break
+    assert fn is not None
+    rng = np.random.RandomState(101)
+    cases = []
+    for case in range(6):
+        n = int(rng.randint(5, 21))
+        xy = rng.uniform(0, 0.7, (n, 2))
+        wh = rng.uniform(0.05, 0.3, (n, 2))
+        boxes = np.concatenate([xy, xy + wh, wh], axis=1).astype(np.float64)
+        if case == 0:
+            boxes[0, :4] = [0, 0, 1, 1]
+            boxes[1, :4] = [3 / 14, 2 / 14, 6 / 14, 9 / 14]
+        classes = [int(c) for c in rng.randint(0, 6, n)]       # few classes -> same-class unions happen
+        random.seed(200 + case)
+        indexs = random.sample(range(0, n), 5)
+        random.seed(200 + case)
+        masks, sel = fn(None, boxes.copy(), list(classes))
+        cases.append({"boxes": torch.from_numpy(boxes), "classes": torch.tensor(classes, dtype=torch.int32),
+                      "indexs": torch.tensor(indexs, dtype=torch.int32), "masks": torch.from_numpy(masks),
+                      "sel_objects": [int(x) for x in sel]})
+    out["region_mem_masks"] = cases
+    # ---- object_tags_masks
+    gl = importlib.import_module("OATrans.base.base_dataset_global_local")
+    otm = None
+    for name in dir(gl):
+        obj = getattr(gl, name)
+        if isinstance(obj, type) and "object_tags_masks" in obj.__dict__:
+            otm = obj.__dict__["object_tags_masks"]
+            break
+    assert otm is not None
+    lens = rng.randint(1, 5, 1601).astype(np.float64)           # np.loadtxt gives float64 (:279)
+    tags = []
+    for k in (1, 7, 20):
+        idx = [int(i) for i in rng.randint(0, 1601, k)]
+        mask, total = otm(SimpleNamespace(object_token_lens=lens), idx)
+        tags.append({"indices": torch.tensor(idx, dtype=torch.int64), "mask": mask.clone(), "total": int(total)})
+    out["object_tags"] = {"lens": torch.from_numpy(lens), "cases": tags}
+    # ---- region features from an extractor .npz
+    bd = importlib.import_module("OATrans.base.base_dataset")
+    feats = []
+    tmp = tempfile.mkdtemp(prefix="oat_npz_")
+    for case, (n, top_k, v) in enumerate([(20, 10, 1), (6, 10, 1), (20, 10, 2), (12, 36, 1), (9, 10, 2)]):
+        x = np.abs(rng.randn(n, 2048)).astype(np.float32)
+        w, h = int(rng.randint(200, 800)), int(rng.randint(200, 800))
+        x1 = rng.uniform(0, 0.7 * w, n)
+        y1 = rng.uniform(0, 0.7 * h, n)
+        bbox = np.stack([x1, y1, x1 + rng.uniform(10, 0.3 * w, n), y1 + rng.uniform(10, 0.3 * h, n)], axis=1).astype(np.float32)
+        conf = rng.permutation(n).astype(np.float32) / n + 0.01            # distinct confidences
+        ids = rng.randint(0, 8, n).astype(np.int64)
+        path = os.path.join(tmp, "%d.npz" % case)
+        np.savez(path, x=x, bbox=bbox, info={"objects_conf": conf, "objects_id": ids, "image_w": w, "image_h": h})
+        feat = bd.read_object_from_disk(path, top_k=top_k, v=v)
+        feats.append({"x": torch.from_numpy(x), "bbox": torch.from_numpy(bbox), "conf": torch.from_numpy(conf),
+                      "ids": torch.from_numpy(ids), "image_w": w, "image_h": h, "top_k": top_k, "v": v,
+                      "feat": feat.clone()})
+        print("  read_object_from_disk n=%d top_k=%d v=%d ->" % (n, top_k, v), tuple(feat.shape), feat.dtype)
+    out["region_features"] = feats
+    torch.save(out, os.path.join(GOLD, "bookkeeping.pt"))
+    print("bookkeeping ok")
 
 
 if __name__ == "__main__":

@@ -398,6 +398,49 @@ def patch_masks_from_bbox(bboxs, patch_rows=14):
     return masks.reshape(len(b), patch_rows * patch_rows)
 
 
+def patch_masks_same_class(bboxs, object_indexs, indexs, patch_rows=14):
+    """base/base_dataset_region_mem.py:233-247 with the random.sample draw passed in as `indexs`: mask j is the union of
+    the patch rectangles of every box whose class equals that of box indexs[j]. Returns (masks, selected classes)."""
+    b = np.array(bboxs, dtype=np.float64, copy=True)
+    b[:, :4] = b[:, :4] * patch_rows
+    masks = np.zeros((len(indexs), patch_rows, patch_rows), dtype=np.float64)
+    sel = []
+    for j, i in enumerate(indexs):
+        sel.append(object_indexs[i])
+        for idx in range(len(b)):
+            if object_indexs[idx] == object_indexs[i]:
+                masks[j, int(b[idx, 1]):math.ceil(b[idx, 3]), int(b[idx, 0]):math.ceil(b[idx, 2])] = 1
+    return masks.reshape(len(indexs), patch_rows ** 2), sel
+
+
+def object_tags_masks(token_lens, indices):
+    """base/base_dataset_global_local.py:395-405: running end offsets of each tag's tokens and the total length."""
+    ends, end = [], 0
+    for item in indices:
+        end += int(token_lens[item])
+        ends.append(float(end))
+    return torch.tensor(ends, dtype=torch.float32), int(end)
+
+
+def region_features_topk(x, bbox, conf, ids, image_w, image_h, top_k=10, v=1):
+    """base/base_dataset.py:611-649 (read_object_from_disk once the .npz is loaded). numpy float32 in, torch fp32 out.
+    np.pad(a, (0, res), 'edge') pads BOTH axes of a 2-D array: with fewer than top_k regions the feature block widens
+    by res columns - kept, because that is what the reference returns."""
+    order = np.argsort(conf)[::-1]
+    boxes, feats = bbox[order], x[order]
+    if v == 2:
+        _, uniq = np.unique(ids, return_index=True)
+        boxes, feats = boxes[uniq], feats[uniq]
+    if boxes.shape[0] < top_k:
+        res = top_k - boxes.shape[0]
+        boxes, feats = np.pad(boxes, (0, res), 'edge'), np.pad(feats, (0, res), 'edge')
+    boxes, feats = boxes[:top_k, :], feats[:top_k, :]
+    bw, bh = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+    sw, sh, sx, sy = bw / image_w, bh / image_h, boxes[:, 0] / image_w, boxes[:, 1] / image_h
+    spatial = np.stack([sx, sy, sx + sw, sy + sh, sw, sh], axis=1)
+    return torch.cat([torch.from_numpy(feats), torch.from_numpy(spatial)], dim=1)
+
+
 def object_patch_attention(q, k, v=None, mode="softmax", masks=None):
     """One op, three score->weight modes:
       'mask'    : weights = binary patch masks; out = masks @ v          (oa_model_global_local.py:178)

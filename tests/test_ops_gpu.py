@@ -421,6 +421,26 @@ def test_object_patch_attention_modes(mode, C, Ob):
     assert rel(o.cpu(), o_ref) < 1e-5
 
 
+def test_bookkeeping_kernels_bit_exact_vs_reference_fixture():
+    """SURVEY.md 8f-2 on the device, against OUTPUTS OF THE REFERENCE (tests/golden/bookkeeping.pt): same-class union
+    patch masks (base_dataset_region_mem.py:233-247), tag-token end offsets (base_dataset_global_local.py:395-405), region
+    features in confidence order with class de-duplication and numpy 'edge' padding (base_dataset.py:593-650)."""
+    from oa_transformer_b200 import ops
+    g = torch.load(os.path.join(GOLD, "bookkeeping.pt"), map_location="cpu", weights_only=False)
+    for c in g["region_mem_masks"]:
+        masks = ops.patch_masks_same_class(c["boxes"].cuda(), c["classes"].cuda(), c["indexs"].cuda())
+        assert torch.equal(masks.cpu().double(), c["masks"])
+    lens = g["object_tags"]["lens"].cuda()
+    for c in g["object_tags"]["cases"]:
+        ends, total = ops.object_tags_masks(lens, c["indices"].cuda())
+        assert torch.equal(ends.cpu(), c["mask"]) and total == c["total"]
+    for c in g["region_features"]:
+        feat = ops.region_features_topk(c["x"].cuda(), c["bbox"].cuda(), c["conf"].cuda(), c["ids"].cuda(),
+                                        c["image_w"], c["image_h"], c["top_k"], c["v"])
+        assert feat.shape == c["feat"].shape
+        assert torch.equal(feat.cpu(), c["feat"]), (c["top_k"], c["v"], float((feat.cpu() - c["feat"]).abs().max()))
+
+
 @pytest.mark.parametrize("mode,C,Ob,L,with_v", [("sigmoid", 256, 5, 196, False), ("sigmoid", 256, 5, 196, True),
                                                    ("softmax", 768, 36, 196, True), ("softmax", 256, 20, 50, False),
                                                    ("mask", 0, 20, 196, True)])
