@@ -298,7 +298,7 @@ def make_region_small():
     mask = torch.ones(B, 8, dtype=torch.long)
     mask[2, 6:] = 0
     ids = ids * mask
-    tre = torch.randn(B, K, 512, generator=g)
+    tre = 0.05 * torch.randn(B, K, 512, generator=g)          # keeps the region logits of O(1): unsaturated sigmoids
     patch_masks = (torch.rand(B, 1, K, L, generator=g) > 0.5).double()     # float64-from-numpy in the loaders
     data = {"video": video, "text": {"input_ids": ids, "attention_mask": mask}, "text_region_embedding": tre,
             "patch_masks": patch_masks}

