@@ -253,13 +253,49 @@ def main():
         print(json.dumps(line))
 
 
+def run_multi_gpu_check(model, params, step, dev, rank, world, device):
+    import torch
+    import torch.distributed as dist
+    loss = step(dev)                                     # with the all-reduce
+    torch.cuda.synchronize()
+    losses = [torch.zeros(1, device=device) for _ in range(world)]
+    dist.all_gather(losses, loss.detach().reshape(1).float())
+    loss_identical = all(bool(torch.equal(losses[0], x)) for x in losses)
+    probe = [p for p in params if p.grad is not None]
+    aliased = all(p.grad.data_ptr() != 0 for p in probe)
+    # checksum of every reduced gradient, compared bit for bit across ranks
+    sums = torch.stack([p.grad.double().sum() for p in probe] + [p.grad.double().abs().sum() for p in probe])
+    allsums = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(allsums, sums)
+    grads_identical = all(bool(torch.equal(allsums[0], x)) for x in allsums)
+    reduced = [p.grad.detach().clone() for p in probe]
+    # local (unreduced) gradients of the same step, averaged with a separate all-reduce on copies
+    os.environ["OAT_BENCH_NO_REDUCE"] = "1"
+    try:
+        step(dev)
+    finally:
+        os.environ.pop("OAT_BENCH_NO_REDUCE")
+    torch.cuda.synchronize()
+    worst = 0.0
+    for p, r in zip(probe, reduced):
+        local = p.grad.detach().clone()
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        local /= world
+        den = float(local.norm())
+        if den > 0:
+            worst = max(worst, float((local - r).norm()) / den)
+    return {"ranks": world, "loss_identical_across_ranks": loss_identical,
+            "reduced_grads_identical_across_ranks": grads_identical, "p_grad_tensors_checked": len(probe),
+            "reduced_vs_mean_of_local_grads_max_rel": worst, "p_grad_is_reduced_in_place": aliased and worst < 1e-5}
+
+
 def run_ours(args):
 
     import torch
     import torch.distributed as dist
     from oa_transformer_b200 import ops
     from oa_transformer_b200._lib import lib, check
-    from oa_transformer_b200.functional import AllGatherSlice
+    from oa_transformer_b200.functional import AllGatherPairSlice
     from oa_transformer_b200.model import NormSoftmaxLoss, sim_matrix
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,7 +324,9 @@ def run_ours(args):
 
     # what DDP's reducer does (base/base_trainer.py:23): average parameter gradients across ranks. Each tower's flat
     # gradient book is all-reduced as soon as that tower's backward has been enqueued (engine.grad_ready_hook): the
-    # text tower finishes first, so its all-reduce runs under the video tower's backward.
+    # text tower finishes first, so its all-reduce runs under the video tower's backward. The towers hand autograd
+    # fresh views of the book, so p.grad ALIASES the book (no clone) and the in-place all-reduce is the all-reduce of
+    # p.grad; step() waits for the handles before it returns (multi_gpu_check verifies p.grad across ranks).
     pending = []
     layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "0") != "0"     # experiment: all-reduce block by block during backward
     reduced = set()
@@ -303,13 +341,13 @@ def run_ours(args):
         return (lo - base) // 4, (hi - base) // 4
 
     def layer_hook(book, prefix):
-        if world > 1 and layer_reduce:
+        if world > 1 and layer_reduce and not os.environ.get("OAT_BENCH_NO_REDUCE"):
             lo, hi = book_range(book, prefix)
             reduced.add((lo, hi))
             pending.append(dist.all_reduce(book.flat[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
 
     def start_reduce(book):
-        if world > 1:
+        if world > 1 and not os.environ.get("OAT_BENCH_NO_REDUCE"):
             done = sorted(r for r in reduced if True)
             if not (layer_reduce and book is getattr(model.video_model._engine, "_gradbook", None)):
                 pending.append(dist.all_reduce(book.flat, op=dist.ReduceOp.AVG, async_op=True))
@@ -332,8 +370,7 @@ def run_ours(args):
         for eng in (model.video_model._engine, model._text_engine):
             eng.grad_ready_hook = start_reduce
         model.video_model._engine.layer_grad_hook = layer_hook
-        video_g = AllGatherSlice.apply(video_e, rank, world)
-        text_g = AllGatherSlice.apply(text_e, rank, world)
+        video_g, text_g = AllGatherPairSlice.apply(video_e, text_e, rank, world)      # ONE packed all-gather
         loss = loss_fn(sim_matrix(text_g, video_g))
         loss.backward()
         reduce_grads()
@@ -342,6 +379,13 @@ def run_ours(args):
     host = synth_batch(B, rank, pinned=True)
     dev = {"video": host["video"].to(device), "object": host["object"].to(device),
            "text": {k: v.to(device) for k, v in host["text"].items()}}
+
+    # ---------------- multi-GPU self-check (N > 1): same loss on every rank, identical averaged p.grad on every rank, and
+    # p.grad == average over ranks of the LOCAL gradients (what DDP delivers, base/base_trainer.py:23) where each local
+    # gradient comes from the all-gather backward's unreduced slice (trainer_dist.py:40-45)
+    multi_gpu_check = None
+    if world > 1:
+        multi_gpu_check = run_multi_gpu_check(model, params, step, dev, rank, world, device)
 
     # ---------------- device-resident timing
     for _ in range(W):
@@ -510,7 +554,8 @@ def run_ours(args):
                 "loss": loss_val,
                 "model_tflops": value * flops / 1e12,
                 "mfu_vs_sustained_bf16": value * flops / 1e12 / world / peaks["bf16_tflops_sustained"],
-                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "e2e": e2e,
+                "multi_gpu_check": multi_gpu_check, "roofline": roofline,
                 "roofline_attention": roofline_attn, "kernel_ms_breakdown": breakdown, "cpu_baseline": cpu}
     if world > 1:
         dist.destroy_process_group()

@@ -118,6 +118,11 @@ class GradBook:
     def zero(self):
         self.flat.zero_()
 
+    def fresh_view(self, name):
+        """A new tensor object over the same storage (see functional.TowerRunner.bwd)."""
+        v = self.views[name]
+        return self.flat.as_strided(v.shape, v.stride(), v.storage_offset())
+
     def __getitem__(self, name):
         return self.views[name]
 
@@ -451,6 +456,8 @@ class VideoEngine:
                 side_done[i] = ev
             hook = getattr(self, "layer_grad_hook", None)
             if hook is not None:        # every gradient of block i has been enqueued (fc2.bias came from block i+1's LN3)
+                if use_side:            # ... the weight gradients on the side stream: order the hook's work after them
+                    main.wait_event(side_done[i])
                 hook(grads, "%sblocks.%d." % (prefix, i))
             dy, dyb = dyb, dy
             dy16 = dy16b

@@ -54,6 +54,14 @@ class TowerRunner:
         if book is None or getattr(eng, "_gradbook_key", None) != key:
             book = GradBook(self.named, (dout if dout is not None else dtokens).device)
             eng._gradbook, eng._gradbook_key = book, key
+        # Gradients are returned as FRESH views of the flat book, so autograd's AccumulateGrad adopts them as p.grad
+        # without a copy (it clones a tensor somebody else still references): p.grad then aliases the book, and an
+        # in-place all-reduce of book.flat (bench.py, grad_ready_hook) lands in p.grad itself. A p.grad that still
+        # aliases the book from the previous step (no zero_grad(set_to_none=True) in between: gradient accumulation)
+        # is detached from it first, otherwise zeroing the book would wipe the accumulated value.
+        for n, p in self.named:
+            if p.grad is not None and p.grad.data_ptr() == book.views[n].data_ptr():
+                p.grad = p.grad.clone()
         book.zero()
         if dout is None:                # only the token features were used downstream
             dout = torch.zeros(self.out_shape, dtype=torch.float32, device=dtokens.device)
@@ -64,7 +72,7 @@ class TowerRunner:
         hook = getattr(eng, "grad_ready_hook", None)
         if hook is not None:        # e.g. start this tower's gradient all-reduce while the other tower still runs backward
             hook(book)
-        return [book[n] if p.requires_grad else None for n, p in self.named]
+        return [book.fresh_view(n) if p.requires_grad else None for n, p in self.named]
 
 
 def run_tower(engine, named_params, **fwd_kwargs):
@@ -125,6 +133,28 @@ def norm_softmax_loss(x, temperature=0.05):
 
 
 # ---------------------------------------------------------------------------------------------- all-gather
+class AllGatherPairSlice(torch.autograd.Function):
+    """The two embedding all-gathers of trainer_dist.py:159-160 as ONE collective: text and video rows are packed into a
+    (B_loc, 2P) buffer, gathered once into (W * B_loc, 2P) and split again (the payload is 64 KB per rank,
+    pure launch latency). Backward of each half = the local row slice, unreduced (trainer_dist.py:40-45)."""
+
+    @staticmethod
+    def forward(ctx, a, b, rank, world_size):
+        import torch.distributed as dist
+        ctx.rank, ctx.bs, ctx.pa = rank, a.shape[0], a.shape[1]
+        if world_size == 1 or not (dist.is_available() and dist.is_initialized()):
+            return a.contiguous().clone(), b.contiguous().clone()
+        packed = torch.cat([a, b], dim=1).contiguous()
+        out = torch.empty((world_size * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(out, packed)
+        return out[:, :ctx.pa].contiguous(), out[:, ctx.pa:].contiguous()
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        lo, hi = ctx.bs * ctx.rank, ctx.bs * (ctx.rank + 1)
+        return (None if ga is None else ga[lo:hi]), (None if gb is None else gb[lo:hi]), None, None
+
+
 class AllGatherSlice(torch.autograd.Function):
     """all_gather_into_tensor forward; backward = the local row slice, unreduced (trainer_dist.py:40-45)."""
 

@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from ..base import Multi_BaseTrainer_dist
-from ..functional import AllGatherSlice
+from ..functional import AllGatherPairSlice, AllGatherSlice
 from ..model.model import sim_matrix
 from ..utils import inf_loop
 
@@ -31,6 +31,11 @@ class AllGather_multi(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         return grad_output[ctx.bs * ctx.rank: ctx.bs * (ctx.rank + 1)], None, None
+
+
+def allgather_pair(video_embeds, text_embeds, n_gpu, args):
+    """Both AllGather_multi calls of trainer_dist.py:159-160 as one packed collective -> (video_all, text_all)."""
+    return AllGatherPairSlice.apply(video_embeds, text_embeds, args.rank, args.world_size)
 
 
 class Multi_Trainer_dist(Multi_BaseTrainer_dist):
@@ -91,8 +96,8 @@ class Multi_Trainer_dist(Multi_BaseTrainer_dist):
                 self.optimizer.zero_grad()
                 with torch.set_grad_enabled(True):
                     text_embeds, video_embeds = self.model(data, aug=True)
-                    video_embeds = self.allgather(video_embeds, self.n_gpu, self.args)
-                    text_embeds = self.allgather(text_embeds, self.n_gpu, self.args)
+                    # trainer_dist.py:159-160: two AllGather_multi calls; here one packed NCCL all-gather
+                    video_embeds, text_embeds = allgather_pair(video_embeds, text_embeds, self.n_gpu, self.args)
                     output = sim_matrix(text_embeds, video_embeds)
                     loss = self.loss(output)
                 loss.backward()

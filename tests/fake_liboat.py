@@ -197,9 +197,10 @@ def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
 
 
 def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None):
-    x = qkv.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
-    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-    _attn(mode, B, T, H, F, n, q, k, v, key_mask).backward(dout.float().view(B, T, H * 64))
+    with torch.enable_grad():         # may run inside an autograd.Function.backward (grad mode off)
+        x = qkv.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
+        q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        _attn(mode, B, T, H, F, n, q, k, v, key_mask).backward(dout.float().view(B, T, H * 64))
     g = x.grad.clone()
     g[:, :, 0] *= scale           # the q slot holds the scaled query: d/d(unscaled q) = scale * d/d(q)
     dqkv.copy_(g.reshape(B * T, 3 * H * 64).to(BF))

@@ -8,7 +8,7 @@ import torch.multiprocessing as mp
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, packed=False):
     import torch.distributed as dist
     from oa_transformer_b200.functional import AllGatherSlice
     from oracle import oracle as O
@@ -19,8 +19,12 @@ def _worker(rank, world, port, ret):
     B = g["B"]
     t = g["text"][rank * B:(rank + 1) * B].clone().requires_grad_(True)
     v = g["video"][rank * B:(rank + 1) * B].clone().requires_grad_(True)
-    vg = AllGatherSlice.apply(v, rank, world)
-    tg = AllGatherSlice.apply(t, rank, world)
+    if packed:      # one packed collective for both tensors (functional.AllGatherPairSlice)
+        from oa_transformer_b200.functional import AllGatherPairSlice
+        vg, tg = AllGatherPairSlice.apply(v, t, rank, world)
+    else:
+        vg = AllGatherSlice.apply(v, rank, world)
+        tg = AllGatherSlice.apply(t, rank, world)
     assert torch.equal(vg.detach(), g["video"]) and torch.equal(tg.detach(), g["text"])   # rank-order concatenation
     loss = O.norm_softmax_loss(O.sim_matrix(tg, vg))
     loss.backward()
@@ -28,11 +32,15 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_allgather_slice_two_ranks_matches_reference():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_allgather_slice_two_ranks_matches_reference(packed):
     g = torch.load(os.path.join(GOLD, "allgather2.pt"), map_location="cpu", weights_only=False)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, 29643, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29643 + int(packed), ret, packed), nprocs=2, join=True)
     for r in range(2):
         loss, tg, vg = ret[r]
         ref = g["ranks"][r]

@@ -125,3 +125,27 @@ def test_text_engine_schedule_matches_oracle(engine_on_fake_ops):
         if ref_p.grad is None:
             continue
         assert rel(book[name], ref_p.grad) < 8e-2, (name, rel(book[name], ref_p.grad))
+
+
+def test_tower_gradients_alias_the_flat_book_and_still_accumulate(engine_on_fake_ops, monkeypatch):
+    """functional.TowerRunner returns fresh views of the flat gradient book: autograd adopts them as p.grad without a copy
+    (so an in-place all-reduce of the book IS the all-reduce of p.grad - bench.py / ADVICE r1), and a second backward
+    without zero_grad still accumulates (the aliasing p.grad is detached from the book before the book is zeroed)."""
+    engine = engine_on_fake_ops
+    from oa_transformer_b200 import functional
+    dim, heads, layers, B, L = 128, 2, 1, 2, 4
+    spec = text_tower_spec(layers=layers, dim=dim, hidden=256, vocab=50, max_pos=16)
+    spec["txt_proj.1.weight"], spec["txt_proj.1.bias"] = (32, dim), (32,)
+    w = fill_seeded(spec, 5, 0.05)
+    named = [(k, torch.nn.Parameter(v.clone())) for k, v in w.items()]
+    ids = torch.randint(1, 50, (B, L), generator=torch.Generator().manual_seed(1))
+    eng = engine.TextEngine(torch.device("cpu"), heads=heads)
+    out = functional.run_tower(eng, named, input_ids=ids, attention_mask=None)
+    out.sum().backward()
+    book = eng._gradbook
+    first = {n: p.grad.clone() for n, p in named}
+    assert all(p.grad.data_ptr() == book.views[n].data_ptr() for n, p in named)
+    out = functional.run_tower(eng, named, input_ids=ids, attention_mask=None)
+    out.sum().backward()
+    for n, p in named:
+        assert torch.allclose(p.grad, 2 * first[n], rtol=1e-6, atol=1e-8), n
