@@ -84,20 +84,31 @@ __global__ void loss_lse_kernel(const float* __restrict__ sims, int n, int ld, f
 
 // dsims[i,j] = (exp(s/T - row_lse_i) + exp(s/T - col_lse_j) - 2 [i==j]) / (n T); loss = -(1/n) sum_i (2 s_ii/T - row_lse_i - col_lse_i)
 __global__ void loss_grad_logits_kernel(const float* __restrict__ sims, int n, int ld, float inv_t,
-                                        const float* __restrict__ row_lse, const float* __restrict__ col_lse,
-                                        float* __restrict__ dsims, float* __restrict__ loss) {
+                                        float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                                        float* __restrict__ dsims) {
   const int i = blockIdx.x;
   const float rl = row_lse[i];
   const float g = inv_t / n;
+  __syncthreads();                       // every thread holds rl before the slot is recycled below
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const float z = sims[static_cast<long long>(i) * ld + j] * inv_t;
     float d = expf(z - rl) + expf(z - col_lse[j]);
     if (i == j) {
       d -= 2.f;
-      atomicAdd(loss, -(2.f * z - rl - col_lse[j]) / n);
+      // this row's term of the loss takes over the row_lse slot (only block i reads row_lse[i]); the fixed-order sum
+      // below makes the loss bit-identical on every rank of a data-parallel run (no floating-point atomics)
+      row_lse[i] = -(2.f * z - rl - col_lse[j]) / n;
     }
     if (dsims != nullptr) dsims[static_cast<long long>(i) * ld + j] = d * g;
   }
+}
+
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__ terms, int n, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += terms[i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss[0] = acc;
 }
 
 // side 0: dan[i,:] = sum_j dsims[i,j] bn[j,:] ; side 1: dbn[j,:] = sum_i dsims[i,j] an[i,:]
@@ -212,10 +223,9 @@ extern "C" int oat_norm_softmax_loss(const float* sims, int32_t n, int64_t ld, f
   cudaStream_t s = as_stream(stream);
   const float inv_t = 1.0f / temperature;
   loss_lse_kernel<<<2 * n, 256, 0, s>>>(sims, n, static_cast<int>(ld), inv_t, scratch, scratch + n);
-  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), s);
-  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-  loss_grad_logits_kernel<<<n, 256, 0, s>>>(sims, n, static_cast<int>(ld), inv_t, scratch, scratch + n, dsims, loss);
-  return check_launch("loss_grad_logits_kernel");
+  loss_grad_logits_kernel<<<n, 256, 0, s>>>(sims, n, static_cast<int>(ld), inv_t, scratch, scratch + n, dsims);
+  loss_sum_kernel<<<1, 256, 0, s>>>(scratch, n, loss);
+  return check_launch("loss_grad_logits_kernel / loss_sum_kernel");
 }
 
 extern "C" size_t oat_infonce_workspace_bytes(int32_t n, int32_t P) {

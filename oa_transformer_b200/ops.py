@@ -341,7 +341,7 @@ def infonce_fwd_bwd(text, video, temperature=0.05, eps=1e-8, want_sims=False, wa
     sims = torch.empty(n, n, dtype=torch.float32, device=text.device) if want_sims else None
     dt = torch.empty_like(text) if want_grad else None
     dv = torch.empty_like(video) if want_grad else None
-    _count(8)
+    _count(9)
     check(lib().oat_infonce_fwd_bwd(ptr(text), ptr(video), _i32(n), _i32(P), _f32(temperature), _f32(eps), ptr(sims),
                                     ptr(loss), ptr(dt), ptr(dv), ptr(workspace), _sz(nbytes), stream_ptr()),
           "oat_infonce_fwd_bwd")
@@ -371,7 +371,7 @@ def sim_matrix_bwd(dsims, eps, da, db, ws, n, m, P):
 def norm_softmax_loss(sims, temperature, loss, dsims):
     n = sims.shape[0]
     scratch = torch.empty(2 * n, dtype=torch.float32, device=sims.device)
-    _count(2)
+    _count(3)
     check(lib().oat_norm_softmax_loss(ptr(sims), _i32(n), _i64(sims.stride(0)), _f32(temperature), ptr(loss),
                                       ptr(dsims), ptr(scratch), stream_ptr()), "oat_norm_softmax_loss")
 
@@ -524,3 +524,26 @@ def region_features_topk(x, bbox, conf, ids, image_w, image_h, top_k=10, v=1):
                                          stream_ptr()), "oat_region_features_topk")
     res = max(0, top_k - int(m.item()))
     return out[:, :fdim + res + 6].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ profiling of the rest
+def _profiled(kind, fn):
+    """Per-launch CUDA-event timing (only while PROFILE is a list) for the ops that do not time themselves."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        with _Prof(kind, 0.0):
+            return fn(*a, **k)
+    return wrapper
+
+
+for _kind, _names in (("ln_fwd", ("layernorm_fwd",)), ("ln_bwd", ("layernorm_bwd",)), ("colsum", ("colsum_bf16",)),
+                      ("cast", ("cast_bf16", "split3_bf16", "relu_bwd")),
+                      ("embed", ("im2col_patches", "assemble_tokens", "assemble_tokens_bwd", "text_embed", "text_embed_bwd")),
+                      ("loss", ("infonce_fwd_bwd", "sim_matrix_fwd", "sim_matrix_bwd", "norm_softmax_loss"))):
+    for _n in _names:
+        globals()[_n] = _profiled(_kind, globals()[_n])
+CastPlan.run = _profiled("cast_multi", CastPlan.run)
