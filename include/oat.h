@@ -103,6 +103,12 @@ typedef struct oat_attn_args {
   void* dqkv; int64_t ld_dqkv;
   float scale;
   float* cls_acc;
+  /* mode 2 only: dropout on the softmax weights (HF DistilBERT attention_dropout, active because the reference keeps
+   * text_model.train(), model/oa_model.py:28). Weight (b, h, i, j) is dropped iff the Philox draw of element
+   * ((b*H + h)*T + i)*T + j at site dropout_site is < dropout_p * 2^32; kept weights are scaled by 1 / (1 - p). */
+  float dropout_p;
+  uint32_t dropout_site;
+  uint64_t dropout_seed;
 } oat_attn_args;
 size_t oat_attn_fwd_workspace_floats(int32_t mode, int32_t B, int32_t H, int32_t F, int32_t n);
 int oat_attn_fwd(const oat_attn_args* args, oat_stream_t stream);
@@ -136,6 +142,19 @@ int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n,
                    oat_stream_t stream);
 int oat_relu_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, float* dx, int64_t lddx,
                  int64_t rows, int32_t cols, oat_stream_t stream);
+/* Element dropout of the text tower in training mode (HF DistilBERT `dropout`: after the embedding LayerNorm and on
+ * the FFN output before the residual add; the reference leaves text_model.train() on, model/oa_model.py:28).
+ * Masks are Philox4x32-10 draws of (seed, site, element index = row * cols + col): nothing is stored.
+ * oat_dropout_fwd: out = keep(x) / (1 - p) + residual (optional); also as bf16 and / or split-bf16 [hi | hi | lo].
+ * oat_dropout_bwd: dx = keep(dy_f32 + dy_bf16) / (1 - p) as fp32 and / or bf16 (either input / output may be NULL).
+ * oat_dropout_mask: keep[idx] (uint8) for idx < n - what the oracle is given so that both sides drop the same elements. */
+int oat_dropout_fwd(const float* x, int64_t ldx, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                    void* out_bf16, int64_t ldob, void* out_split3, int64_t ld3, int64_t rows, int32_t cols, float p,
+                    uint64_t seed, uint32_t site, oat_stream_t stream);
+int oat_dropout_bwd(const float* dy_f32, int64_t lddy, const void* dy_bf16, int64_t lddyb, float* dx_f32, int64_t lddx,
+                    void* dx_bf16, int64_t lddxb, int64_t rows, int32_t cols, float p, uint64_t seed, uint32_t site,
+                    oat_stream_t stream);
+int oat_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, oat_stream_t stream);
 int oat_im2col_patches(const float* video, void* out_bf16, int64_t BF, int32_t C, int32_t H, int32_t W, int32_t P,
                        oat_stream_t stream);
 int oat_assemble_tokens(const float* patch, const float* object, const float* cls_token, const float* pos_embed,

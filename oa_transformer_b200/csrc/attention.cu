@@ -37,6 +37,10 @@ struct AttnGeom {
   __nv_bfloat16* dqkv;
   float scale;
   float* cls_acc;
+  // mode 2: dropout on the softmax weights (see oat_attn_args)
+  uint32_t drop_thresh, drop_site;
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 struct Group {
@@ -237,6 +241,20 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnGeom G)
       m0 = mn0; m1 = mn1;
 #pragma unroll
       for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      if (G.drop_thresh != 0u) {
+        // dropout acts on the normalised weights: the row sum above keeps every weight, the P.V product only the kept ones
+        const unsigned long long row_base = (static_cast<unsigned long long>(gr.b) * G.H + gr.h) * G.T;
+        const unsigned long long r0 = (row_base + qt * 16 + g) * G.T, r1 = (row_base + qt * 16 + g + 8) * G.T;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = kc * 32 + nt * 8 + 2 * t + e;
+            s[nt][e] = dropout_keep(G.drop_seed, G.drop_site, r0 + j, G.drop_thresh) ? s[nt][e] * G.drop_inv_keep : 0.f;
+            s[nt][2 + e] = dropout_keep(G.drop_seed, G.drop_site, r1 + j, G.drop_thresh) ? s[nt][2 + e] * G.drop_inv_keep : 0.f;
+          }
+        }
+      }
       uint32_t pa[2][4];
       c_to_a(s, pa);
       mma_p_rows(o, pa, vb, kc * 32, lane);
@@ -403,8 +421,14 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_kernel(const AttnGeom G)
           const bool pair_ok = !(gr.has_cls && j == 0) || own_cls_pair;   // only matters for the CLS query rows
           const float p0 = (ok && i0 < nqe && (!cls0 || pair_ok)) ? __expf(s[nt][e] - ls0) : 0.f;
           const float p1 = (ok && i1 < nqe && (!cls1 || pair_ok)) ? __expf(s[nt][2 + e] - ls1) : 0.f;
-          s[nt][e] = p0 * (dp[nt][e] - dl0);
-          s[nt][2 + e] = p1 * (dp[nt][2 + e] - dl1);
+          float dp0 = dp[nt][e], dp1 = dp[nt][2 + e];
+          if (G.drop_thresh != 0u) {      // dP = keep(dO . V^T) / (1 - p); delta already holds sum_j P dP
+            const unsigned long long rb = (static_cast<unsigned long long>(gr.b) * G.H + gr.h) * G.T;
+            dp0 = dropout_keep(G.drop_seed, G.drop_site, (rb + i0) * G.T + j, G.drop_thresh) ? dp0 * G.drop_inv_keep : 0.f;
+            dp1 = dropout_keep(G.drop_seed, G.drop_site, (rb + i1) * G.T + j, G.drop_thresh) ? dp1 * G.drop_inv_keep : 0.f;
+          }
+          s[nt][e] = p0 * (dp0 - dl0);
+          s[nt][2 + e] = p1 * (dp1 - dl1);
         }
       }
       uint32_t dsa[2][4];
@@ -465,9 +489,15 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_bwd_kernel(const AttnGeom G)
           const float ls = lse_s[i], dl = del_s[i];
           const float p0 = (qok && kok0 && !(qcls && kcls0 && !own_cls_pair)) ? __expf(st[nt][e] - ls) : 0.f;
           const float p1 = (qok && kok1) ? __expf(st[nt][2 + e] - ls) : 0.f;
-          pt[nt][e] = p0; pt[nt][2 + e] = p1;
-          st[nt][e] = p0 * (dpt[nt][e] - dl);
-          st[nt][2 + e] = p1 * (dpt[nt][2 + e] - dl);
+          float m0k = 1.f, m1k = 1.f;
+          if (G.drop_thresh != 0u) {      // weight (query i, key j0 / j1): the same draw as in the forward pass
+            const unsigned long long rb = ((static_cast<unsigned long long>(gr.b) * G.H + gr.h) * G.T + i) * G.T;
+            m0k = dropout_keep(G.drop_seed, G.drop_site, rb + j0, G.drop_thresh) ? G.drop_inv_keep : 0.f;
+            m1k = dropout_keep(G.drop_seed, G.drop_site, rb + j1, G.drop_thresh) ? G.drop_inv_keep : 0.f;
+          }
+          pt[nt][e] = p0 * m0k; pt[nt][2 + e] = p1 * m1k;
+          st[nt][e] = p0 * (dpt[nt][e] * m0k - dl);
+          st[nt][2 + e] = p1 * (dpt[nt][2 + e] * m1k - dl);
         }
       }
       uint32_t pa[2][4], dsa[2][4];
@@ -514,6 +544,11 @@ static AttnGeom to_geom(const oat_attn_args* a) {
   G.dout = reinterpret_cast<const __nv_bfloat16*>(a->dout);
   G.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
   G.scale = a->scale; G.cls_acc = a->cls_acc;
+  const bool drop = a->mode == 2 && a->dropout_p > 0.f && a->dropout_p < 1.f;
+  G.drop_thresh = drop ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
+  G.drop_inv_keep = drop ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+  G.drop_site = a->dropout_site;
+  G.drop_seed = a->dropout_seed;
   return G;
 }
 

@@ -66,6 +66,82 @@ __global__ void split3_bf16_kernel(const float* __restrict__ src, long long lds,
   }
 }
 
+// Element dropout (text tower, training mode): see include/oat.h. 4 elements per thread.
+__global__ void dropout_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ residual,
+                                   long long ldr, float* __restrict__ out, long long ldo,
+                                   __nv_bfloat16* __restrict__ out_bf16, long long ldob,
+                                   __nv_bfloat16* __restrict__ out3, long long ld3, long long rows, int cols, float inv_keep,
+                                   uint32_t thresh, uint64_t seed, uint32_t site) {
+  const int vec_per_row = cols >> 2;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const int c = static_cast<int>(idx - r * vec_per_row) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = dropout_keep(seed, site, static_cast<uint64_t>(r) * cols + c + k, thresh) ? o[k] * inv_keep : 0.f;
+    if (residual != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(residual + r * ldr + c);
+      o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+    }
+    if (out != nullptr) *reinterpret_cast<float4*>(out + r * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+    uint2 hi;
+    hi.x = pack_bf16x2(o[0], o[1]);
+    hi.y = pack_bf16x2(o[2], o[3]);
+    if (out_bf16 != nullptr) *reinterpret_cast<uint2*>(out_bf16 + r * ldob + c) = hi;
+    if (out3 != nullptr) {
+      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y);
+      uint2 lo;
+      lo.x = pack_bf16x2(o[0] - h0.x, o[1] - h0.y);
+      lo.y = pack_bf16x2(o[2] - h1.x, o[3] - h1.y);
+      __nv_bfloat16* d = out3 + r * ld3 + c;
+      *reinterpret_cast<uint2*>(d) = hi;
+      *reinterpret_cast<uint2*>(d + cols) = hi;
+      *reinterpret_cast<uint2*>(d + 2 * cols) = lo;
+    }
+  }
+}
+
+__global__ void dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ dyb,
+                                   long long lddyb, float* __restrict__ dx, long long lddx,
+                                   __nv_bfloat16* __restrict__ dxb, long long lddxb, long long rows, int cols,
+                                   float inv_keep, uint32_t thresh, uint64_t seed, uint32_t site) {
+  const int vec_per_row = cols >> 2;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const int c = static_cast<int>(idx - r * vec_per_row) << 2;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (dy != nullptr) {
+      const float4 v = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    if (dyb != nullptr) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(dyb + r * lddyb + c);
+      const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+      o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = dropout_keep(seed, site, static_cast<uint64_t>(r) * cols + c + k, thresh) ? o[k] * inv_keep : 0.f;
+    if (dx != nullptr) *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (dxb != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      *reinterpret_cast<uint2*>(dxb + r * lddxb + c) = pk;
+    }
+  }
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, uint32_t thresh, uint64_t seed, uint32_t site) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    keep[idx] = dropout_keep(seed, site, static_cast<uint64_t>(idx), thresh) ? 1 : 0;
+}
+
 // Many casts in one launch (the bf16 operand copies of every weight of a tower, re-packed each step): a device table
 // row = {src, dst, rows, cols, cols_padded, src pitch, dst pitch, kind}, chunk_prefix = prefix sum of the
 // 1024-element chunks of each tensor's padded (rows x cols_padded) extent. kind 0: bf16 copy; 1: plain fp32 copy (bias
@@ -354,6 +430,43 @@ extern "C" int oat_split3_bf16(const float* src, int64_t lds, void* dst, int64_t
   split3_bf16_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
       src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, relu);
   return check_launch("split3_bf16_kernel");
+}
+
+extern "C" int oat_dropout_fwd(const float* x, int64_t ldx, const float* residual, int64_t ldr, float* out, int64_t ldo,
+                               void* out_bf16, int64_t ldob, void* out_split3, int64_t ld3, int64_t rows, int32_t cols,
+                               float p, uint64_t seed, uint32_t site, oat_stream_t stream) {
+  OAT_REQUIRE(x != nullptr && cols > 0 && cols % 4 == 0 && p >= 0.f && p < 1.f, "oat_dropout_fwd: bad arguments (cols %% 4, 0 <= p < 1)");
+  OAT_REQUIRE(ldx % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && ldob % 4 == 0 && ld3 % 4 == 0, "oat_dropout_fwd: pitches must be multiples of 4");
+  OAT_REQUIRE(out_split3 == nullptr || ld3 >= 3LL * cols, "oat_dropout_fwd: split output needs a pitch >= 3 * cols");
+  if (rows <= 0) return OAT_OK;
+  const long long total = rows * (cols / 4);
+  dropout_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      x, ldx, residual, ldr, out, ldo, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldob,
+      reinterpret_cast<__nv_bfloat16*>(out_split3), ld3, rows, cols, 1.0f / (1.0f - p),
+      static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0), seed, site);
+  return check_launch("dropout_fwd_kernel");
+}
+
+extern "C" int oat_dropout_bwd(const float* dy_f32, int64_t lddy, const void* dy_bf16, int64_t lddyb, float* dx_f32,
+                               int64_t lddx, void* dx_bf16, int64_t lddxb, int64_t rows, int32_t cols, float p,
+                               uint64_t seed, uint32_t site, oat_stream_t stream) {
+  OAT_REQUIRE((dy_f32 != nullptr || dy_bf16 != nullptr) && (dx_f32 != nullptr || dx_bf16 != nullptr) && cols > 0 &&
+              cols % 4 == 0 && p >= 0.f && p < 1.f, "oat_dropout_bwd: bad arguments");
+  OAT_REQUIRE(lddy % 4 == 0 && lddyb % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0, "oat_dropout_bwd: pitches must be multiples of 4");
+  if (rows <= 0) return OAT_OK;
+  const long long total = rows * (cols / 4);
+  dropout_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      dy_f32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), lddyb, dx_f32, lddx,
+      reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb, rows, cols, 1.0f / (1.0f - p),
+      static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0), seed, site);
+  return check_launch("dropout_bwd_kernel");
+}
+
+extern "C" int oat_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, oat_stream_t stream) {
+  OAT_REQUIRE(keep != nullptr && n > 0 && p >= 0.f && p < 1.f, "oat_dropout_mask: bad arguments");
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      keep, n, static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0), seed, site);
+  return check_launch("dropout_mask_kernel");
 }
 
 extern "C" int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,

@@ -360,6 +360,30 @@ __device__ __forceinline__ void gelu_fwd_grad2(float x0, float x1, float& g0, fl
   f2_unpack(f2_fma(f2_mul(x, f2_pack(0.39894228040143268f, 0.39894228040143268f)), e, cdf), d0, d1);
 }
 
+// Counter-based dropout masks (Philox4x32-10): element `idx` of dropout site `site` under `seed` is kept iff its
+// 32-bit draw is >= thresh = p * 2^32. The same function runs in the forward kernels, the backward kernels and the
+// mask-export kernel (oat_dropout_mask), so a mask never has to be stored.
+__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint32_t c0 = static_cast<uint32_t>(idx >> 2), c1 = static_cast<uint32_t>(idx >> 34), c2 = site, c3 = 0x0A7D0u;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint32_t sel = static_cast<uint32_t>(idx) & 3u;
+  return sel == 0 ? c0 : (sel == 1 ? c1 : (sel == 2 ? c2 : c3));
+}
+__device__ __forceinline__ uint32_t dropout_thresh(float p) {
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thresh) {
+  return philox_draw(seed, site, idx) >= thresh;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));

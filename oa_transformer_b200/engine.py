@@ -492,8 +492,15 @@ class TextEngine:
         self._plan = ops.CastPlan()
 
     def forward(self, p, input_ids, attention_mask=None, proj=("txt_proj.1.weight", "txt_proj.1.bias"),
-                prefix="text_model.", save=True):
+                prefix="text_model.", save=True, dropout=None):
+        """dropout = {"p": hidden dropout, "p_attn": attention dropout, "seed": int} reproduces DistilBERT's training
+        mode (the reference keeps text_model.train(), model/oa_model.py:28): after the embedding LayerNorm (site 0), on
+        the softmax weights of layer i (site 1 + 3 i) and on the FFN output before the residual add (site 2 + 3 i).
+        The masks are Philox draws of (seed, site, element): nothing is stored, backward re-draws them."""
         bufs = self.bufs
+        pd = float(dropout["p"]) if dropout else 0.0
+        pa = float(dropout["p_attn"]) if dropout else 0.0
+        seed = int(dropout["seed"]) if dropout else 0
         B, Lq = input_ids.shape
         H = self.H
         word = p[prefix + "embeddings.word_embeddings.weight"]
@@ -536,22 +543,26 @@ class TextEngine:
         emb = bufs.get("emb", (M, D), F32)
         ops.text_embed(ids, word, pos, emb, Lq)
 
-        def ln(tag, src, wname):
-            """-> (GEMM operand [M, S3*D], its plain bf16 part [M, D], fp32 value, mean, rstd)"""
+        def ln(tag, src, wname, drop_site=None):
+            """-> (GEMM operand [M, S3*D], its plain bf16 part [M, D], fp32 value, mean, rstd); with drop_site the
+            normalised rows pass through dropout before they become the residual stream and the GEMM operand."""
             y32 = bufs.get("y32." + tag, (M, D), F32)
             mean = bufs.get("mean." + tag, (M,), F32)
             rstd = bufs.get("rstd." + tag, (M,), F32)
+            dropped = drop_site is not None and pd > 0.0
+            y3 = bufs.get("y3." + tag, (M, 3 * D), BF) if split else None
+            y16 = None if split else bufs.get("y16." + tag, (M, D), BF)
+            if dropped:
+                ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_f32=y32, mean=mean, rstd=rstd)
+                ops.dropout_fwd(y32, pd, seed, drop_site, out=y32, out_bf16=y16, out_split3=y3)
+            else:
+                ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_bf16=y16, y_f32=y32,
+                                  mean=mean, rstd=rstd, y_split=y3, split_period=1)
             if split:
-                y3 = bufs.get("y3." + tag, (M, 3 * D), BF)
-                ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_f32=y32, mean=mean,
-                                  rstd=rstd, y_split=y3, split_period=1)
                 return y3, y3[:, :D], y32, mean, rstd
-            y16 = bufs.get("y16." + tag, (M, D), BF)
-            ops.layernorm_fwd(src, p[wname + ".weight"], p[wname + ".bias"], self.eps, y_bf16=y16, y_f32=y32,
-                              mean=mean, rstd=rstd)
             return y16, y16, y32, mean, rstd
 
-        xop, x16, x32, m0, r0 = ln("emb", emb, prefix + "embeddings.LayerNorm")
+        xop, x16, x32, m0, r0 = ln("emb", emb, prefix + "embeddings.LayerNorm", drop_site=0)
         layers = []
         for i in range(layers_n):
             b = "%stransformer.layer.%d." % (prefix, i)
@@ -561,7 +572,8 @@ class TextEngine:
             ops.gemm(xop, wqkv, bias=bqkv, scale_cols=D, scale=Q_SCALE, out_bf16=qkv)
             ctx = bufs.get("ctx.%d" % i, (M, D), BF)
             lse = bufs.get("lse.%d" % i, (B * H * Lq,), F32)
-            ops.attn_fwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, qkv, ctx, lse, key_mask)
+            ops.attn_fwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, qkv, ctx, lse, key_mask,
+                         dropout=(pa, seed, 1 + 3 * i) if pa > 0.0 else None)
             wo = W[(i, "o")]
             sa_sum = bufs.get("sa_sum.%d" % i, (M, D), F32)
             ops.gemm(ctx, hi(wo), bias=p[b + "attention.out_lin.bias"], residual=x32, out_f32=sa_sum)
@@ -573,15 +585,20 @@ class TextEngine:
             u = bufs.get("u.%d" % i, (M, Hd), BF)
             g = bufs.get("g.%d" % i, (M, Hd), BF)
             ffn_sum = bufs.get("ffn_sum.%d" % i, (M, D), F32)
+            # FFN.ff_chunk: lin2 output -> dropout -> + residual; without dropout the residual add rides in the GEMM epilogue
+            ffn_out = bufs.get("ffn_tmp", (M, D), F32) if pd > 0.0 else ffn_sum
+            ffn_res = None if pd > 0.0 else y32
             if split:
                 g32 = bufs.get("g32", (M, Hd), F32)
                 ops.gemm(yop, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_f32=g32, out_bf16=g, out2_bf16=u)
                 g3 = bufs.get("g3", (M, 3 * Hd), BF)
                 ops.split3_bf16(g32, g3)
-                ops.gemm(g3, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
+                ops.gemm(g3, w2, bias=p[b + "ffn.lin2.bias"], residual=ffn_res, out_f32=ffn_out)
             else:
                 ops.gemm(y16, w1, bias=p[b + "ffn.lin1.bias"], act=ops.ACT_GELU, out_bf16=g, out2_bf16=u)
-                ops.gemm(g, w2, bias=p[b + "ffn.lin2.bias"], residual=y32, out_f32=ffn_sum)
+                ops.gemm(g, w2, bias=p[b + "ffn.lin2.bias"], residual=ffn_res, out_f32=ffn_out)
+            if pd > 0.0:
+                ops.dropout_fwd(ffn_out, pd, seed, 2 + 3 * i, residual=y32, out=ffn_sum)
             xop, x16, x32, m2, r2 = ln("out.%d" % i, ffn_sum, b + "output_layer_norm")
             L.update(wqkv=hi(wqkv), qkv=qkv, ctx=ctx, lse=lse, wo=hi(wo), sa_sum=sa_sum, y16=y16, m1=m1, r1=r1,
                      w1=hi(w1), w2=hi(w2), u=u, g=g, ffn_sum=ffn_sum, m2=m2, r2=r2)
@@ -604,7 +621,7 @@ class TextEngine:
                 ops.gemm(r16, wt, bias=p[proj[1]], out_f32=out)
         if save:
             self.saved = dict(B=B, Lq=Lq, M=M, D=D, ids=ids, key_mask=key_mask, emb=emb, m0=m0, r0=r0, layers=layers,
-                              last32=x32, r16=r16, wt=wt, proj=proj, prefix=prefix)
+                              last32=x32, r16=r16, wt=wt, proj=proj, prefix=prefix, drop=(pd, pa, seed))
         return out
 
     def backward(self, p, grads, dout):
@@ -615,6 +632,7 @@ class TextEngine:
         H = self.H
         prefix = S["prefix"]
         layers = S["layers"]
+        pd, pa, seed = S["drop"]
 
         def wgrad_into(dy16, act16, wview, bview):
             ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=wview, accumulate=True)
@@ -651,9 +669,16 @@ class TextEngine:
             Hd = L["u"].shape[1]
             du = bufs.get("du", (M, Hd), BF)
             # x_out = LN(ffn_sum),  ffn_sum = lin2(gelu(lin1(y))) + y
-            ops.layernorm_bwd(L["ffn_sum"], L["m2"], L["r2"], p[b + "output_layer_norm.weight"], dy_bf16=dX16,
-                              dy_f32=dX, dx=dffn, dx_bf16=dffn16, dgamma=grads[b + "output_layer_norm.weight"],
-                              dbeta=grads[b + "output_layer_norm.bias"], dxsum=grads[b + "ffn.lin2.bias"])
+            if pd > 0.0:    # the FFN branch sees the gradient through its dropout mask; the skip (dffn) does not
+                ops.layernorm_bwd(L["ffn_sum"], L["m2"], L["r2"], p[b + "output_layer_norm.weight"], dy_bf16=dX16,
+                                  dy_f32=dX, dx=dffn, dgamma=grads[b + "output_layer_norm.weight"],
+                                  dbeta=grads[b + "output_layer_norm.bias"])
+                ops.dropout_bwd(pd, seed, 2 + 3 * i, dy_f32=dffn, dx_bf16=dffn16)
+                ops.colsum_bf16(dffn16, grads[b + "ffn.lin2.bias"])
+            else:
+                ops.layernorm_bwd(L["ffn_sum"], L["m2"], L["r2"], p[b + "output_layer_norm.weight"], dy_bf16=dX16,
+                                  dy_f32=dX, dx=dffn, dx_bf16=dffn16, dgamma=grads[b + "output_layer_norm.weight"],
+                                  dbeta=grads[b + "output_layer_norm.bias"], dxsum=grads[b + "ffn.lin2.bias"])
             ops.gemm(dffn16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du)
             wgrad_into(dffn16, L["g"], grads[b + "ffn.lin2.weight"], None)
             ops.gemm(du, L["w1"], b_major=1, out_bf16=dya)
@@ -665,7 +690,7 @@ class TextEngine:
             ops.gemm(dsa16, L["wo"], b_major=1, out_bf16=dctx)
             wgrad_into(dsa16, L["ctx"], grads[b + "attention.out_lin.weight"], None)
             ops.attn_bwd(ops.MODE_PLAIN, B, Lq, H, 0, 0, L["qkv"], L["ctx"], L["lse"], dctx, dqkv, Q_SCALE, None,
-                         S["key_mask"])
+                         S["key_mask"], dropout=(pa, seed, 1 + 3 * i) if pa > 0.0 else None)
             ops.gemm(dqkv, L["wqkv"], b_major=1, out_bf16=dxa)
             dwqkv.zero_()
             dbqkv.zero_()
@@ -678,6 +703,9 @@ class TextEngine:
             dX16 = dxa      # consumed by the first LayerNorm backward of the next iteration, rewritten after it
 
         demb = dffn
+        if pd > 0.0:        # embedding dropout sits between the LayerNorm and everything that consumed its output
+            ops.dropout_bwd(pd, seed, 0, dy_f32=dX, dy_bf16=dX16, dx_f32=dsa)
+            dX, dX16 = dsa, None
         ops.layernorm_bwd(S["emb"], S["m0"], S["r0"], p[prefix + "embeddings.LayerNorm.weight"], dy_bf16=dX16,
                           dy_f32=dX, dx=demb, dgamma=grads[prefix + "embeddings.LayerNorm.weight"],
                           dbeta=grads[prefix + "embeddings.LayerNorm.bias"])

@@ -146,8 +146,17 @@ class FrozenInTime(BaseModel):
                              "truncation=True, max_length=%d" % (MAX_TEXT_TOKENS, ids.shape[1], MAX_TEXT_TOKENS))
         if self._text_engine is None or self._text_engine.device != ids.device:
             self._text_engine = TextEngine(ids.device, heads=self.text_model.config.n_heads)
+        # `self.text_model.train()` (oa_model.py:28) leaves DistilBERT's dropout on whenever the module is in training mode:
+        # embedding, attention-weight and FFN-output dropout at the config's rates, fresh Philox masks every call
+        # (seeded from torch's CPU generator, so torch.manual_seed reproduces a run); model.eval() turns it off
+        dropout = None
+        if self.training:
+            cfg = self.text_model.config
+            pd, pa = float(getattr(cfg, "dropout", 0.0)), float(getattr(cfg, "attention_dropout", 0.0))
+            if pd > 0.0 or pa > 0.0:
+                dropout = {"p": pd, "p_attn": pa, "seed": int(torch.randint(0, 2 ** 62, (1,)).item())}
         return run_tower(self._text_engine, self._text_named(), input_ids=ids,
-                         attention_mask=text_data.get('attention_mask'))
+                         attention_mask=text_data.get('attention_mask'), dropout=dropout)
 
     # ------------------------------------------------------------------ video
     def _video_named(self):

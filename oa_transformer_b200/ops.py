@@ -147,6 +147,7 @@ class AttnArgs(ctypes.Structure):
         ("dqkv", _vp), ("ld_dqkv", _i64),
         ("scale", _f32),
         ("cls_acc", _vp),
+        ("dropout_p", _f32), ("dropout_site", ctypes.c_uint32), ("dropout_seed", ctypes.c_uint64),
     ]
 
 
@@ -185,10 +186,18 @@ def attn_fwd_workspace_floats(mode, B, H, F, n=1):
     return int(f(_i32(mode), _i32(B), _i32(H), _i32(F), _i32(n)))
 
 
-def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
+def _set_dropout(a, mode, dropout):
+    if dropout is not None and dropout[0] > 0.0:
+        assert mode == MODE_PLAIN, "attention-weight dropout exists in the text tower only"
+        a.dropout_p, a.dropout_seed, a.dropout_site = float(dropout[0]), int(dropout[1]), int(dropout[2])
+
+
+def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None, dropout=None):
     """qkv bf16 [B*T, 3*H*64] (q pre-scaled) -> out bf16 [B*T, H*64], lse fp32 [B*H*T].
-    cls_ws (fp32, attn_fwd_workspace_floats) selects the tcgen05 space kernel with the CLS query fused in."""
+    cls_ws (fp32, attn_fwd_workspace_floats) selects the tcgen05 space kernel with the CLS query fused in.
+    dropout = (p, seed, site): mode 2 only, Philox dropout on the softmax weights (same triple in attn_bwd)."""
     a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
+    _set_dropout(a, mode, dropout)
     if cls_ws is not None:
         assert cls_ws.dtype == torch.float32 and cls_ws.numel() >= attn_fwd_workspace_floats(mode, B, H, F, n)
         a.cls_acc = ptr(cls_ws)
@@ -197,8 +206,9 @@ def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
         check(lib().oat_attn_fwd(ctypes.byref(a), stream_ptr()), "oat_attn_fwd")
 
 
-def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None):
+def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None):
     a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
+    _set_dropout(a, mode, dropout)
     assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16
     a.dout, a.ld_dout = ptr(dout), dout.stride(0)
     a.dqkv, a.ld_dqkv = ptr(dqkv), dqkv.stride(0)
@@ -229,6 +239,42 @@ def split3_bf16(src, dst, *, rows=None, cols=None, lds=None, relu=False):
     _count(1)
     check(lib().oat_split3_bf16(ptr(src), _i64(lds), ptr(dst), _i64(dst.stride(0)), _i64(rows), _i32(cols),
                                 _i32(1 if relu else 0), stream_ptr()), "oat_split3_bf16")
+
+
+_u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
+
+
+def dropout_fwd(x, p, seed, site, *, residual=None, out=None, out_bf16=None, out_split3=None, rows=None):
+    """out = keep(x) / (1 - p) + residual, optionally also as bf16 / split-bf16 [hi | hi | lo] (include/oat.h)."""
+    rows = x.shape[0] if rows is None else rows
+    cols = x.shape[1]
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    _count(1)
+    check(lib().oat_dropout_fwd(ptr(x), _i64(x.stride(0)), ptr(residual), _i64(residual.stride(0) if residual is not None else 0),
+                                ptr(out), _i64(out.stride(0) if out is not None else 0),
+                                ptr(out_bf16), _i64(out_bf16.stride(0) if out_bf16 is not None else 0),
+                                ptr(out_split3), _i64(out_split3.stride(0) if out_split3 is not None else 0),
+                                _i64(rows), _i32(cols), _f32(p), _u64(seed), _u32(site), stream_ptr()), "oat_dropout_fwd")
+
+
+def dropout_bwd(p, seed, site, *, dy_f32=None, dy_bf16=None, dx_f32=None, dx_bf16=None):
+    """dx = keep(dy_f32 + dy_bf16) / (1 - p) as fp32 and / or bf16."""
+    ref = dy_f32 if dy_f32 is not None else dy_bf16
+    rows, cols = ref.shape
+    _count(1)
+    check(lib().oat_dropout_bwd(ptr(dy_f32), _i64(dy_f32.stride(0) if dy_f32 is not None else 0),
+                                ptr(dy_bf16), _i64(dy_bf16.stride(0) if dy_bf16 is not None else 0),
+                                ptr(dx_f32), _i64(dx_f32.stride(0) if dx_f32 is not None else 0),
+                                ptr(dx_bf16), _i64(dx_bf16.stride(0) if dx_bf16 is not None else 0),
+                                _i64(rows), _i32(cols), _f32(p), _u64(seed), _u32(site), stream_ptr()), "oat_dropout_bwd")
+
+
+def dropout_mask(n, p, seed, site, device):
+    """uint8 keep flags of elements 0..n-1 of a dropout site: the draws every liboat kernel makes for (seed, site)."""
+    keep = torch.empty(n, dtype=torch.uint8, device=device)
+    _count(1)
+    check(lib().oat_dropout_mask(ptr(keep), _i64(n), _f32(p), _u64(seed), _u32(site), stream_ptr()), "oat_dropout_mask")
+    return keep
 
 
 class CastPlan:

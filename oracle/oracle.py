@@ -146,13 +146,16 @@ def gelu(x, cfg):
     return _GeluBF16.apply(x) if cfg.bf16 else F.gelu(x)
 
 
-def _softmax_attention(q, k, v, cfg, add_mask=None):
-    """softmax(q k^T (+mask)) v over the last two dims (video_transformer.py:28-32). q is already scaled."""
+def _softmax_attention(q, k, v, cfg, add_mask=None, drop=None):
+    """softmax(q k^T (+mask)) v over the last two dims (video_transformer.py:28-32). q is already scaled.
+    drop: multiplier (0 or 1 / (1 - p)) on the softmax weights = nn.functional.dropout with a given mask."""
     q, k, v = _ste(q, cfg), _ste(k, cfg), _ste(v, cfg)
     s = q @ k.transpose(-1, -2)
     if add_mask is not None:
         s = s + add_mask
     p = s.softmax(dim=-1)
+    if drop is not None:
+        p = p * drop
     return _ste(p, cfg) @ v
 
 
@@ -272,16 +275,21 @@ def video_tower(video, p, cfg, objects=None, prefix="video_model.", depth=None, 
 # ----------------------------------------------------------------------------------------------------------------
 # text tower (HF DistilBERT, call site model/oa_model.py:110-115)
 # ----------------------------------------------------------------------------------------------------------------
-def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model."):
-    """DistilBertModel forward in eval mode (dropout off): word + position embeddings, LN(1e-12); 6 post-LN blocks of
+def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model.", drop=None):
+    """DistilBertModel forward: word + position embeddings, LN(1e-12); 6 post-LN blocks of
     [q/k/v/out linears, softmax(q k^T / sqrt(d) + key-padding mask) v, LN(x + attn), lin2(GELU(lin1)), LN(x + ffn)].
-    Returns last_hidden_state (B, L, 768)."""
+    Returns last_hidden_state (B, L, 768). Eval mode unless `drop` is given: a dict site -> multiplier tensor (0 or
+    1 / (1 - p)) for DistilBERT's three dropout sites - 0: after the embedding LayerNorm (B, L, D); 1 + 3 i: softmax
+    weights of layer i (B, h, L, L); 2 + 3 i: FFN output of layer i before the residual add (B, L, D) - i.e.
+    nn.Dropout in training mode with the masks injected (the reference trains with text_model.train(), oa_model.py:28)."""
     B, L = input_ids.shape
     h = cfg.heads
     e = cfg.ln_eps_text
     x = p[prefix + "embeddings.word_embeddings.weight"][input_ids] + \
         p[prefix + "embeddings.position_embeddings.weight"][:L].unsqueeze(0)
     x = layer_norm(x, p[prefix + "embeddings.LayerNorm.weight"], p[prefix + "embeddings.LayerNorm.bias"], e)
+    if drop is not None and 0 in drop:
+        x = x * drop[0]
     D = x.shape[-1]
     d = D // h
     add_mask = None
@@ -297,11 +305,14 @@ def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model."):
         q = heads(linear(x, p[pre + "attention.q_lin.weight"], p[pre + "attention.q_lin.bias"], cfg, True)) * (d ** -0.5)
         k = heads(linear(x, p[pre + "attention.k_lin.weight"], p[pre + "attention.k_lin.bias"], cfg, True))
         v = heads(linear(x, p[pre + "attention.v_lin.weight"], p[pre + "attention.v_lin.bias"], cfg, True))
-        ctx = _ste(_softmax_attention(q, k, v, cfg, add_mask).permute(0, 2, 1, 3).reshape(B, L, D), cfg)  # stored bf16
+        dm = drop.get(1 + 3 * i) if drop is not None else None
+        ctx = _ste(_softmax_attention(q, k, v, cfg, add_mask, dm).permute(0, 2, 1, 3).reshape(B, L, D), cfg)  # stored bf16
         sa = linear(ctx, p[pre + "attention.out_lin.weight"], p[pre + "attention.out_lin.bias"], cfg, True)
         x = layer_norm(sa + x, p[pre + "sa_layer_norm.weight"], p[pre + "sa_layer_norm.bias"], e)
         f = linear(gelu(linear(x, p[pre + "ffn.lin1.weight"], p[pre + "ffn.lin1.bias"], cfg, True), cfg),
                    p[pre + "ffn.lin2.weight"], p[pre + "ffn.lin2.bias"], cfg, True)
+        if drop is not None and (2 + 3 * i) in drop:
+            f = f * drop[2 + 3 * i]
         x = layer_norm(f + x, p[pre + "output_layer_norm.weight"], p[pre + "output_layer_norm.bias"], e)
     return x
 
@@ -309,9 +320,9 @@ def distilbert(input_ids, attention_mask, p, cfg, prefix="text_model."):
 # ----------------------------------------------------------------------------------------------------------------
 # dual encoder, similarity, loss
 # ----------------------------------------------------------------------------------------------------------------
-def compute_text(text, p, cfg):
+def compute_text(text, p, cfg, drop=None):
     """FrozenInTime.compute_text (oa_model.py:106-123): last_hidden_state[:, 0] -> ReLU -> Linear(768, 256)."""
-    hid = distilbert(text["input_ids"], text.get("attention_mask"), p, cfg)[:, 0]
+    hid = distilbert(text["input_ids"], text.get("attention_mask"), p, cfg, drop=drop)[:, 0]
     return linear(F.relu(hid.float()), p["txt_proj.1.weight"], p["txt_proj.1.bias"], cfg, True)
 
 

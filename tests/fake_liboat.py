@@ -169,6 +169,49 @@ def layernorm_bwd(x, mean, rstd, gamma, *, dy_bf16=None, dy_f32=None, rows=None,
     _count(1)
 
 
+def dropout_mask(n, p, seed, site, device=None):
+    """Stand-in for the Philox draws: a torch generator seeded by (seed, site) - consistent inside the fake world."""
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + int(site)) % (2 ** 63))
+    return (torch.rand(n, generator=g) >= p).to(torch.uint8)
+
+
+def _mult(shape, p, seed, site):
+    n = 1
+    for d in shape:
+        n *= d
+    return dropout_mask(n, p, seed, site).view(shape).float() / (1.0 - p)
+
+
+def dropout_fwd(x, p, seed, site, *, residual=None, out=None, out_bf16=None, out_split3=None, rows=None):
+    v = x.float() * _mult(tuple(x.shape), p, seed, site)
+    if residual is not None:
+        v = v + residual
+    cols = x.shape[1]
+    if out is not None:
+        out.copy_(v)
+    if out_bf16 is not None:
+        out_bf16.copy_(v.to(BF))
+    if out_split3 is not None:
+        hi = v.to(BF)
+        out_split3[:, :cols], out_split3[:, cols:2 * cols], out_split3[:, 2 * cols:] = hi, hi, (v - hi.float()).to(BF)
+    _count(1)
+
+
+def dropout_bwd(p, seed, site, *, dy_f32=None, dy_bf16=None, dx_f32=None, dx_bf16=None):
+    ref = dy_f32 if dy_f32 is not None else dy_bf16
+    v = torch.zeros(ref.shape)
+    if dy_f32 is not None:
+        v = v + dy_f32
+    if dy_bf16 is not None:
+        v = v + dy_bf16.float()
+    v = v * _mult(tuple(ref.shape), p, seed, site)
+    if dx_f32 is not None:
+        dx_f32.copy_(v)
+    if dx_bf16 is not None:
+        dx_bf16.copy_(v.to(BF))
+    _count(1)
+
+
 def attn_core_work(mode, B, T, H, F, n):
     return (0.0, 0.0)
 
@@ -177,30 +220,31 @@ def attn_fwd_workspace_floats(mode, B, H, F, n=1):
     return 1
 
 
-def _attn(mode, B, T, H, F, n, q, k, v, key_mask):
+def _attn(mode, B, T, H, F, n, q, k, v, key_mask, dropout=None):
     cfg = O.OracleCfg(heads=H, bf16=True)
     if mode == MODE_PLAIN:
         add = None
         if key_mask is not None:
             add = torch.zeros(B, 1, 1, T)
             add.masked_fill_(key_mask.view(B, 1, 1, T) == 0, float("-inf"))
-        out = O._softmax_attention(q, k, v, cfg, add)                       # (B, H, T, d)
+        dm = _mult((B, H, T, T), dropout[0], dropout[1], dropout[2]) if dropout is not None else None
+        out = O._softmax_attention(q, k, v, cfg, add, dm)                   # (B, H, T, d)
         return out.permute(0, 2, 1, 3).reshape(B, T, H * 64)
     return O.divided_attention_core(q, k, v, "space" if mode == MODE_SPACE else "time", F, n, cfg)
 
 
-def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None):
+def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None, dropout=None):
     x = qkv.float().view(B, T, 3, H, 64)
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-    out.copy_(_attn(mode, B, T, H, F, n, q, k, v, key_mask).reshape(B * T, H * 64).to(BF))
+    out.copy_(_attn(mode, B, T, H, F, n, q, k, v, key_mask, dropout).reshape(B * T, H * 64).to(BF))
     _count(1)
 
 
-def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None):
+def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None):
     with torch.enable_grad():         # may run inside an autograd.Function.backward (grad mode off)
         x = qkv.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
         q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-        _attn(mode, B, T, H, F, n, q, k, v, key_mask).backward(dout.float().view(B, T, H * 64))
+        _attn(mode, B, T, H, F, n, q, k, v, key_mask, dropout).backward(dout.float().view(B, T, H * 64))
     g = x.grad.clone()
     g[:, :, 0] *= scale           # the q slot holds the scaled query: d/d(unscaled q) = scale * d/d(q)
     dqkv.copy_(g.reshape(B * T, 3 * H * 64).to(BF))

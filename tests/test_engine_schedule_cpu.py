@@ -149,3 +149,52 @@ def test_tower_gradients_alias_the_flat_book_and_still_accumulate(engine_on_fake
     out.sum().backward()
     for n, p in named:
         assert torch.allclose(p.grad, 2 * first[n], rtol=1e-6, atol=1e-8), n
+
+
+def _text_dropout_multipliers(ops_mod, B, L, D, H, layers, pd, pa, seed, device=None):
+    """site -> multiplier tensor, from the same draws the operator layer makes (ops.dropout_mask)."""
+    drop = {}
+    def mult(shape, p, site):
+        n = 1
+        for d in shape:
+            n *= d
+        return ops_mod.dropout_mask(n, p, seed, site, device).view(shape).float().cpu() / (1.0 - p)
+    drop[0] = mult((B, L, D), pd, 0)
+    for i in range(layers):
+        drop[1 + 3 * i] = mult((B, H, L, L), pa, 1 + 3 * i)
+        drop[2 + 3 * i] = mult((B, L, D), pd, 2 + 3 * i)
+    return drop
+
+
+def test_text_engine_training_dropout_schedule(engine_on_fake_ops):
+    """DistilBERT's training-mode dropout (embedding, attention weights, FFN output - the reference keeps
+    text_model.train(), model/oa_model.py:28) in the text schedule, forward and backward, vs the oracle with the SAME
+    masks injected."""
+    engine = engine_on_fake_ops
+    dim, heads, layers, B, L = 128, 2, 2, 3, 6
+    spec = text_tower_spec(layers=layers, dim=dim, hidden=256, vocab=50, max_pos=16)
+    spec["txt_proj.1.weight"], spec["txt_proj.1.bias"] = (32, dim), (32,)
+    w = fill_seeded(spec, 5, 0.05)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(1, 50, (B, L), generator=g)
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 4:] = 0
+    coef = torch.randn(B, 32, generator=g)
+    pd, pa, seed = 0.1, 0.1, 1234567
+    drop = _text_dropout_multipliers(fake_liboat, B, L, dim, heads, layers, pd, pa, seed)
+    p = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    cfg = O.OracleCfg(heads=heads, bf16=True, text_layers=layers)
+    ref = O.compute_text({"input_ids": ids, "attention_mask": mask}, p, cfg, drop=drop)
+    ref_eval = O.compute_text({"input_ids": ids, "attention_mask": mask}, w, cfg)
+    (ref * coef).sum().backward()
+    eng = engine.TextEngine(torch.device("cpu"), heads=heads)
+    params = {k: v.clone() for k, v in w.items()}
+    out = eng.forward(params, ids, mask, dropout={"p": pd, "p_attn": pa, "seed": seed})
+    assert rel(out, ref.detach()) < 1e-3 and rel(out, ref_eval.detach()) > 5e-2      # dropout really changes the output
+    named = [(k, torch.nn.Parameter(v)) for k, v in params.items()]
+    book = engine.GradBook(named, torch.device("cpu"))
+    eng.backward(params, book, coef.clone())
+    for name, ref_p in p.items():
+        if name.endswith("k_lin.bias") or ref_p.grad is None:
+            continue
+        assert rel(book[name], ref_p.grad) < 8e-2, (name, rel(book[name], ref_p.grad))

@@ -377,6 +377,61 @@ def test_train_dist_region_mem_entry_point_synthetic(tmp_path, monkeypatch):
     assert "txt_proj_2.1.weight" in ck["state_dict"] and "video_model.region_norm.weight" in ck["state_dict"]
 
 
+def test_text_tower_training_dropout_vs_oracle_with_same_masks():
+    """DistilBERT's dropout stays active in training (oa_model.py:28). Full-size text tower,
+    forward and backward, with the three dropout sites on, against the oracle given exactly the masks the kernels draw
+    (ops.dropout_mask); and model.eval() / model.train() switch it through the module surface."""
+    from oa_transformer_b200 import ops
+    from oa_transformer_b200.engine import TextEngine
+    from oa_transformer_b200.functional import run_tower
+    from oracle.weights import text_tower_spec
+    spec = text_tower_spec()
+    spec["txt_proj.1.weight"], spec["txt_proj.1.bias"] = (256, 768), (256,)
+    w = fill_seeded(spec, 51, 0.02)
+    g = torch.Generator().manual_seed(52)
+    B, L, H, D, layers = 4, 32, 12, 768, 6
+    text = O.synth_text(B, L, g, ragged=True)
+    coef = torch.randn(B, 256, generator=g)
+    pd, pa, seed = 0.1, 0.1, 20261017
+    drop = {}
+
+    def mult(shape, p, site):
+        n = 1
+        for d in shape:
+            n *= d
+        return ops.dropout_mask(n, p, seed, site, "cuda").view(shape).float().cpu() / (1.0 - p)
+    drop[0] = mult((B, L, D), pd, 0)
+    for i in range(layers):
+        drop[1 + 3 * i] = mult((B, H, L, L), pa, 1 + 3 * i)
+        drop[2 + 3 * i] = mult((B, L, D), pd, 2 + 3 * i)
+
+    def oracle_run(cfg, d):
+        p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in w.items()}
+        te = O.compute_text(text, p, cfg, drop=d)
+        (te * coef).sum().backward()
+        return te.detach(), {k: v.grad for k, v in p.items() if v.is_floating_point() and v.grad is not None}
+
+    t16, g16 = oracle_run(O.OracleCfg(bf16=True), drop)
+    t32, g32 = oracle_run(O.OracleCfg(), drop)
+    t_eval, _ = oracle_run(O.OracleCfg(), None)
+    dev = torch.device("cuda")
+    params = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in w.items()}
+    named = [(k, v) for k, v in params.items() if v.is_floating_point()]
+    te = run_tower(TextEngine(dev, heads=H), named, input_ids=text["input_ids"].to(dev),
+                   attention_mask=text["attention_mask"].to(dev), dropout={"p": pd, "p_attn": pa, "seed": seed})
+    (te * coef.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    grads = {k: v.grad.detach().cpu() for k, v in params.items() if v.is_floating_point() and v.grad is not None}
+    out = te.detach().cpu()
+    assert rel(out, t32) < 2e-3 and rel(out, t16) < 2e-3, (rel(out, t32), rel(out, t16))
+    assert rel(t32, t_eval) > 5e-2                       # the masks matter: training output != eval output
+    floor = summarize("noise_floor_text_dropout", out, t16, 0.0, 0.0, g16, g32)
+    rep32 = summarize("text_dropout_vs_fp32_oracle", out, t32, 0.0, 0.0, grads, g32)
+    rep16 = summarize("text_dropout_vs_bf16_oracle", out, t16, 0.0, 0.0, grads, g16)
+    gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
+    assert not rep32["missing"]
+
+
 def test_frozen_in_time_module_surface():
     """The nn.Module mirror: constructor, forward(data) -> (text, video) embeddings, backward into .grad."""
     from oa_transformer_b200.model import FrozenInTime, NormSoftmaxLoss, sim_matrix
@@ -397,6 +452,17 @@ def test_frozen_in_time_module_surface():
     with torch.no_grad():
         s = m(data, return_embeds=False)
     assert s.shape == (2, 2)
+    # training mode keeps DistilBERT's dropout on (oa_model.py:28): two calls differ, the video tower (no dropout) does
+    # not; eval() makes the text embeddings deterministic again
+    with torch.no_grad():
+        t1, v1 = m(data)
+        t2, v2 = m(data)
+        assert not torch.equal(t1, t2) and torch.equal(v1, v2)
+        m.eval()
+        t3, _ = m(data)
+        t4, _ = m(data)
+        assert torch.equal(t3, t4)
+        m.train()
 
 
 def test_train_dist_multi_entry_point_synthetic(tmp_path, monkeypatch):

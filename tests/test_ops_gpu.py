@@ -519,6 +519,85 @@ def test_token_pool_bce_and_linear_heads_vs_torch():
         assert rel(a.grad.cpu(), r_.grad) < 6e-3, (name, rel(a.grad.cpu(), r_.grad))
 
 
+def test_dropout_draws_statistics_and_elementwise_kernels():
+    """Philox dropout (include/oat.h): keep rate and independence of the draws over sites / seeds, and the forward /
+    backward element kernels against the exported mask (exact)."""
+    from oa_transformer_b200 import ops
+    n, p = 1 << 20, 0.1
+    keeps = {}
+    for seed in (1, 2, 987654321012345):
+        for site in (0, 1, 7):
+            k = ops.dropout_mask(n, p, seed, site, "cuda").float()
+            keeps[(seed, site)] = k
+            rate = float(k.mean())
+            assert abs(rate - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5, (seed, site, rate)       # 5 sigma
+            # no structure along the index: lag-1 / lag-4 / lag-768 autocorrelation of the keep flags ~ 0
+            c = k - k.mean()
+            for lag in (1, 4, 768):
+                assert abs(float((c[:-lag] * c[lag:]).mean()) / float(c.var())) < 6e-3, (seed, site, lag)
+    a, b, c = keeps[(1, 0)], keeps[(2, 0)], keeps[(1, 1)]
+    for x, y in ((a, b), (a, c)):       # different seed / different site: independent masks
+        agree = float((x == y).float().mean())
+        assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 3e-3, agree
+    assert torch.equal(ops.dropout_mask(n, p, 1, 0, "cuda").float(), a)         # same triple, same draws
+    rows, cols, seed, site = 37, 768, 42, 5
+    g = gen(41)
+    x = torch.randn(rows, cols, generator=g).cuda()
+    res = torch.randn(rows, cols, generator=g).cuda()
+    m = ops.dropout_mask(rows * cols, p, seed, site, "cuda").view(rows, cols).float() / (1 - p)
+    out = torch.empty_like(x)
+    out16 = torch.empty(rows, cols, device="cuda", dtype=BF)
+    out3 = torch.empty(rows, 3 * cols, device="cuda", dtype=BF)
+    ops.dropout_fwd(x, p, seed, site, residual=res, out=out, out_bf16=out16, out_split3=out3)
+    ref = x * m + res
+    assert torch.equal(out, ref) and torch.equal(out16, ref.to(BF))
+    hi, lo = _split_ref(ref)
+    assert torch.equal(out3[:, :cols], hi) and torch.equal(out3[:, cols:2 * cols], hi) and torch.equal(out3[:, 2 * cols:], lo)
+    dy32 = torch.randn(rows, cols, generator=g).cuda()
+    dy16 = torch.randn(rows, cols, generator=g).to(BF).cuda()
+    dx32 = torch.empty_like(x)
+    dx16 = torch.empty(rows, cols, device="cuda", dtype=BF)
+    ops.dropout_bwd(p, seed, site, dy_f32=dy32, dy_bf16=dy16, dx_f32=dx32, dx_bf16=dx16)
+    assert torch.equal(dx32, (dy32 + dy16.float()) * m) and torch.equal(dx16, ((dy32 + dy16.float()) * m).to(BF))
+
+
+def test_text_attention_weight_dropout_vs_oracle_with_same_mask():
+    """mode 2 attention with dropout on the softmax weights (HF DistilBERT attention_dropout): forward and backward against
+    the oracle given the multiplier built from the exported draws of the same (seed, site)."""
+    from oa_transformer_b200 import ops
+    B, L, H, p, seed, site = 3, 32, 4, 0.1, 77, 4
+    T = L
+    qkv16 = _qkv(B, T, H, 5)
+    dout16 = torch.randn(B, T, H * 64, generator=gen(6)).to(BF)
+    key_mask = torch.ones(B, L, dtype=torch.long)
+    key_mask[1, 20:] = 0
+    qkv = qkv16.reshape(B * T, 3 * H * 64).cuda()
+    out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
+    lse = torch.zeros(B * H * T, device="cuda")
+    km = key_mask.to(torch.int32).cuda().contiguous()
+    ops.attn_fwd(ops.MODE_PLAIN, B, T, H, 0, 0, qkv, out, lse, km, dropout=(p, seed, site))
+    dqkv = torch.zeros_like(qkv)
+    ops.attn_bwd(ops.MODE_PLAIN, B, T, H, 0, 0, qkv, out, lse, dout16.reshape(B * T, H * 64).cuda(), dqkv, 0.125, None, km,
+                 dropout=(p, seed, site))
+    mult = ops.dropout_mask(B * H * T * T, p, seed, site, "cuda").view(B, H, T, T).float().cpu() / (1 - p)
+    x = qkv16.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    add = torch.zeros(B, 1, 1, T).masked_fill(key_mask.view(B, 1, 1, T) == 0, float("-inf"))
+    ref = O._softmax_attention(q, k, v, O.OracleCfg(heads=H, bf16=True), add, mult).permute(0, 2, 1, 3).reshape(B, T, H * 64)
+    ref.backward(dout16.float())
+    gref = x.grad.clone()
+    gref[:, :, 0] *= 0.125
+    o = out.cpu().float().view(B, T, H * 64)
+    valid = key_mask.bool()
+    assert rel(o[valid], ref.detach()[valid]) < 6e-3
+    dq = dqkv.cpu().float().view(B, T, 3, H, 64)
+    assert rel(dq[valid], gref[valid]) < 1.2e-2, rel(dq[valid], gref[valid])
+    # and it differs from the no-dropout result by the expected amount (sqrt(p / (1 - p)) relative noise on the weights)
+    out0 = torch.zeros_like(out)
+    ops.attn_fwd(ops.MODE_PLAIN, B, T, H, 0, 0, qkv, out0, lse, km)
+    assert rel(o[valid], out0.cpu().float().view(B, T, H * 64)[valid]) > 2e-2
+
+
 def test_device_prefetcher_stages_batches_in_order():
     from oa_transformer_b200.data_loader import DevicePrefetcher
     host = [{"video": torch.full((2, 3, 8), float(i)).pin_memory(),
