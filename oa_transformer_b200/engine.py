@@ -32,6 +32,40 @@ OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
+GRAPH = os.environ.get("OAT_GRAPH", "1") != "0"               # replay the video tower's forward / backward as CUDA graphs
+MAX_GRAPHS = 8
+
+
+class _GraphedSchedule:
+    """CUDA-graph replay of one schedule (the video tower's forward or backward: ~190 / ~280 launches whose arguments do
+    not change from step to step because every activation lives in a name-keyed buffer). First call with a given key
+    runs eagerly (lazy initialisation, buffer allocation), the second is captured, later ones replay. The key carries
+    everything a captured kernel argument depends on: input addresses and shapes, the parameter storage, the flags.
+    Kernels inside a replayed graph are still counted in ops.LAUNCHES (they do launch on the device)."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def run(self, key, fn):
+        """fn() -> result (tensors living in static buffers). Returns (result, replayed)."""
+        e = self.entries.get(key)
+        if e is None:
+            if len(self.entries) >= MAX_GRAPHS:          # too many distinct input addresses: stay eager for new ones
+                return fn(), False
+            self.entries[key] = {"graph": None}
+            return fn(), False
+        if e["graph"] is None:
+            n0 = ops.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e["result"] = fn()
+            e["launches"] = ops.LAUNCHES - n0
+            e["graph"] = g
+            ops.LAUNCHES = n0                              # capture enqueued nothing; the replay below does the work
+        e["graph"].replay()
+        ops._count(e["launches"])
+        ops.GRAPH_REPLAYS += 1
+        return e["result"], True
 
 
 class _Buffers:
@@ -142,8 +176,33 @@ class VideoEngine:
         self._plan = ops.CastPlan()
 
     # ------------------------------------------------------------------ forward
+    def _fingerprint(self, p):
+        return hash(tuple(v.data_ptr() for v in p.values()))
+
     def forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
                 save=True, tokens=None, region_layer=6):
+        """See _forward. With OAT_GRAPH (default) a training forward of a repeating shape is replayed as a CUDA graph."""
+        graphable = (GRAPH and save and tokens is None and ops.PROFILE is None and video.is_cuda
+                     and getattr(self, "layer_grad_hook", None) is None and not torch.cuda.is_current_stream_capturing())
+        if not graphable:
+            return self._forward(p, video, objects, proj, prefix, save, tokens, region_layer)
+        video = video.contiguous()
+        objects = None if objects is None else objects.contiguous()
+        key = ("fwd", video.data_ptr(), tuple(video.shape), None if objects is None else objects.data_ptr(),
+               None if objects is None else tuple(objects.shape), proj, prefix, SPLIT, self._fingerprint(p))
+        box = {}
+
+        def fn():
+            out = self._forward(p, video, objects, proj, prefix, True, None, region_layer)
+            box["saved"] = self.saved
+            return out, self.saved
+        (out, saved), replayed = self._graphs_fwd.run(key, fn)
+        self.saved = saved
+        self._saved_key = key if replayed else None
+        return out.clone() if replayed else out
+
+    def _forward(self, p, video, objects=None, proj=("vid_proj.0.weight", "vid_proj.0.bias"), prefix="video_model.",
+                 save=True, tokens=None, region_layer=6):
         """p: dict name -> fp32 parameter tensor. video fp32 (B,F,3,H,W); objects fp32 (B,F,O,2054) or None.
         Returns projected CLS embeddings fp32 (B, P).
         tokens="final": also returns the final LayerNorm of EVERY token row, fp32 (B, T, D) - forward_features'
@@ -329,10 +388,25 @@ class VideoEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, p, grads, dout, dtokens=None):
+        """See _backward. Replayed as a CUDA graph when the forward it belongs to was (same shapes, same buffers)."""
+        graphable = (GRAPH and dtokens is None and ops.PROFILE is None and dout.is_cuda and self._saved_key is not None
+                     and hasattr(grads, "flat") and getattr(self, "layer_grad_hook", None) is None
+                     and not torch.cuda.is_current_stream_capturing())
+        if not graphable:
+            return self._backward(p, grads, dout, dtokens)
+        static = self.bufs.get("graph.dout", tuple(dout.shape), F32)
+        static.copy_(dout)
+        # every forward graph of one shape shares the activation buffers, so one backward graph serves them all
+        key = ("bwd", self._saved_key[2], self._saved_key[4], self._saved_key[5:], grads.flat.data_ptr(), tuple(dout.shape),
+               SIDE_STREAM)
+        saved = self.saved
+        self._graphs_bwd.run(key, lambda: self._backward(p, grads, static, None, saved))
+
+    def _backward(self, p, grads, dout, dtokens=None, saved=None):
         """dout: fp32 (B, P) gradient of the projected embeddings; dtokens: fp32 (B, T, D) gradient of the token
         features returned with tokens="final" / "region" (None: unused). Fills `grads` (GradBook-like: name -> fp32
         view, pre-zeroed) with every parameter gradient."""
-        S = self.saved
+        S = self.saved if saved is None else saved
         assert S is not None, "backward without a saved forward"
         bufs = self.bufs
         B, Fr, N, O, n, T, M, D, depth = (S[k] for k in ("B", "Fr", "N", "O", "n", "T", "M", "D", "depth"))

@@ -14,6 +14,7 @@ ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
 
 # Kernel-launch accounting (bench.py reports it) and an optional per-launch CUDA-event profiler for the roofline lines.
 LAUNCHES = 0
+GRAPH_REPLAYS = 0   # CUDA-graph replays of whole schedules (engine._GraphedSchedule); their kernels are counted in LAUNCHES
 PROFILE = None      # when a list: (kind, work, start_event, end_event) is appended around every profiled launch
 
 

@@ -11,6 +11,7 @@ from oracle import oracle as O
 ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
 MODE_SPACE, MODE_TIME, MODE_PLAIN = 0, 1, 2
 LAUNCHES = 0
+GRAPH_REPLAYS = 0
 PROFILE = None
 BF = torch.bfloat16
 

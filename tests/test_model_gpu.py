@@ -294,7 +294,7 @@ def test_region_variant_vs_reference_golden():
     from oa_transformer_b200.trainer.trainer_region_mem import region_loss
     g = torch.load(os.path.join(GOLD, "region_small.pt"), map_location="cpu", weights_only=False)
     m, w = _region_model(g)
-    m.train()
+    m.eval()            # the fixture was generated with the reference in eval mode (DistilBERT dropout off)
     data = {"video": g["video"].cuda(), "text": {"input_ids": g["input_ids"].cuda(),
                                                   "attention_mask": g["attention_mask"].cuda()},
             "text_region_embedding": g["text_region_embedding"].cuda(), "patch_masks": g["patch_masks"].cuda()}
@@ -386,12 +386,13 @@ def test_text_tower_training_dropout_vs_oracle_with_same_masks():
     from oa_transformer_b200.functional import run_tower
     from oracle.weights import text_tower_spec
     spec = text_tower_spec()
-    spec["txt_proj.1.weight"], spec["txt_proj.1.bias"] = (256, 768), (256,)
     w = fill_seeded(spec, 51, 0.02)
     g = torch.Generator().manual_seed(52)
     B, L, H, D, layers = 4, 32, 12, 768, 6
     text = O.synth_text(B, L, g, ragged=True)
-    coef = torch.randn(B, 256, generator=g)
+    # the tower's own output (last_hidden_state[:, 0]) under a linear loss: the ReLU of txt_proj would add its mask-flip
+    # noise (see the config-shaped test below) to what this test is about
+    coef = torch.randn(B, D, generator=g)
     pd, pa, seed = 0.1, 0.1, 20261017
     drop = {}
 
@@ -407,7 +408,7 @@ def test_text_tower_training_dropout_vs_oracle_with_same_masks():
 
     def oracle_run(cfg, d):
         p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in w.items()}
-        te = O.compute_text(text, p, cfg, drop=d)
+        te = O.distilbert(text["input_ids"], text["attention_mask"], p, cfg, drop=d)[:, 0]
         (te * coef).sum().backward()
         return te.detach(), {k: v.grad for k, v in p.items() if v.is_floating_point() and v.grad is not None}
 
@@ -418,7 +419,8 @@ def test_text_tower_training_dropout_vs_oracle_with_same_masks():
     params = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in w.items()}
     named = [(k, v) for k, v in params.items() if v.is_floating_point()]
     te = run_tower(TextEngine(dev, heads=H), named, input_ids=text["input_ids"].to(dev),
-                   attention_mask=text["attention_mask"].to(dev), dropout={"p": pd, "p_attn": pa, "seed": seed})
+                   attention_mask=text["attention_mask"].to(dev), dropout={"p": pd, "p_attn": pa, "seed": seed},
+                   proj=None)
     (te * coef.to(dev)).sum().backward()
     torch.cuda.synchronize()
     grads = {k: v.grad.detach().cpu() for k, v in params.items() if v.is_floating_point() and v.grad is not None}
@@ -430,6 +432,65 @@ def test_text_tower_training_dropout_vs_oracle_with_same_masks():
     rep16 = summarize("text_dropout_vs_bf16_oracle", out, t16, 0.0, 0.0, grads, g16)
     gate_grads(floor, vs_truth=rep32, vs_bf16_oracle=rep16)
     assert not rep32["missing"]
+
+
+def test_video_tower_cuda_graph_replay_matches_eager(monkeypatch):
+    """engine._GraphedSchedule: the video tower's forward and backward replayed as CUDA graphs (third call on) give what
+    the eager launches give (first call), with new input values copied into the same tensors and updated weights."""
+    from oa_transformer_b200 import engine, ops
+    from oa_transformer_b200.functional import run_tower
+    from oracle.weights import video_tower_spec
+    monkeypatch.setattr(engine, "GRAPH", True)
+    spec = video_tower_spec(depth=2, frames=4, objects=True)
+    spec["vid_proj.0.weight"], spec["vid_proj.0.bias"] = (256, 768), (256,)
+    w = fill_seeded(spec, 61, 0.02)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(62)
+    B, Fr, Oo = 2, 4, 36
+    vids = [torch.randn(B, Fr, 3, 224, 224, generator=g) for _ in range(2)]
+    objs = [O.synth_objects(B, Fr, Oo, g) for _ in range(2)]
+    coef = torch.randn(B, 256, generator=g).to(dev)
+
+    def run(eng, params, video, objects):
+        for p in params.values():
+            p.grad = None
+        named = list(params.items())
+        ve = run_tower(eng, named, video=video, objects=objects)
+        (ve * coef).sum().backward()
+        torch.cuda.synchronize()
+        return ve.detach().clone(), {k: v.grad.detach().clone() for k, v in params.items()}
+
+    def fresh():
+        return {k: v.to(dev).clone().requires_grad_(True) for k, v in w.items()}
+
+    # reference: eager engine (graphs off), the two inputs, and a weight update in between
+    monkeypatch.setattr(engine, "GRAPH", False)
+    eng0, p0 = engine.VideoEngine(dev, heads=12), fresh()
+    ref = []
+    for i in range(2):
+        ref.append(run(eng0, p0, vids[i].to(dev), objs[i].to(dev)))
+        with torch.no_grad():
+            for v in p0.values():
+                v.mul_(1.01)
+    monkeypatch.setattr(engine, "GRAPH", True)
+    eng1, p1 = engine.VideoEngine(dev, heads=12), fresh()
+    vbuf, obuf = vids[0].to(dev), objs[0].to(dev)
+    run(eng1, p1, vbuf, obuf)                    # 1st call: eager
+    run(eng1, p1, vbuf, obuf)                    # 2nd call: captured + replayed
+    n_replays = ops.GRAPH_REPLAYS
+    got = []
+    for i in range(2):                           # later calls: replays, inputs refreshed in place, weights updated in place
+        vbuf.copy_(vids[i])
+        obuf.copy_(objs[i])
+        got.append(run(eng1, p1, vbuf, obuf))
+        with torch.no_grad():
+            for v in p1.values():
+                v.mul_(1.01)
+    assert ops.GRAPH_REPLAYS - n_replays == 4            # forward + backward of both steps were graph replays
+    for (ve_r, g_r), (ve_g, g_g) in zip(ref, got):
+        assert rel(ve_g, ve_r) < 2e-3                    # split-K reductions: equal to rounding, not bit for bit
+        for k in g_r:
+            assert rel(g_g[k], g_r[k]) < 2e-2, (k, rel(g_g[k], g_r[k]))
 
 
 def test_frozen_in_time_module_surface():
@@ -457,7 +518,8 @@ def test_frozen_in_time_module_surface():
     with torch.no_grad():
         t1, v1 = m(data)
         t2, v2 = m(data)
-        assert not torch.equal(t1, t2) and torch.equal(v1, v2)
+        # (the video tower has no dropout; its split-K reductions make it reproducible to rounding, not bit for bit)
+        assert float((t1 - t2).abs().max()) > 1e-2 and float((v1 - v2).abs().max()) < 5e-3
         m.eval()
         t3, _ = m(data)
         t4, _ = m(data)
