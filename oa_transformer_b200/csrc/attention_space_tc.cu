@@ -198,25 +198,48 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
       mbar_wait(&s_full[j], par);
       tc_fence_after();
       uint32_t v[32];
-      // pass 1: row maximum
-      float mx = -INFINITY;
+      // ONE pass over the score row. Reading S out of TMEM is what bounds this kernel (64 B/clk per SM: a 128 x 240 fp32
+      // tile costs ~1.9 k clk per pass), so the row maximum is not found in a pass of its own: chunk by chunk (32 keys),
+      // p = 2^(s*log2e - m2) against a running reference m2 that starts as the maximum of the first chunk and is only
+      // moved when a later chunk exceeds it by more than 2^8 (then the few P chunks already written are re-scaled in
+      // TMEM - rare, and exact: softmax is shift-invariant and bf16 / fp32 carry the exponent). P never exceeds 2^8.
+      float m2 = -INFINITY, sum = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         ld32_wait(t_row + c * 32, v);
+        float cm = -INFINITY;
         if (c < NCH - 1) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) cm = fmaxf(cm, __uint_as_float(v[e]));
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c * 32 + e < limit) ? __uint_as_float(v[e]) : -INFINITY);
+          for (int e = 0; e < 32; ++e) cm = fmaxf(cm, (c * 32 + e < limit) ? __uint_as_float(v[e]) : -INFINITY);
         }
-      }
-      const float m2 = mx * kLog2e;
-      // pass 2: p = 2^(s*log2e - m2), row sum, P (bf16) back into TMEM over the S columns already consumed
-      float sum = 0.f;
+        const float cm2 = cm * kLog2e;
+        if (c == 0) {
+          m2 = cm2;
+        } else {
+          const bool need = cm2 > m2 + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m2n = need ? cm2 : m2;
+            const float sc = ex2_approx(m2 - m2n);          // exactly 1 for the rows that keep their reference
+            sum *= sc;
+            tmem_st_wait();
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        ld32_wait(t_row + c * 32, v);
+            for (int cc = 0; cc < c; ++cc) {
+              uint32_t old[16];
+              tmem_ld_32x32b_x16(t_row + cc * 16, old);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float2 f = unpack_bf16x2(old[e]);
+                old[e] = pack_bf16x2(f.x * sc, f.y * sc);
+              }
+              tmem_st_32x32b_x16(t_row + cc * 16, old);
+            }
+            m2 = m2n;
+          }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {

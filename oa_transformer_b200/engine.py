@@ -174,6 +174,9 @@ class VideoEngine:
         self.saved = None
         self._side = None
         self._plan = ops.CastPlan()
+        self._graphs_fwd = _GraphedSchedule()
+        self._graphs_bwd = _GraphedSchedule()
+        self._saved_key = None
 
     # ------------------------------------------------------------------ forward
     def _fingerprint(self, p):

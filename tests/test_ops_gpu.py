@@ -283,6 +283,47 @@ def test_space_attention_tcgen05_fwd(B, F, n, H):
     assert (l_tc - l_old).abs().max() < 2e-3, (l_tc - l_old).abs().max()
 
 
+@pytest.mark.parametrize("late", ["ramp", "spike", "cls"])
+def test_space_attention_single_pass_softmax_reference_moves(late):
+    """The forward softmax runs ONE pass over each score row with a running reference (first-chunk maximum, moved only
+    when a later 32-key chunk exceeds it by > 2^8, re-scaling the P chunks already in TMEM). Rows whose large scores come
+    late - a ramp over the keys, a single spike in the last chunk, a dominant CLS key (the LAST key column) - force that
+    path; the result must still be the exact softmax, and backward (which recomputes P from the saved log-sum-exp) must
+    agree with it."""
+    from oa_transformer_b200 import ops
+    B, F, n, H = 2, 2, 232, 2
+    T = 1 + F * n
+    g = gen(21)
+    x = torch.randn(B, T, 3, H, 64, generator=g)
+    x[:, :, 0] *= 0.125
+    k = x[:, :, 1]
+    if late == "ramp":            # key norms grow along the frame: every chunk raises the maximum by far more than 2^8
+        ramp = torch.linspace(0.2, 6.0, n).repeat(F)
+        k[:, 1:] *= ramp.view(1, -1, 1, 1)
+        x[:, :, 0] *= 4.0
+    elif late == "spike":         # one key near the end of every frame aligned with every query direction
+        x[:, :, 0] = x[:, :, 0].abs() * 2.0
+        k[:, 1:].view(B, F, n, H, 64)[:, :, n - 3] = 3.0
+    else:                         # the CLS key (read as the last key column by the kernel) dominates
+        x[:, :, 0] = x[:, :, 0].abs() * 2.0
+        k[:, 0] = 4.0
+    qkv16 = x.to(BF)
+    dout16 = torch.randn(B, T, H * 64, generator=g).to(BF)
+    out, dqkv = _run_attn(ops.MODE_SPACE, B, F, n, H, qkv16, dout16)
+    cfg = O.OracleCfg(heads=H, bf16=True)
+    xr = qkv16.float().requires_grad_(True)
+    q, kk, v = (xr[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s_max = float((q[:, :, 1:2] @ kk.transpose(-1, -2)).abs().max())
+    assert s_max > 30.0, s_max                       # the scenario really spans far more than 2^8 in the exponent
+    ref = O.divided_attention_core(q, kk, v, "space", F, n, cfg)
+    ref.backward(dout16.float())
+    gref = xr.grad.clone()
+    gref[:, :, 0] *= 0.125
+    assert torch.isfinite(out).all() and rel(out, ref.detach()) < 5e-3, rel(out, ref.detach())
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, :, i], gref[:, :, i]) < 1e-2, (name, rel(dqkv[:, :, i], gref[:, :, i]))
+
+
 @pytest.mark.parametrize("B,L,H", [(3, 32, 12), (2, 8, 2), (2, 50, 2)])
 def test_text_attention_with_padding_mask(B, L, H):
     from oa_transformer_b200 import ops
