@@ -32,7 +32,10 @@ OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
-GRAPH = os.environ.get("OAT_GRAPH", "1") != "0"               # replay the video tower's forward / backward as CUDA graphs
+# Replay the video tower's forward / backward as CUDA graphs. Off by default: measured 529 vs 540 pairs/s (graph / eager)
+# on the benchmark step - the step is GPU-bound and the host already runs 3x ahead of the device, so there is no launch
+# gap to reclaim; worth turning on when the host is the slower side (small batches, busy hosts).
+GRAPH = os.environ.get("OAT_GRAPH", "0") != "0"
 MAX_GRAPHS = 8
 
 
