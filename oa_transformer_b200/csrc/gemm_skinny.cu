@@ -1,0 +1,188 @@
+// Skinny GEMM: C[M <= 64, N] = A(M,K) . B(N,K)^T, both operands K-major bf16, fp32 accumulate - the few-row products
+// of the path: the split-bf16 CLS rows of the video tower ([B, 3K] x [N, 3K], engine.py), the two projections
+// (oa_model.py:68-75: [B, 768] -> [B, 256]) and their input gradients.
+//
+// With M = batch rows the contraction is a weight STREAM ([N, K] read once, <= 64 output rows): the 128-row tcgen05 tile
+// would leave a handful of CTAs pulling the whole weight through one SM each (or need split-K with floating-point
+// atomics). Here every CTA owns 16 output columns over the full K: N/16 CTAs stream their 16 weight rows with cp.async
+// (128-column chunks, double-buffered), warp w multiplies rows [16w, 16w+16) on bf16 mma.sync m16n8k16, and the fused
+// epilogue of oat_gemm_bf16 (alpha, bias, column scale, GELU + derivative / x aux / ReLU, fp32 residual, accumulate)
+// is applied to the fragments. One owner per output element and a fixed k order: bit-reproducible, no atomics.
+#include "oat_host.h"
+#include "oat_ptx.cuh"
+
+namespace oat {
+
+namespace {
+
+constexpr int kSkM = 64;          // rows per CTA (4 warps x 16)
+constexpr int kSkN = 16;          // columns per CTA
+constexpr int kSkK = 128;         // k chunk
+constexpr int kSkPitch = kSkK + 8;                // bf16 elements: 272-byte rows keep ldmatrix conflict-free
+constexpr int kSkStage = (kSkM + kSkN) * kSkPitch;    // elements per stage
+
+__device__ __forceinline__ void sk_cp16(uint32_t smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void sk_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sk_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sk_ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sk_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct SkinnyParams {
+  const __nv_bfloat16* A; long long lda;
+  const __nv_bfloat16* B; long long ldb;
+  int M, N, K;
+  float alpha;
+  const float* bias;
+  int scale_cols; float scale;
+  int act;
+  const __nv_bfloat16* aux; long long ld_aux;
+  const float* residual; long long ldr;
+  float* out_f32; long long ld_f32;
+  __nv_bfloat16* out_bf16; long long ld_bf16;
+  __nv_bfloat16* out2; long long ld2;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyParams p) {
+  extern __shared__ __align__(16) __nv_bfloat16 sk_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * kSkN;
+  const int chunks = (p.K + kSkK - 1) / kSkK;
+
+  auto stage = [&](int c, int s) {
+    __nv_bfloat16* As = sk_smem + s * kSkStage;
+    __nv_bfloat16* Bs = As + kSkM * kSkPitch;
+    const int k0 = c * kSkK;
+    // (64 + 16) rows x 16 vectors of 8 bf16
+    for (int idx = tid; idx < (kSkM + kSkN) * (kSkK / 8); idx += 128) {
+      const int r = idx / (kSkK / 8), v = idx - r * (kSkK / 8);
+      const int k = k0 + v * 8;
+      const bool is_a = r < kSkM;
+      const int row = is_a ? r : n0 + (r - kSkM);
+      __nv_bfloat16* dst = (is_a ? As + r * kSkPitch : Bs + (r - kSkM) * kSkPitch) + v * 8;
+      const bool ok = k < p.K && (is_a ? row < p.M : row < p.N);
+      if (ok) {
+        sk_cp16(smem_u32(dst), (is_a ? p.A + static_cast<long long>(row) * p.lda : p.B + static_cast<long long>(row) * p.ldb) + k);
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  stage(0, 0);
+  sk_commit();
+  for (int c = 0; c < chunks; ++c) {
+    const int s = c & 1;
+    if (c + 1 < chunks) stage(c + 1, s ^ 1);
+    sk_commit();
+    sk_wait<1>();
+    __syncthreads();
+    if (warp * 16 < p.M) {
+      const uint32_t a_base = smem_u32(sk_smem + s * kSkStage);
+      const uint32_t b_base = a_base + kSkM * kSkPitch * 2;
+#pragma unroll
+      for (int ks = 0; ks < kSkK / 16; ++ks) {
+        uint32_t a[4], b[4];
+        sk_ldsm4(a_base + ((warp * 16 + (lane & 15)) * kSkPitch + ks * 16 + (lane >> 4) * 8) * 2, a);
+        // B rows = output columns: matrices (n 0-7, k lo), (n 0-7, k hi), (n 8-15, k lo), (n 8-15, k hi)
+        sk_ldsm4(b_base + (((lane & 7) + ((lane >> 4) << 3)) * kSkPitch + ks * 16 + ((lane >> 3) & 1) * 8) * 2, b);
+        sk_mma(acc[0], a, b[0], b[1]);
+        sk_mma(acc[1], a, b[2], b[3]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue on the fragments: lane (g, t) holds rows g / g+8 and columns 2t, 2t+1 of each 8-column tile
+  if (warp * 16 >= p.M) return;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int col = n0 + nt * 8 + 2 * t;
+    if (col >= p.N) continue;                    // N is a multiple of 4 and col is even: col + 1 < N as well
+    float b0 = 0.f, b1 = 0.f;
+    if (p.bias != nullptr) { b0 = p.bias[col]; b1 = p.bias[col + 1]; }
+    const float sc = col < p.scale_cols ? p.scale : 1.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = warp * 16 + g + half * 8;
+      if (row >= p.M) continue;
+      float x0 = (acc[nt][2 * half] * p.alpha + b0) * sc, x1 = (acc[nt][2 * half + 1] * p.alpha + b1) * sc;
+      if (p.act == 1) {
+        float d0, d1;
+        gelu_fwd_grad(x0, x0, d0);
+        gelu_fwd_grad(x1, x1, d1);
+        *reinterpret_cast<uint32_t*>(p.out2 + static_cast<long long>(row) * p.ld2 + col) = pack_bf16x2(d0, d1);
+      } else if (p.act == 2) {
+        const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.aux + static_cast<long long>(row) * p.ld_aux + col));
+        x0 *= a.x; x1 *= a.y;
+      } else if (p.act == 3) {
+        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f);
+      }
+      if (p.residual != nullptr) {
+        const float2 r = *reinterpret_cast<const float2*>(p.residual + static_cast<long long>(row) * p.ldr + col);
+        x0 += r.x; x1 += r.y;
+      }
+      if (p.out_f32 != nullptr) {
+        float2* o = reinterpret_cast<float2*>(p.out_f32 + static_cast<long long>(row) * p.ld_f32 + col);
+        if (p.accumulate) { const float2 old = *o; x0 += old.x; x1 += old.y; }
+        *o = make_float2(x0, x1);
+      }
+      if (p.out_bf16 != nullptr)
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + static_cast<long long>(row) * p.ld_bf16 + col) = pack_bf16x2(x0, x1);
+    }
+  }
+}
+
+}  // namespace
+
+// K-major x K-major problems with at most 64 rows whose tensors allow the vector accesses above.
+bool skinny_gemm_supported(const oat_gemm_args* a) {
+  if (a->M > kSkM || a->a_major != 0 || a->b_major != 0) return false;
+  if (a->K % 8 != 0 || a->lda % 8 != 0 || a->ldb % 8 != 0 || a->N % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->B) & 15) != 0) return false;
+  if (a->accumulate && a->out_bf16 != nullptr) return false;
+  auto even = [](const void* p, long long ld, int esz) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % (2 * esz)) == 0 && ld % 2 == 0); };
+  return even(a->out_f32, a->ld_f32, 4) && even(a->residual, a->ldr, 4) && even(a->out_bf16, a->ld_bf16, 2) &&
+         even(a->out2_bf16, a->ld2, 2) && even(a->aux_bf16, a->ld_aux, 2);
+}
+
+int launch_skinny_gemm(const oat_gemm_args* a, cudaStream_t stream) {
+  SkinnyParams p;
+  p.A = reinterpret_cast<const __nv_bfloat16*>(a->A); p.lda = a->lda;
+  p.B = reinterpret_cast<const __nv_bfloat16*>(a->B); p.ldb = a->ldb;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.alpha = a->alpha; p.bias = a->bias; p.scale_cols = a->scale_cols; p.scale = a->scale; p.act = a->act;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16); p.ld_aux = a->ld_aux;
+  p.residual = a->residual; p.ldr = a->ldr;
+  p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->ld_bf16;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p.ld2 = a->ld2;
+  p.accumulate = a->accumulate;
+  constexpr int smem = 2 * kSkStage * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "skinny_gemm smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  skinny_gemm_kernel<<<(a->N + kSkN - 1) / kSkN, 128, smem, stream>>>(p);
+  return check_launch("skinny_gemm_kernel");
+}
+
+}  // namespace oat

@@ -714,6 +714,9 @@ static bool use_pairs(const oat_gemm_args* a, int epi) {
   return enabled && epi != EPI_GENERIC && a->M > BLOCK_M;
 }
 
+bool skinny_gemm_supported(const oat_gemm_args* a);          // gemm_skinny.cu: <= 64 rows, K-major x K-major
+int launch_skinny_gemm(const oat_gemm_args* a, cudaStream_t stream);
+
 }  // namespace oat
 
 extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
@@ -727,6 +730,11 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
   OAT_REQUIRE(a->scale_cols % 4 == 0, "oat_gemm_bf16: scale_cols must be a multiple of 4");
   cudaStream_t s = as_stream(stream);
   const bool amn = a->a_major != 0, bmn = a->b_major != 0;
+  {
+    // few-row products (CLS rows, projections) are weight streams: one CTA per 16 output columns, no split-K atomics
+    static const bool skinny_on = [] { const char* e = getenv("OAT_GEMM_SKINNY"); return e == nullptr || atoi(e) != 0; }();
+    if (skinny_on && skinny_gemm_supported(a)) return launch_skinny_gemm(a, s);
+  }
   // 256-wide tiles unless the problem is narrow
   const bool wide = (a->N % 256 == 0) || a->N > 512;
   const int code = (amn ? 2 : 0) | (bmn ? 1 : 0);

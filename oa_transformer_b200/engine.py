@@ -127,13 +127,6 @@ def _lo(w3):
     return w3[:, k:2 * k]
 
 
-def _spread(N, K, sms=148):
-    """split-K factor that spreads a skinny (few-row) accumulate GEMM over the whole chip: its cost is streaming the
-    [N, K] weight, which a handful of output tiles cannot do fast."""
-    tiles = max(1, (N + 255) // 256)
-    return max(1, min((K + 63) // 64, sms // tiles))
-
-
 def _lohi(w3):
     """[lo | hi]: against activation columns [hi | lo] this is the correction hi.lo + lo.hi."""
     return w3[:, w3.shape[1] // 3:]
@@ -315,8 +308,7 @@ class VideoEngine:
                 wproj = W[(i, tag, "proj")]
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
                 if split:       # the attention output is bf16 already (lo = 0): add a . w_lo on the CLS rows
-                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True,
-                             split_k=_spread(D, D))
+                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True)
                 return wqkv, wproj, qkv, a, lse
 
             # time attention on norm3(x); residual from x                    (video_transformer.py:164-165)
@@ -345,8 +337,7 @@ class VideoEngine:
                 ops.split3_bf16(g32, g3)
             ops.gemm(g, L["w2"], bias=p[b + "mlp.fc2.bias"], residual=sr, out_f32=xs[i + 1])
             if split:           # + g_hi . w_lo + g_lo . w_hi on the CLS rows
-                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True,
-                         split_k=_spread(D, 8 * D))
+                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True)
             L["tr"], L["sr"], L["u"], L["g"] = tr, sr, u, g
             layers.append(L)
             if tokens == "region" and i + 1 == region_layer:

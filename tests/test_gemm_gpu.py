@@ -169,3 +169,60 @@ def test_gemm_cta_pairs_and_single_cta_agree(pairs, monkeypatch):
     dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
     ops.gemm(o16, B, b_major=1, out_bf16=dx)
     assert torch.allclose(dx.float(), o16.float() @ B.float(), rtol=2e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 2304, 2304), (32, 768, 6144), (4, 256, 768), (64, 3072, 2304), (1, 768, 768),
+                                   (17, 260, 136)])
+def test_skinny_gemm_epilogues_strided_and_reproducible(M, N, K, monkeypatch):
+    """gemm_skinny.cu (<= 64 rows, K-major x K-major: the split-bf16 CLS rows and the projections): every epilogue of
+    oat_gemm_bf16 on strided rows (the CLS rows of a token buffer), the accumulate form, and bit-for-bit reproducibility
+    (one owner per output element, fixed k order: no atomics)."""
+    from oa_transformer_b200 import ops
+    T = 5
+    A_all = _mk((M * T, K), 7)
+    A = A_all.view(M, T * K)[:, :K]                       # rows 0, T, 2T, ... of a token buffer
+    B = (_mk((N, K), 8).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda") * 0.1
+    exact = A.float() @ B.float().t()
+    scale = exact.abs().max().item()
+    # plain fp32 + bf16 outputs on strided rows, with bias and the q column scale
+    big32 = torch.zeros(M * T, N, device="cuda")
+    big16 = torch.zeros(M * T, N, device="cuda", dtype=torch.bfloat16)
+    sc = (N // 3) // 4 * 4
+    ops.gemm(A, B, bias=bias, scale_cols=sc, scale=0.125, out_f32=big32.view(M, T * N)[:, :N],
+             out_bf16=big16.view(M, T * N)[:, :N])
+    ref = exact + bias
+    ref[:, :sc] *= 0.125
+    assert (big32[::T] - ref).abs().max().item() <= 2e-3 * scale + 1e-3
+    assert torch.allclose(big16[::T].float(), ref, rtol=1e-2, atol=1e-2 * scale)
+    assert float(big32[1::T].abs().max()) == 0.0 and float(big16[1::T].float().abs().max()) == 0.0
+    # reproducible bit for bit
+    again = torch.zeros_like(big32)
+    ops.gemm(A, B, bias=bias, scale_cols=sc, scale=0.125, out_f32=again.view(M, T * N)[:, :N])
+    assert torch.equal(again, big32)
+    # residual + accumulate on top
+    res = torch.randn(M, N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, residual=res, out_f32=out)
+    ops.gemm(A, B, out_f32=out, accumulate=True)
+    assert (out - (2 * exact + res)).abs().max().item() <= 4e-3 * scale + 2e-3
+    # GELU with its stored derivative, fp32 + bf16 outputs at once (the fc1 CLS rows)
+    g32 = torch.empty(M, N, device="cuda")
+    g16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    d16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, out_f32=g32, out_bf16=g16, out2_bf16=d16)
+    u = (exact + bias).double()
+    cdf = 0.5 * (1 + torch.erf(u / 2 ** 0.5))
+    gref = (u * cdf).float()
+    dref = (cdf + u * torch.exp(-0.5 * u * u) / (2 * 3.141592653589793) ** 0.5).float()
+    assert (g32 - gref).abs().max().item() <= 3e-3 * scale + 1e-3
+    assert torch.allclose(d16.float(), dref, rtol=2e-2, atol=2e-2)
+    # x aux (GELU backward) and ReLU
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, act=ops.ACT_GELU_BWD, aux=d16, out_bf16=o)
+    assert torch.allclose(o.float(), exact * d16.float(), rtol=2e-2, atol=2e-2 * scale)
+    r = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, bias=bias, act=ops.ACT_RELU, out_f32=r)
+    assert (r - (exact + bias).clamp_min(0)).abs().max().item() <= 2e-3 * scale + 1e-3
+    # and it agrees with the tcgen05 kernel on the same problem
+    monkeypatch.setenv("OAT_GEMM_SKINNY", "0")
