@@ -5,7 +5,7 @@
 // With M = batch rows the contraction is a weight STREAM ([N, K] read once, <= 64 output rows): the 128-row tcgen05 tile
 // would leave a handful of CTAs pulling the whole weight through one SM each (or need split-K with floating-point
 // atomics). Here every CTA owns 16 output columns over the full K: N/16 CTAs stream their 16 weight rows with cp.async
-// (128-column chunks, double-buffered), warp w multiplies rows [16w, 16w+16) on bf16 mma.sync m16n8k16, and the fused
+// (128-column chunks, 4-stage ring), warp w multiplies rows [16w, 16w+16) on bf16 mma.sync m16n8k16, and the fused
 // epilogue of oat_gemm_bf16 (alpha, bias, column scale, GELU + derivative / x aux / ReLU, fp32 residual, accumulate)
 // is applied to the fragments. One owner per output element and a fixed k order: bit-reproducible, no atomics.
 #include "oat_host.h"
@@ -20,6 +20,7 @@ constexpr int kSkN = 16;          // columns per CTA
 constexpr int kSkK = 128;         // k chunk
 constexpr int kSkPitch = kSkK + 8;                // bf16 elements: 272-byte rows keep ldmatrix conflict-free
 constexpr int kSkStage = (kSkM + kSkN) * kSkPitch;    // elements per stage
+constexpr int kSkStages = 4;      // cp.async ring depth: three chunks (65 KB) in flight per CTA hide the L2 / HBM latency
 
 __device__ __forceinline__ void sk_cp16(uint32_t smem, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(g) : "memory");
@@ -84,14 +85,17 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyParams p) 
 #pragma unroll
   for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-  stage(0, 0);
-  sk_commit();
-  for (int c = 0; c < chunks; ++c) {
-    const int s = c & 1;
-    if (c + 1 < chunks) stage(c + 1, s ^ 1);
+#pragma unroll
+  for (int c = 0; c < kSkStages - 1; ++c) {
+    if (c < chunks) stage(c, c);
     sk_commit();
-    sk_wait<1>();
-    __syncthreads();
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const int s = c % kSkStages;
+    sk_wait<kSkStages - 2>();                 // chunk c has landed (groups complete in order)
+    __syncthreads();                          // ... for every thread, and the stage refilled below is no longer being read
+    if (c + kSkStages - 1 < chunks) stage(c + kSkStages - 1, (c + kSkStages - 1) % kSkStages);
+    sk_commit();
     if (warp * 16 < p.M) {
       const uint32_t a_base = smem_u32(sk_smem + s * kSkStage);
       const uint32_t b_base = a_base + kSkM * kSkPitch * 2;
@@ -105,7 +109,6 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyParams p) 
         sk_mma(acc[1], a, b[2], b[3]);
       }
     }
-    __syncthreads();
   }
 
   // ---- epilogue on the fragments: lane (g, t) holds rows g / g+8 and columns 2t, 2t+1 of each 8-column tile
@@ -174,7 +177,7 @@ int launch_skinny_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->ld_bf16;
   p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p.ld2 = a->ld2;
   p.accumulate = a->accumulate;
-  constexpr int smem = 2 * kSkStage * 2;
+  constexpr int smem = kSkStages * kSkStage * 2;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -3,8 +3,9 @@ attribute names and state_dict keys (OATrans/model/video_transformer.py:179-357;
 the liboat video engine instead of eager PyTorch.
 
 Differences that are part of the design, not of the contract:
-  * forward() returns (cls_feature, None): only the CLS row is normalised by the final LayerNorm because that is the
-    only row FrozenInTime consumes (oa_model.py:130-131). return_tokens=True is not offered by the CUDA path.
+  * forward() returns (cls_feature, None) by default: only the CLS row is normalised by the final LayerNorm because that
+    is the only row FrozenInTime consumes (oa_model.py:130-131). forward(x, return_tokens=True) returns
+    (x[:, 0], x[:, 1:]) exactly like video_transformer.py:346-351 (final norm over every token row, differentiable).
   * object_tokens=True adds `object_embed` Linear(2054, embed_dim) (oa_video_transformer_region.py:250) and, with
     modality_token=True, `token_type_embeddings` (ibid. :257-261); forward then takes region features.
 """
@@ -127,10 +128,13 @@ class SpaceTimeTransformer(nn.Module):
         skip = ("head.", "pre_logits.", "fc.")
         return [(prefix + n, p) for n, p in self.named_parameters() if not n.startswith(skip)]
 
-    def forward_features(self, x, objects=None, aug=False):
+    def forward_features(self, x, objects=None, aug=False, return_tokens=False):
         named = self.tower_params()
+        if return_tokens:
+            cls_feature, tok = run_tower(self.engine(x.device), named, video=x, objects=objects, proj=None, tokens="final")
+            return cls_feature, tok[:, 1:]
         out = run_tower(self.engine(x.device), named, video=x, objects=objects, proj=None)
         return out, None
 
-    def forward(self, x, objects=None, aug=False):
-        return self.forward_features(x, objects=objects, aug=aug)
+    def forward(self, x, objects=None, aug=False, return_tokens=False):
+        return self.forward_features(x, objects=objects, aug=aug, return_tokens=return_tokens)

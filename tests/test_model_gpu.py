@@ -493,6 +493,29 @@ def test_video_tower_cuda_graph_replay_matches_eager(monkeypatch):
             assert rel(g_g[k], g_r[k]) < 2e-2, (k, rel(g_g[k], g_r[k]))
 
 
+def test_space_time_transformer_returns_patch_tokens_like_the_reference():
+    """video_transformer.py:346-351 returns (x[:, 0], x[:, 1:]) after the final norm: the module mirror with
+    return_tokens=True against the reference's own outputs and gradients (tests/golden/video_small.pt, whose loss mixes
+    the CLS feature and the patch tokens)."""
+    from oa_transformer_b200.model import SpaceTimeTransformer
+    g = torch.load(os.path.join(GOLD, "video_small.pt"), map_location="cpu", weights_only=False)
+    m = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_frames=3,
+                             time_init="rand")
+    m.head = torch.nn.Identity()
+    missing, unexpected = m.load_state_dict(g["weights"], strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    m = m.cuda()
+    cls, tokens = m(g["video"].cuda(), return_tokens=True)
+    assert rel(cls.detach().cpu(), g["cls"]) < 5e-3 and rel(tokens.detach().cpu(), g["tokens"]) < 5e-3
+    ((cls * g["probe"].cuda()).sum() + (tokens * g["probe_tokens"].cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    errs = {k: rel(dict(m.named_parameters())[k].grad.cpu(), v) for k, v in g["grads"].items()}
+    worst = max(errs.values())
+    assert worst < 3e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    cls2, none = m(g["video_short"].cuda())
+    assert none is None and rel(cls2.detach().cpu(), g["cls_short"]) < 5e-3
+
+
 def test_frozen_in_time_module_surface():
     """The nn.Module mirror: constructor, forward(data) -> (text, video) embeddings, backward into .grad."""
     from oa_transformer_b200.model import FrozenInTime, NormSoftmaxLoss, sim_matrix
