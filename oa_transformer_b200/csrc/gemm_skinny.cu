@@ -72,14 +72,18 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyParams p) 
       const bool is_a = r < kSkM;
       const int row = is_a ? r : n0 + (r - kSkM);
       __nv_bfloat16* dst = (is_a ? As + r * kSkPitch : Bs + (r - kSkM) * kSkPitch) + v * 8;
-      const bool ok = k < p.K && (is_a ? row < p.M : row < p.N);
-      if (ok) {
+      const bool ok = is_a ? row < p.M : row < p.N;        // rows beyond M / N stay zero from the clear below
+      if (!ok) continue;
+      if (k < p.K) {
         sk_cp16(smem_u32(dst), (is_a ? p.A + static_cast<long long>(row) * p.lda : p.B + static_cast<long long>(row) * p.ldb) + k);
       } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);      // k tail of the last chunk
       }
     }
   };
+  // rows that no load ever writes (A rows >= M, B rows >= N) must read as zero: clear the ring once
+  for (int idx = tid; idx < kSkStages * kSkStage / 8; idx += 128) reinterpret_cast<uint4*>(sk_smem)[idx] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
 
   float acc[2][4];
 #pragma unroll
