@@ -164,6 +164,12 @@ int oat_assemble_tokens_bwd(const float* dx, void* dpatch_bf16, void* dobject_bf
                             float* dtemporal, float* dtype_embed, int32_t B, int32_t F, int32_t N, int32_t O,
                             int32_t D, oat_stream_t stream);
 int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int32_t cols, float* out, oat_stream_t stream);
+/* Bias gradient for free: a weight-gradient GEMM dY^T . [X | 1 0 .. 0] (activation rows extended by a ones column, pitch
+ * cols + 16) leaves dW in columns [0, cols) and the column sums of dY - the bias gradient - in column `cols` of its fp32
+ * scratch output [rows, ld]; oat_gemm_bf16 multiplies that last, 16-wide column block with an N = 16 instruction. This
+ * call adds both into their gradient tensors (dw [rows, ldw], db [rows]) and re-zeroes the scratch. */
+int oat_unpack_wgrad(float* scratch, int64_t ld, int32_t cols, float* dw, int64_t ldw, float* db, int64_t rows,
+                     oat_stream_t stream);
 int oat_text_embed(const int64_t* ids, const float* word_emb, const float* pos_emb, float* out, int64_t rows,
                    int32_t L, int32_t D, oat_stream_t stream);
 int oat_text_embed_bwd(const int64_t* ids, const float* dsum, float* dword, float* dpos, int64_t rows, int32_t L,

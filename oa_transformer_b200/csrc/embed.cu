@@ -142,6 +142,32 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, uin
     keep[idx] = dropout_keep(seed, site, static_cast<uint64_t>(idx), thresh) ? 1 : 0;
 }
 
+// Weight-gradient GEMMs run against the activation matrix extended by a column of ones ([tokens, cols | 1 0 ... 0]): the
+// product dY^T [X | 1] carries the bias gradient (column sums of dY) in column `cols` for free - the tensor core reads dY
+// anyway, a separate column-sum kernel would read it again. This kernel moves the result out of the fp32 scratch
+// [rows, ld]: dW += scratch[:, :cols], db += scratch[:, cols], and re-zeroes the scratch for the next accumulate.
+__global__ void unpack_wgrad_kernel(float* __restrict__ scratch, long long ld, int cols, float* __restrict__ dw,
+                                    long long ldw, float* __restrict__ db, long long rows) {
+  const int vec_per_row = (cols >> 2) + 1;            // cols / 4 weight vectors + the vector that starts with the bias sum
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const int v = static_cast<int>(idx - r * vec_per_row);
+    float4* sp = reinterpret_cast<float4*>(scratch + r * ld) + v;
+    const float4 x = *sp;
+    *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < (cols >> 2)) {
+      float4* wp = reinterpret_cast<float4*>(dw + r * ldw) + v;
+      float4 w = *wp;
+      w.x += x.x; w.y += x.y; w.z += x.z; w.w += x.w;
+      *wp = w;
+    } else {
+      db[r] += x.x;
+    }
+  }
+}
+
 // Many casts in one launch (the bf16 operand copies of every weight of a tower, re-packed each step): a device table
 // row = {src, dst, rows, cols, cols_padded, src pitch, dst pitch, kind}, chunk_prefix = prefix sum of the
 // 1024-element chunks of each tensor's padded (rows x cols_padded) extent. kind 0: bf16 copy; 1: plain fp32 copy (bias
@@ -467,6 +493,18 @@ extern "C" int oat_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed
   dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
       keep, n, static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0), seed, site);
   return check_launch("dropout_mask_kernel");
+}
+
+extern "C" int oat_unpack_wgrad(float* scratch, int64_t ld, int32_t cols, float* dw, int64_t ldw, float* db, int64_t rows,
+                                oat_stream_t stream) {
+  OAT_REQUIRE(scratch != nullptr && dw != nullptr && db != nullptr && cols > 0 && cols % 4 == 0 && ld >= cols + 4 &&
+              ld % 4 == 0 && ldw % 4 == 0, "oat_unpack_wgrad: bad arguments (cols %% 4 == 0, ld >= cols + 4)");
+  OAT_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0,
+              "oat_unpack_wgrad: scratch and dw must be 16-byte aligned");
+  if (rows <= 0) return OAT_OK;
+  const long long total = rows * ((cols >> 2) + 1);
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(scratch, ld, cols, dw, ldw, db, rows);
+  return check_launch("unpack_wgrad_kernel");
 }
 
 extern "C" int oat_cast_multi(const int64_t* table, const int64_t* chunk_prefix, int32_t n, int64_t total_chunks,

@@ -247,6 +247,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
       const uint32_t acc = local_iter & 1;
       const uint32_t acc_phase = (local_iter >> 1) & 1;
+      // Narrow last column block: when only a few columns of the tile exist (the "ones" column that turns a weight-
+      // gradient GEMM into weight + bias gradient, engine.py) the instruction's N shrinks to 16 instead of multiplying
+      // BLOCK_N - n zero columns. Pair mode feeds instruction columns [0, N/2) from the leader and [N/2, N) from the
+      // peer's (all out-of-range, zero) half tile, so it is only taken there when the valid columns fit in the first 8.
+      uint32_t idesc_t = idesc;
+      {
+        const int mn = tile - split * tiles_mn;
+        const int n_blk = mn % p.num_n_blocks;
+        const int n_valid = p.N - n_blk * BLOCK_N;
+        if (n_valid <= (TWO ? 8 : 16)) idesc_t = make_idesc_bf16(kPair * BLOCK_M, 16, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      }
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -260,8 +271,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            if constexpr (TWO) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO) tc_mma_bf16_pair(d_tmem, adesc, bdesc, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if constexpr (TWO) {
             tc_commit_pair(&empty_bar[stage]);                       // frees the slot in both CTAs
@@ -613,7 +624,10 @@ static bool tma_ok(const void* ptr, long long ld, int esz) {
 
 // The specialised (TMA-box) epilogues need 64-column granularity and 16-byte aligned tensors; anything else is generic.
 static int pick_epi(const oat_gemm_args* a) {
-  if (a->alpha != 1.0f || a->N % 64 != 0) return EPI_GENERIC;
+  // the reduce-add boxes of the accumulate epilogue are clipped by the TMA unit, so a ragged N (the ones column of the
+  // weight + bias gradient GEMM: N = K_in + 16) stays on the fast path; the other epilogues read bias / aux in whole boxes
+  const bool ragged_ok = a->accumulate && a->N % 4 == 0;
+  if (a->alpha != 1.0f || (a->N % 64 != 0 && !ragged_ok)) return EPI_GENERIC;
   if (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15) != 0) return EPI_GENERIC;
   const bool f32 = a->out_f32 != nullptr, b16 = a->out_bf16 != nullptr;
   const bool f32_ok = tma_ok(a->out_f32, a->ld_f32, 4), b16_ok = tma_ok(a->out_bf16, a->ld_bf16, 2);

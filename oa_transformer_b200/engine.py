@@ -30,6 +30,8 @@ HEAD_DIM = 64
 Q_SCALE = HEAD_DIM ** -0.5
 OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py:593-650)
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
+ONES_PAD = 16           # activation rows are [x | 1 0 ... 0]: the weight-gradient GEMM then yields the bias gradient too
+BIAS_VIA_WGRAD = os.environ.get("OAT_BIAS_VIA_WGRAD", "1") != "0"
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
 # Replay the video tower's forward / backward as CUDA graphs. Off by default: measured 529 vs 540 pairs/s (graph / eager)
@@ -80,8 +82,11 @@ class _Buffers:
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.inited = {}
 
-    def get(self, name, shape, dtype, zero=False):
+    def get(self, name, shape, dtype, zero=False, init=None):
+        """init(t): run whenever the buffer is (re)allocated or viewed to a new shape (contents that the schedule
+        never rewrites, e.g. the ones column of the extended activations)."""
         key = (name, dtype)
         numel = 1
         for d in shape:
@@ -93,6 +98,9 @@ class _Buffers:
         t = flat[:numel].view(tuple(shape))
         if zero:
             t.zero_()
+        if init is not None and (self.inited.get(key) != (flat.data_ptr(), tuple(shape))):
+            init(t)
+            self.inited[key] = (flat.data_ptr(), tuple(shape))
         return t
 
 
@@ -115,6 +123,13 @@ def _w16(bufs, name, w, rows=None, cols=None, pitch=None, plan=None, split=False
     else:
         ops.cast_bf16(w2, dst, rows=rows, cols=cols)
     return dst
+
+
+def _ones_column(D):
+    def init(t):
+        t.zero_()
+        t[:, D] = 1.0
+    return init
 
 
 def _hi(w3):
@@ -285,12 +300,14 @@ class VideoEngine:
 
             def ln(tag, src, wname):
                 """LayerNorm of every token row -> bf16 GEMM operand; the CLS rows also leave as [hi | hi | lo]."""
-                h = bufs.get("h%s.%d" % (tag, i), (M, D), BF)
+                hx = bufs.get("h%s.%d" % (tag, i), (M, D + ONES_PAD), BF, init=_ones_column(D))
+                h = hx[:, :D]
                 mean = bufs.get("mean%s.%d" % (tag, i), (M,), F32)
                 rstd = bufs.get("rstd%s.%d" % (tag, i), (M,), F32)
                 c3 = bufs.get("c3." + tag, (B, 3 * D), BF) if split else None
                 ops.layernorm_fwd(src, p[b + wname + ".weight"], p[b + wname + ".bias"], self.eps, y_bf16=h,
                                   mean=mean, rstd=rstd, y_split=c3, split_period=T)
+                L["h%sx" % tag] = hx
                 return h, mean, rstd, c3
 
             def attention(tag, mode, h, c3, aname, resid, out):
@@ -424,9 +441,18 @@ class VideoEngine:
             side.wait_stream(main)              # gradient book zeroed, forward finished
         side_done = {}
 
-        def wgrad(dy16, act16, name, bias=True):
-            # bias=False: the bias gradient was already reduced (fp32) by the LayerNorm-backward kernel that produced dy
+        def wgrad(dy16, act16, name, bias=True, ext=None):
+            # bias=False: the bias gradient was already reduced (fp32) by the LayerNorm-backward kernel that produced dy.
+            # ext: the activation rows extended by a ones column ([x | 1 0 .. 0]); dY^T . ext then carries the bias
+            # gradient in its last column block (an N = 16 MMA) instead of a second pass over dY (oat_unpack_wgrad).
             def run():
+                if bias and ext is not None and BIAS_VIA_WGRAD:
+                    n_out, k_in = dy16.shape[1], act16.shape[1]
+                    scratch = bufs.get("wgrad.scratch", (4 * D, D + ONES_PAD), F32, init=lambda t: t.zero_())
+                    scratch = scratch[:n_out]
+                    ops.gemm(dy16, ext, a_major=1, b_major=1, out_f32=scratch, accumulate=True)
+                    ops.unpack_wgrad(scratch, k_in, grads[name + ".weight"].view(n_out, k_in), grads[name + ".bias"])
+                    return
                 ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
                          accumulate=True)
                 if bias:
@@ -494,7 +520,7 @@ class VideoEngine:
             ops.gemm(dy16, L["w2"], b_major=1, act=ops.ACT_GELU_BWD, aux=L["u"], out_bf16=du[k])
             wgrad(dy16, L["g"], b + "mlp.fc2", bias=False)
             ops.gemm(du[k], L["w1"], b_major=1, out_bf16=dh)
-            wgrad(du[k], L["h2"], b + "mlp.fc1")
+            wgrad(du[k], L["h2"], b + "mlp.fc1", ext=L["h2x"])
             ops.layernorm_bwd(L["sr"], L["m2"], L["r2"], p[b + "norm2.weight"], dy_bf16=dh, add1=dy, dx=dsr,
                               dx_bf16=dsr16[k], dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"],
                               dxsum=grads[b + "attn.proj.bias"])
@@ -503,7 +529,7 @@ class VideoEngine:
             wgrad(dsr16[k], L["a_s"], b + "attn.proj", bias=False)
             ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv_s[k], Q_SCALE, acc)
             ops.gemm(dqkv_s[k], L["wqkv_s"], b_major=1, out_bf16=dh)
-            wgrad(dqkv_s[k], L["h1"], b + "attn.qkv")
+            wgrad(dqkv_s[k], L["h1"], b + "attn.qkv", ext=L["h1x"])
             ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16[k],
                               dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"],
                               dxsum=grads[b + "timeattn.proj.bias"])
@@ -512,7 +538,7 @@ class VideoEngine:
             wgrad(dtr16[k], L["a_t"], b + "timeattn.proj", bias=False)
             ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc)
             ops.gemm(dqkv_t[k], L["wqkv_t"], b_major=1, out_bf16=dh)
-            wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv")
+            wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv", ext=L["h3x"])
             if i == region_at:      # x_i also fed region_norm: dsr += region_norm'(dtokens), in place, before the sum below
                 wn = prefix + "region_norm"
                 ops.layernorm_bwd(xs[i], S["tmean"], S["trstd"], p[wn + ".weight"], dy_f32=dtokens, add1=dsr, dx=dsr,

@@ -357,6 +357,16 @@ def colsum_bf16(x, out):
                                 stream_ptr()), "oat_colsum_bf16")
 
 
+def unpack_wgrad(scratch, cols, dw, db):
+    """dw (+)= scratch[:, :cols]; db (+)= scratch[:, cols]; scratch <- 0 (see oat_unpack_wgrad)."""
+    rows = scratch.shape[0]
+    assert scratch.dtype == torch.float32 and dw.dtype == torch.float32 and db.dtype == torch.float32
+    assert dw.shape == (rows, cols) and db.numel() == rows and scratch.shape[1] >= cols + 4
+    _count(1)
+    check(lib().oat_unpack_wgrad(ptr(scratch), _i64(scratch.stride(0)), _i32(cols), ptr(dw), _i64(dw.stride(0)), ptr(db),
+                                 _i64(rows), stream_ptr()), "oat_unpack_wgrad")
+
+
 def text_embed(ids, word, pos, out, L):
     assert ids.dtype == torch.int64 and ids.is_contiguous()
     _count(1)
@@ -587,7 +597,7 @@ def _profiled(kind, fn):
     return wrapper
 
 
-for _kind, _names in (("ln_fwd", ("layernorm_fwd",)), ("ln_bwd", ("layernorm_bwd",)), ("colsum", ("colsum_bf16",)),
+for _kind, _names in (("ln_fwd", ("layernorm_fwd",)), ("ln_bwd", ("layernorm_bwd",)), ("colsum", ("colsum_bf16", "unpack_wgrad")),
                       ("cast", ("cast_bf16", "split3_bf16", "relu_bwd")),
                       ("embed", ("im2col_patches", "assemble_tokens", "assemble_tokens_bwd", "text_embed", "text_embed_bwd")),
                       ("loss", ("infonce_fwd_bwd", "sim_matrix_fwd", "sim_matrix_bwd", "norm_softmax_loss"))):

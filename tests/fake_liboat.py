@@ -299,6 +299,13 @@ def colsum_bf16(x, out):
     _count(1)
 
 
+def unpack_wgrad(scratch, cols, dw, db):
+    dw += scratch[:, :cols]
+    db += scratch[:, cols]
+    scratch.zero_()
+    _count(1)
+
+
 def text_embed(ids, word, pos, out, L):
     r = torch.arange(ids.numel())
     out.copy_(word.detach()[ids.view(-1)] + pos.detach()[r % L])

@@ -226,3 +226,30 @@ def test_skinny_gemm_epilogues_strided_and_reproducible(M, N, K, monkeypatch):
     assert (r - (exact + bias).clamp_min(0)).abs().max().item() <= 2e-3 * scale + 1e-3
     # and it agrees with the tcgen05 kernel on the same problem
     monkeypatch.setenv("OAT_GEMM_SKINNY", "0")
+
+
+@pytest.mark.parametrize("pairs", ["1", "0"])
+@pytest.mark.parametrize("M,N,K", [(2304, 784, 5000), (3072, 784, 1857 * 4), (768, 272, 3000)])
+def test_gemm_wgrad_with_ones_column_gives_bias_gradient(M, N, K, pairs, monkeypatch):
+    """Weight + bias gradient in one GEMM: dY^T . [X | 1 0 .. 0] with a ragged, 16-wide last column block (multiplied by
+    an N = 16 instruction, gemm_tcgen05.cu) accumulated into an fp32 scratch, then oat_unpack_wgrad. vs torch."""
+    from oa_transformer_b200 import ops
+    monkeypatch.setenv("OAT_GEMM_2CTA", pairs)
+    kin = N - 16
+    dy = _mk((K, M), 11)                                   # [tokens, N_out]
+    xe = torch.zeros(K, N, device="cuda", dtype=torch.bfloat16)
+    xe[:, :kin] = _mk((K, kin), 12)
+    xe[:, kin] = 1.0
+    scratch = torch.zeros(M, N, device="cuda")
+    ops.gemm(dy, xe, a_major=1, b_major=1, out_f32=scratch, accumulate=True)
+    ref = dy.float().t() @ xe.float()
+    scale = ref[:, :kin].abs().max().item()
+    assert (scratch[:, :kin] - ref[:, :kin]).abs().max().item() <= 2e-3 * scale + 1e-2
+    bsum = dy.float().sum(0)
+    assert (scratch[:, kin] - bsum).abs().max().item() <= 2e-3 * bsum.abs().max().item() + 1e-2
+    dw = torch.ones(M, kin, device="cuda")
+    db = torch.ones(M, device="cuda")
+    ops.unpack_wgrad(scratch, kin, dw, db)
+    assert (dw - 1 - ref[:, :kin]).abs().max().item() <= 2e-3 * scale + 1e-2
+    assert (db - 1 - bsum).abs().max().item() <= 2e-3 * bsum.abs().max().item() + 1e-2
+    assert float(scratch.abs().max()) == 0.0                # handed back zeroed for the next accumulate
