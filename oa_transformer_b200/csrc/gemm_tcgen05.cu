@@ -672,7 +672,12 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   const int workers = num_sms() / kPair;          // CTAs, or CTA pairs
   const bool can_split = a->accumulate && a->out_f32 != nullptr && a->out_bf16 == nullptr && a->act == 0;
-  p.split_k = (a->split_k == 0 && !can_split) ? 1 : pick_split_k(p.num_m_blocks * p.num_n_blocks, p.k_blocks, workers, a->split_k);
+  // a narrow last column block (N = 16 instruction, see the MMA issuer) costs ~1/16 of a tile: balance the split on the
+  // full-width tiles only
+  const int n_tail = a->N % BLOCK_N;
+  const bool narrow_last = n_tail != 0 && n_tail <= (TWO ? 8 : 16) && p.num_n_blocks > 1;
+  const int tiles_for_split = p.num_m_blocks * (p.num_n_blocks - (narrow_last ? 1 : 0));
+  p.split_k = (a->split_k == 0 && !can_split) ? 1 : pick_split_k(tiles_for_split, p.k_blocks, workers, a->split_k);
   {  // no empty splits
     const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
     p.split_k = (p.k_blocks + per - 1) / per;

@@ -30,7 +30,8 @@ HEAD_DIM = 64
 Q_SCALE = HEAD_DIM ** -0.5
 OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py:593-650)
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
-ONES_PAD = 16           # activation rows are [x | 1 0 ... 0]: the weight-gradient GEMM then yields the bias gradient too
+ONES_PAD = 8            # activation rows are [x | 1 0 ... 0]: the weight-gradient GEMM then yields the bias gradient too
+                        # (8: keeps 16-byte row pitches and fits the first half of a CTA pair's N = 16 instruction)
 BIAS_VIA_WGRAD = os.environ.get("OAT_BIAS_VIA_WGRAD", "1") != "0"
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
@@ -140,6 +141,13 @@ def _hi(w3):
 def _lo(w3):
     k = w3.shape[1] // 3
     return w3[:, k:2 * k]
+
+
+def _spread(N, K, sms=148):
+    """split-K factor that spreads a few-row accumulate GEMM over the whole chip: its cost is streaming the [N, K]
+    weight, which a handful of output tiles cannot do fast."""
+    tiles = max(1, (N + 255) // 256)
+    return max(1, min((K + 63) // 64, sms // tiles))
 
 
 def _lohi(w3):
@@ -325,7 +333,8 @@ class VideoEngine:
                 wproj = W[(i, tag, "proj")]
                 ops.gemm(a, wproj, bias=p[b + aname + ".proj.bias"], residual=resid, out_f32=out)
                 if split:       # the attention output is bf16 already (lo = 0): add a . w_lo on the CLS rows
-                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True)
+                    ops.gemm(cls(a), _lo(W3[(i, tag, "proj")]), out_f32=cls(out), accumulate=True,
+                             split_k=_spread(D, D))
                 return wqkv, wproj, qkv, a, lse
 
             # time attention on norm3(x); residual from x                    (video_transformer.py:164-165)
@@ -354,7 +363,8 @@ class VideoEngine:
                 ops.split3_bf16(g32, g3)
             ops.gemm(g, L["w2"], bias=p[b + "mlp.fc2.bias"], residual=sr, out_f32=xs[i + 1])
             if split:           # + g_hi . w_lo + g_lo . w_hi on the CLS rows
-                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True)
+                ops.gemm(g3[:, 4 * D:], _lohi(W3[(i, "fc2")]), out_f32=cls(xs[i + 1]), accumulate=True,
+                         split_k=_spread(D, 8 * D))
             L["tr"], L["sr"], L["u"], L["g"] = tr, sr, u, g
             layers.append(L)
             if tokens == "region" and i + 1 == region_layer:

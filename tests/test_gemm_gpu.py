@@ -200,7 +200,7 @@ def test_skinny_gemm_epilogues_strided_and_reproducible(M, N, K, monkeypatch):
     again = torch.zeros_like(big32)
     ops.gemm(A, B, bias=bias, scale_cols=sc, scale=0.125, out_f32=again.view(M, T * N)[:, :N])
     assert torch.equal(again, big32)
-    # residual + accumulate on top
+    # residual, then the accumulate form on top (the accumulate form itself runs split-K on the tcgen05 kernel)
     res = torch.randn(M, N, device="cuda")
     out = torch.empty(M, N, device="cuda")
     ops.gemm(A, B, residual=res, out_f32=out)
@@ -229,13 +229,13 @@ def test_skinny_gemm_epilogues_strided_and_reproducible(M, N, K, monkeypatch):
 
 
 @pytest.mark.parametrize("pairs", ["1", "0"])
-@pytest.mark.parametrize("M,N,K", [(2304, 784, 5000), (3072, 784, 1857 * 4), (768, 272, 3000)])
+@pytest.mark.parametrize("M,N,K", [(2304, 776, 5000), (3072, 776, 1857 * 4), (768, 264, 3000), (2304, 784, 4000)])
 def test_gemm_wgrad_with_ones_column_gives_bias_gradient(M, N, K, pairs, monkeypatch):
     """Weight + bias gradient in one GEMM: dY^T . [X | 1 0 .. 0] with a ragged, 16-wide last column block (multiplied by
     an N = 16 instruction, gemm_tcgen05.cu) accumulated into an fp32 scratch, then oat_unpack_wgrad. vs torch."""
     from oa_transformer_b200 import ops
     monkeypatch.setenv("OAT_GEMM_2CTA", pairs)
-    kin = N - 16
+    kin = (N // 256) * 256
     dy = _mk((K, M), 11)                                   # [tokens, N_out]
     xe = torch.zeros(K, N, device="cuda", dtype=torch.bfloat16)
     xe[:, :kin] = _mk((K, kin), 12)
