@@ -32,7 +32,10 @@ OBJ_DIM = 2054          # 2048 ROI feature + 6 box numbers (base/base_dataset.py
 OBJ_PITCH = 2112        # padded to a multiple of 64 for TMA (16-byte row pitch) and whole k-blocks
 ONES_PAD = 8            # activation rows are [x | 1 0 ... 0]: the weight-gradient GEMM then yields the bias gradient too
                         # (8: keeps 16-byte row pitches and fits the first half of a CTA pair's N = 16 instruction)
-BIAS_VIA_WGRAD = os.environ.get("OAT_BIAS_VIA_WGRAD", "1") != "0"
+# Bias gradients of qkv / fc1 out of the weight-gradient GEMM's ones column instead of a column-sum kernel. Off by default:
+# measured 60.3 vs 59.2 ms/step - the column sums already run on the side stream under tensor-bound chain kernels, while
+# the extra (narrow) column block still streams every dY tile through shared memory a second time.
+BIAS_VIA_WGRAD = os.environ.get("OAT_BIAS_VIA_WGRAD", "0") != "0"
 SIDE_STREAM = os.environ.get("OAT_SIDE_STREAM", "1") != "0"   # weight gradients on a second stream (engine backward)
 SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forward products on the CLS / text rows
 # Replay the video tower's forward / backward as CUDA graphs. Off by default: measured 529 vs 540 pairs/s (graph / eager)
