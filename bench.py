@@ -48,8 +48,8 @@ def load_gemm_traffic():
     """Measured DRAM bytes per GEMM launch (ncu --set full, profiles/r1_kernel_traffic.json made by
     scripts/ncu_traffic_table.py from one launch of every per-layer GEMM shape at the bench geometry), averaged over the
     18 GEMM launches of one transformer layer; beside it the algorithmic operand + output bytes of the same launches."""
-    path = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-    if not os.path.exists(path):
+    path = traffic_table_path()
+    if path is None:
         return None, None
     with open(path) as f:
         t = json.load(f)
@@ -60,7 +60,16 @@ def load_gemm_traffic():
         return None, None
     n = sum(count.values())
     meas = sum(c * (t[k]["dram_read_bytes"] + t[k]["dram_write_bytes"]) for k, c in count.items()) / n
-    return meas, "average over the 18 GEMM launches of one layer at M=59424 (B=32); per shape in profiles/r1_kernel_traffic.json"
+    return meas, "average over the 18 GEMM launches of one layer at M=59424 (B=32); per shape in profiles/" + os.path.basename(path)
+
+
+def traffic_table_path():
+    """Newest committed ncu traffic table (scripts/ncu_traffic_table.py output)."""
+    for name in ("r2_kernel_traffic.json", "r1_kernel_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            return path
+    return None
 
 
 def load_peaks():
@@ -507,8 +516,8 @@ def run_ours(args):
         # attention cores: HBM-bound. Algorithmic bytes per group = 128 B x (q + out rows, k + v rows) forward and
         # twice that backward (q, dO, O, dQ rows; k, v, dK, dV rows) - ops.attn_core_work / SURVEY.md 8(d).
         ktraffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-        if B == 32 and os.path.exists(tpath):
+        tpath = traffic_table_path()
+        if B == 32 and tpath is not None:
             with open(tpath) as f:
                 ktraffic = json.load(f)
         roofline_attn = {}
@@ -534,17 +543,18 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
-            cb = 2
+            cb = 4                                  # B = 4 at F = 8, 1 warm-up + 3 timed, median
             cstep = cpu_oracle_step_fn(cb, cores)
             cstep()
-            t0 = time.perf_counter()
-            n_rep = 2
-            for _ in range(n_rep):
+            times = []
+            for _ in range(3):
+                t0 = time.perf_counter()
                 cstep()
-            cdt = (time.perf_counter() - t0) / n_rep
+                times.append(time.perf_counter() - t0)
+            cdt = sorted(times)[1]
             cpu = {"value": cb / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d fwd+bwd steps of %d pairs (same per-pair workload), fp32 oracle port of the reference "
-                             "path, after 1 warm-up" % (n_rep, cb)}
+                   "sample": "median of 3 fwd+bwd steps of %d pairs (same per-pair workload: 8x224^2 frames, 36 objects, "
+                             "32 tokens), fp32 oracle port of the reference path, after 1 warm-up" % cb}
         except Exception as ex:  # the baseline is informative; never lose the GPU line over it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 

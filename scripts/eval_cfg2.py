@@ -25,6 +25,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=50)
+    ap.add_argument("--oracle-pairs", type=int, default=24,
+                    help="first N pairs also go through the fp32 CPU oracle (= what the reference computes): logits, "
+                         "R@1 / R@5 and forward latency of that sub-problem, reference vs CUDA")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     model = bench.build_model(dev).eval()
@@ -50,8 +53,29 @@ def main():
         t2v, v2t = M.t2v_metrics(sims), M.v2t_metrics(sims)
         host = sims.cpu().numpy()
         same = M.t2v_metrics(host) == t2v and M.v2t_metrics(host) == v2t
+    vs_ref = None
+    if args.oracle_pairs > 0:
+        import time
+        from oracle import oracle as O
+        n = min(args.oracle_pairs, args.batch)
+        g = torch.Generator().manual_seed(777)
+        video = torch.randn(args.batch, bench.FRAMES, 3, bench.IMG, bench.IMG, generator=g)[:n]
+        objects = synth_objects(args.batch, bench.FRAMES, bench.OBJECTS, g)[:n]
+        text = {k: v[:n] for k, v in synth_text(args.batch, bench.TEXT_LEN, g).items()}
+        w = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            te, ve = O.dual_encoder({"video": video, "object": objects, "text": text}, w, O.OracleCfg())
+            cpu_s = time.perf_counter() - t0
+        ref = O.sim_matrix(te, ve).numpy()
+        ours = host[:n, :n]
+        vs_ref = {"pairs": n, "logit_max_abs_err": float(abs(ours - ref).max()),
+                  "reference_t2v": M.t2v_metrics(ref), "ours_t2v": M.t2v_metrics(ours.copy()),
+                  "reference_v2t": M.v2t_metrics(ref), "ours_v2t": M.v2t_metrics(ours.copy()),
+                  "reference_cpu_fwd_pairs_per_s": n / cpu_s, "cpu_threads": os.cpu_count()}
     lat.sort()
-    print(json.dumps({"config": "cfg2: %d pairs, batch %d, 8x224^2 + 36 obj + 32 tok, forward only" % (args.pairs, args.batch),
+    print(json.dumps({"vs_reference_fp32_oracle": vs_ref,"config": "cfg2: %d pairs, batch %d, 8x224^2 + 36 obj + 32 tok, forward only" % (args.pairs, args.batch),
                       "fwd_ms_per_batch_median": lat[len(lat) // 2], "fwd_pairs_per_s": args.batch / (lat[len(lat) // 2] / 1e3),
                       "t2v": t2v, "v2t": v2t, "device_metrics_equal_host_numpy": bool(same),
                       "note": "random-init weights: recall at chance level (0.1 % R@1 expected)"}))
