@@ -90,7 +90,10 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
     _count(1)
-    with _Prof("gemm", 2.0 * M * N * K):
+    # products with <= 64 rows take the mma.sync weight-stream kernel (gemm_skinny.cu) unless they accumulate: a different
+    # kernel, profiled under its own name so that "gemm" is the tcgen05 kernel only
+    skinny = M <= 64 and a_major == 0 and b_major == 0 and not accumulate and K % 8 == 0
+    with _Prof("gemm_skinny" if skinny else "gemm", 2.0 * M * N * K):
         check(lib().oat_gemm_bf16(ctypes.byref(a), stream_ptr()), "oat_gemm_bf16")
 
 
