@@ -265,6 +265,7 @@ def main():
 def run_multi_gpu_check(model, params, step, dev, rank, world, device):
     import torch
     import torch.distributed as dist
+    torch.manual_seed(4321)                              # same DistilBERT dropout masks in both evaluations below
     loss = step(dev)                                     # with the all-reduce
     torch.cuda.synchronize()
     losses = [torch.zeros(1, device=device) for _ in range(world)]
@@ -282,6 +283,7 @@ def run_multi_gpu_check(model, params, step, dev, rank, world, device):
     reduced = [p.grad.detach().clone() for p in probe]
     # local (unreduced) gradients of the same step, averaged with a separate all-reduce on copies
     os.environ["OAT_BENCH_NO_REDUCE"] = "1"
+    torch.manual_seed(4321)
     try:
         step(dev)
     finally:

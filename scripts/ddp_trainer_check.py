@@ -63,7 +63,8 @@ def main():
 
     for p in params:
         p.grad = None
-    loss = hot_lines()
+    torch.manual_seed(4321)              # the text tower draws its dropout seed from torch's CPU generator: same masks
+    loss = hot_lines()                   # in the DDP evaluation and in the no_sync() one below
     torch.cuda.synchronize()
     losses = [torch.zeros(1, device=device) for _ in range(world)]
     dist.all_gather(losses, loss.detach().reshape(1))
@@ -74,6 +75,7 @@ def main():
     reduced = [p.grad.detach().clone() for p in probe]
     for p in params:
         p.grad = None
+    torch.manual_seed(4321)
     with ddp.no_sync():
         hot_lines()
     torch.cuda.synchronize()
