@@ -76,6 +76,7 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HDIM = G.H * SD;
+  pdl_launch_dependents();
 
   // operand rows that no load ever writes (key rows nk..nkp, query rows n+1..255) must be finite: zero everything once
   for (int i = tid; i < 2 * kStageBytes / 16; i += kSpThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -98,6 +99,7 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                   // shared memory cleared, barriers and TMEM ready: now wait for the qkv GEMM
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -353,7 +355,8 @@ int launch_space_tc(const CUtensorMap& tm, const SpaceGeom& G, cudaStream_t s) {
   }
   const int sms = num_sms();
   const int grid = G.groups < sms ? G.groups : sms;
-  kern<<<grid, kSpThreads, kSpSmem, s>>>(tm, G);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kSpThreads), kSpSmem, s, tm, G);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_fwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("attn_space_tc_fwd_kernel");
 }
 
@@ -419,6 +422,7 @@ attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HDIM = G.H * SD;
   const int n = G.n;
+  pdl_launch_dependents();
 
   for (int i = tid; i < (kBwdOperandBytes + kBwdDsBytes) / 16; i += kSpThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -441,6 +445,7 @@ attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -810,7 +815,8 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
   }
   const int sms = num_sms();
   const int grid = G.groups < sms ? G.groups : sms;
-  attn_space_tc_bwd_kernel<<<grid, kSpThreads, kBwdSmem, s>>>(tq, td, G);
+  cudaError_t e = launch_pdl(attn_space_tc_bwd_kernel, dim3(grid), dim3(kSpThreads), kBwdSmem, s, tq, td, G);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("attn_space_tc_bwd_kernel");
 }
 

@@ -244,6 +244,8 @@ __device__ __forceinline__ void add_row0(float* dst, int lane, const float (&acc
 // attn_time_cls_combine_kernel; without a workspace the caller runs the separate all-keys pass instead.
 template <int MINB>
 __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGeom G) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_time_raw[];
   uint8_t* Qs = sm_time_raw;
   uint8_t* Ks = Qs + kArr;
@@ -426,6 +428,8 @@ __global__ void __launch_bounds__(kCombSlices * TD) attn_time_cls_combine_kernel
 
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom G) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_time_raw[];
   uint8_t* Qs = sm_time_raw;
   uint8_t* Ks = Qs + kArr;
@@ -694,10 +698,10 @@ int launch_time_fwd(const oat_attn_args* a, cudaStream_t s, bool* cls_done) {
   int rc;
   if (four) {
     if ((rc = set_smem_once(attn_time_fwd_kernel<4>, smem, &done4, "attn_time_fwd")) != OAT_OK) return rc;
-    attn_time_fwd_kernel<4><<<grid, kRows, smem, s>>>(G);
+    if (launch_pdl(attn_time_fwd_kernel<4>, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_fwd_kernel");
   } else {
     if ((rc = set_smem_once(attn_time_fwd_kernel<3>, smem, &done3, "attn_time_fwd")) != OAT_OK) return rc;
-    attn_time_fwd_kernel<3><<<grid, kRows, smem, s>>>(G);
+    if (launch_pdl(attn_time_fwd_kernel<3>, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_fwd_kernel");
   }
   rc = check_launch("attn_time_fwd_kernel");
   if (rc != OAT_OK || !*cls_done) return rc;
@@ -713,7 +717,7 @@ int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   static bool done = false;
   int rc = set_smem_once(attn_time_bwd_kernel, smem, &done, "attn_time_bwd");
   if (rc != OAT_OK) return rc;
-  attn_time_bwd_kernel<<<grid, kRows, smem, s>>>(G);
+  if (launch_pdl(attn_time_bwd_kernel, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_bwd_kernel");
   rc = check_launch("attn_time_bwd_kernel");
   if (rc != OAT_OK) return rc;
   attn_time_cls_finalize_kernel<<<a->B * a->H, 32, 0, s>>>(G);

@@ -1,4 +1,5 @@
 // Library-level entry points: version, error string, device check.
+#include <stdlib.h>
 #include <string.h>
 
 #include "oat_host.h"
@@ -16,6 +17,14 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(last_error_buffer(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OAT_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 
 int num_sms() {

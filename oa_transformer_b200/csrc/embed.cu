@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(512) colsum_bf16_kernel(const __nv_bfloat16* _
                                                           long long rows, int cols, float* __restrict__ out,
                                                           int rows_per_cta) {
   extern __shared__ __align__(16) uint8_t colsum_ring[];          // [kColsumRing][blockDim.x] x 16 B
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (c >= cols) return;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
@@ -572,8 +574,9 @@ extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int
   long long rows_per = (rows + k * sms - 1) / (k * sms);
   if (rows_per < 16) rows_per = 16;
   dim3 grid(static_cast<unsigned>((rows + rows_per - 1) / rows_per), static_cast<unsigned>((cols / 8 + threads - 1) / threads));
-  colsum_bf16_kernel<<<grid, threads, static_cast<size_t>(kColsumRing) * threads * 16, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows,
-                                                             cols, out, static_cast<int>(rows_per));
+  if (launch_pdl(colsum_bf16_kernel, grid, dim3(threads), static_cast<size_t>(kColsumRing) * threads * 16, as_stream(stream),
+                 reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, out, static_cast<int>(rows_per)) != cudaSuccess)
+    return check_launch("colsum_bf16_kernel");
   return check_launch("colsum_bf16_kernel");
 }
 

@@ -125,6 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int kPair = TWO ? 2 : 1;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();      // the next kernel's prologue may overlap this grid's tail (it waits before touching memory)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                // [kStages][16 KB]
   uint8_t* smem_b = smem + kStages * S::kABytes;          // [kStages][kLoadN*128 B]
@@ -167,6 +168,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (TWO) cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive
   else __syncthreads();
   tc_fence_after();
+  pdl_wait();                   // prologue done; from here on the kernel reads what earlier kernels in the stream wrote
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
   const int worker = TWO ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
@@ -706,20 +708,23 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   const long long tiles = 1LL * p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int nwork = static_cast<int>(tiles < workers ? tiles : workers);
   if constexpr (!TWO) {
-    kern<<<nwork, kGemmThreads, S::kTotal, stream>>>(ta, tb, to, tx, p);
+    cudaError_t e = launch_pdl(kern, dim3(nwork), dim3(kGemmThreads), S::kTotal, stream, ta, tb, to, tx, p);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "gemm_bf16_kernel launch: %s", cudaGetErrorString(e));
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nwork, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = S::kTotal;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p);
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "gemm_bf16_kernel (CTA pair) launch: %s", cudaGetErrorString(e));
   }

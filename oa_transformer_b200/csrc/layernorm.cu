@@ -20,6 +20,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
                      float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y_split, long long ldys,
                      long long split_period) {
   constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -187,6 +189,8 @@ layernorm_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dy_bf16, long long
                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = NV * 128;
   constexpr int kRowBytes = D * 14;
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t ln_smem[];
   float(*red)[D] = reinterpret_cast<float(*)[D]>(ln_smem);                       // [kLnWarps][D]
   float* s_gamma = reinterpret_cast<float*>(ln_smem + kLnWarps * D * 4);           // [D]
@@ -309,10 +313,10 @@ static int launch_ln_fwd(const float* x, long long ldx, const float* gamma, cons
                          long long rows, void* y_bf16, long long ldy, float* y_f32, long long ldyf, float* mean,
                          float* rstd, void* y_split, long long ldys, long long split_period, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
-  layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, s>>>(x, ldx, gamma, beta, eps, rows,
-                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, y_f32, ldyf,
-                                                          mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_split), ldys,
-                                                          split_period);
+  cudaError_t e = launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(kLnWarps * 32), 0, s, x, ldx, gamma, beta, eps, rows,
+                             reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, y_f32, ldyf, mean, rstd,
+                             reinterpret_cast<__nv_bfloat16*>(y_split), ldys, split_period);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "layernorm_fwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("layernorm_fwd_kernel");
 }
 
@@ -338,9 +342,11 @@ static int launch_ln_bwd(const void* dyb, long long lddyb, const float* dyf, lon
     }
     const long long cap1 = static_cast<long long>(num_sms());
     const unsigned grid1 = static_cast<unsigned>(want < cap1 ? want : cap1);
-    layernorm_bwd_staged_kernel<NV><<<grid1, kLnWarps * 32, smem, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dyb), lddyb, dyf, lddyf, x, ldx, mean, rstd, gamma, rows, add1, add2,
-        ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, dxsum);
+    cudaError_t e = launch_pdl(layernorm_bwd_staged_kernel<NV>, dim3(grid1), dim3(kLnWarps * 32), smem, s,
+                               reinterpret_cast<const __nv_bfloat16*>(dyb), lddyb, dyf, lddyf, x, ldx, mean, rstd, gamma,
+                               rows, add1, add2, ldadd, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma,
+                               dbeta, dxsum);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "layernorm_bwd_staged_kernel launch: %s", cudaGetErrorString(e));
     return check_launch("layernorm_bwd_staged_kernel");
   }
   const long long cap = static_cast<long long>(num_sms()) * 8;

@@ -22,6 +22,26 @@ inline cudaStream_t as_stream(oat_stream_t s) { return reinterpret_cast<cudaStre
 
 int num_sms();
 
+// OAT_PDL=0 turns programmatic dependent launch off (plain stream order).
+bool pdl_enabled();
+
+// Launch `kern` so that it may overlap its prologue with the tail of the previous kernel in the stream (the kernel must
+// call pdl_wait() before its first global access - oat_ptx.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace oat
 
 #define OAT_REQUIRE(cond, ...)                                        \

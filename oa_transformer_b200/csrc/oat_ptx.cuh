@@ -278,6 +278,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute (oat_host.h: launch_pdl) may become resident
+// while its predecessor in the stream is still draining: its prologue (barrier init, TMEM allocation, shared-memory
+// clears, descriptor prefetch) then overlaps the predecessor's tail. pdl_wait() blocks until the predecessor grid has
+// completed and its memory is visible - it must precede every global access; pdl_launch_dependents() tells the runtime
+// that the NEXT kernel in the stream may start being scheduled once every CTA of this grid has issued it (or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
