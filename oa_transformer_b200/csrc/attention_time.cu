@@ -252,8 +252,11 @@ __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGe
   uint8_t* Vs = Ks + kArr;
   uint8_t* Cm = Vs + kArr;                                     // 3 CLS matrices [8][128 B]: q, k, v
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bh = blockIdx.x / G.chunks, chunk = blockIdx.x - bh * G.chunks;
-  const int b = bh / G.H, h = bh - b * G.H;
+  // head-fastest block order: the H CTAs that read the 128-byte head slices of the SAME token rows (one 4.6 KB qkv row
+  // holds all heads) are neighbours in launch order, so they hit the same DRAM pages at about the same time
+  const int h = blockIdx.x % G.H, rest_ = blockIdx.x / G.H;
+  const int chunk = rest_ % G.chunks, b = rest_ / G.chunks;
+  const int bh = b * G.H + h;
   const int HD3 = G.H * TD;
   const long long row0 = static_cast<long long>(b) * G.T;
   const __nv_bfloat16* base = G.qkv + row0 * G.ld_qkv + h * TD;
@@ -440,8 +443,11 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   float* sDelta = sLse + kRows;                                             // [kRows]
   float* sAcc = sDelta + kRows;                                             // [3][64]: dq_cls, dk_cls, dv_cls
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bh = blockIdx.x / G.chunks, chunk = blockIdx.x - bh * G.chunks;
-  const int b = bh / G.H, h = bh - b * G.H;
+  // head-fastest block order: the H CTAs that read the 128-byte head slices of the SAME token rows (one 4.6 KB qkv row
+  // holds all heads) are neighbours in launch order, so they hit the same DRAM pages at about the same time
+  const int h = blockIdx.x % G.H, rest_ = blockIdx.x / G.H;
+  const int chunk = rest_ % G.chunks, b = rest_ / G.chunks;
+  const int bh = b * G.H + h;
   const int HD3 = G.H * TD;
   const long long row0 = static_cast<long long>(b) * G.T;
   const __nv_bfloat16* base = G.qkv + row0 * G.ld_qkv + h * TD;

@@ -22,7 +22,7 @@ inline cudaStream_t as_stream(oat_stream_t s) { return reinterpret_cast<cudaStre
 
 int num_sms();
 
-// OAT_PDL=0 turns programmatic dependent launch off (plain stream order).
+// OAT_PDL=1 turns programmatic dependent launch on (default: plain stream order; measured no gain, see common.cu).
 bool pdl_enabled();
 
 // Launch `kern` so that it may overlap its prologue with the tail of the previous kernel in the stream (the kernel must
