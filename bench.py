@@ -450,9 +450,24 @@ def run_ours(args):
             for _ in range(n):
                 yield host
 
+        host_ms = {"stage_next_batch": 0.0, "enqueue_step": 0.0, "wait_for_loss": 0.0}
+
         def run_e2e(n):
-            for data in DevicePrefetcher(host_batches(n), device):
-                float(step(data).detach().item())        # D2H read of the loss closes the step
+            it = iter(DevicePrefetcher(host_batches(n), device))
+            while True:
+                t0 = time.perf_counter()
+                try:
+                    data = next(it)                       # waits for nothing: enqueues the H2D copies of the NEXT batch
+                except StopIteration:
+                    break
+                t1 = time.perf_counter()
+                loss = step(data)
+                t2 = time.perf_counter()
+                float(loss.detach().item())               # D2H read of the loss closes the step
+                t3 = time.perf_counter()
+                host_ms["stage_next_batch"] += (t1 - t0) * 1e3
+                host_ms["enqueue_step"] += (t2 - t1) * 1e3
+                host_ms["wait_for_loss"] += (t3 - t2) * 1e3
 
         run_e2e(2)
         barrier()
@@ -466,6 +481,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         h2d_ms = c0.elapsed_time(c1) / 3
         barrier()
+        for k in host_ms:
+            host_ms[k] = 0.0
         t0 = time.perf_counter()
         e0.record()
         run_e2e(K)
@@ -478,6 +495,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / (float(t) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 4, "ms_per_step": float(t), "bare_h2d_copy_ms": h2d_ms,
+               "host_ms_per_step": {k: round(v / K, 2) for k, v in host_ms.items()},
                "h2d": "pinned host batch -> device on a copy stream, one step ahead (double-buffered), every step"}
 
     # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)
