@@ -21,6 +21,7 @@
 // The CLS query (row n of tile 1) produces one partial (max, sum, unnormalised O) per (b, h, f); a small combine
 // kernel merges the F partials (the CLS key is counted by frame 0 only).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "oat_host.h"
 #include "oat_ptx.cuh"
@@ -746,6 +747,470 @@ attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
   }
 }
 
+
+// =============================================================================================== backward, pipelined
+// Same key-major formulation as above, re-cut so that the tensor pipe, the math warps, the loads and the stores all run
+// at the same time (the kernel above runs them one after the other: measured 33 k clk per group, of which 2.4 k math +
+// 2.5 k MMA + handshakes per unit, 4 k delta prologue and 4.7 k exposed loads).
+//   * sub-unit = (key tile kt of 128 keys) x (64 queries): S^T / dP^T are N = 64 accumulators, DOUBLE-buffered in TMEM
+//     (2 x 128 columns), so the MMAs of sub-unit v+1 and the gradient MMAs of v-1 run under the math of v;
+//   * dS^T goes through a ring of four [128 keys x 64 queries] shared-memory blocks; dQ is issued once per PAIR of
+//     sub-units (M = 128 queries) from two adjacent blocks;
+//   * 16 warps: TMA producer, MMA issuer, 2 warps that prepare lse2 / delta of the NEXT group from global memory,
+//     8 math warps, 4 epilogue warps (dV, dK, dQ out of TMEM -> bf16 -> coalesced stores) that run beside the math;
+//   * operands are loaded in three phases ({K0,V0}, {Q0,dO0}, {K1,V1,Q1,dO1,CLS rows}) and released tile by tile, so
+//     the next group's first two phases land while the current group is still in its second key tile.
+// Tensor-pipe budget (scripts/probes/mma_rate_probe.cu): every M = 128 instruction with N <= 128 costs ~68 clk (the A
+// operand feed), 82 from TMEM, 88 for an MN-major A: ~11.5 k clk per group for the 160 instructions - about the time
+// HBM needs for the group's 238 KB (10.3 k clk at 1/148 of 6.4 TB/s).
+#ifdef OAT_SPACE_DBG
+__device__ long long g_dbg[8192];
+#define DBG2(it, slot) do { if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_dbg[(it) * 128 + (slot)] = clock64(); } while (0)
+#else
+#define DBG2(it, slot) do { } while (0)
+#endif
+constexpr int kB2Threads = 512;
+constexpr int kB2RingBytes = 4 * (kTileBytes);                   // dS^T ring: 4 blocks of [128 keys x 64 queries] bf16
+constexpr int kB2StageBytes = 4 * 4096;                          // epilogue staging: 32 rows x 128 B per epilogue warp
+constexpr int kB2Smem = kBwdOperandBytes + kB2RingBytes + kB2StageBytes + 4 * 256 * 4 + 1024 + 512;
+
+__global__ void __launch_bounds__(kB2Threads, 1)
+attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const __grid_constant__ CUtensorMap tmap_qkv_b,
+                          const __grid_constant__ CUtensorMap tmap_do_a, const __grid_constant__ CUtensorMap tmap_do_b,
+                          const __grid_constant__ CUtensorMap tmap_dqkv_a, const __grid_constant__ CUtensorMap tmap_dqkv_b,
+                          const SpaceBwdGeom G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + kMatBytes;
+  uint8_t* Vs = smem + 2 * kMatBytes;
+  uint8_t* Ds = smem + 3 * kMatBytes;                                   // dO
+  uint8_t* ring = smem + kBwdOperandBytes;                              // dS^T blocks
+  uint8_t* stage = ring + kB2RingBytes;                                 // epilogue staging
+  float* lse2_s = reinterpret_cast<float*>(stage + kB2StageBytes);      // [2][256]
+  float* del_s = lse2_s + 512;                                          // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(del_s + 512);
+  uint64_t* full = bars;             // [3] producer -> MMA: load phases A, B, C of a group
+  uint64_t* empty = bars + 3;        // [3] MMA -> producer
+  uint64_t* st_full = bars + 6;      // [2] MMA -> math: S^T, dP^T of a sub-unit ready (per TMEM buffer)
+  uint64_t* math_done = bars + 8;    // [2] math -> MMA: P^T in TMEM, dS^T in the ring
+  uint64_t* acc_full = bars + 10;    // MMA -> epilogue: dV, dK of a key tile complete
+  uint64_t* acc_free = bars + 11;    // epilogue -> MMA
+  uint64_t* dq_full = bars + 12;     // [2] MMA -> epilogue: dQ of query half 0 (after sub-unit 5) / 1 (after 7) complete
+  uint64_t* dq_free = bars + 14;     // [2] epilogue -> MMA
+  uint64_t* dl_full = bars + 16;     // [2] delta warps -> math: lse2 / delta of a group ready
+  uint64_t* dl_free = bars + 18;     // [2] math -> delta warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HDIM = G.H * SD;
+  const int n = G.n;
+  const int rem = n - 128;           // token rows of the second tile (the CLS row follows them)
+  pdl_launch_dependents();
+
+  for (int i = tid; i < (kBwdOperandBytes + kB2RingBytes) / 16; i += kB2Threads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qkv_a); tma_prefetch_desc(&tmap_qkv_b);
+      tma_prefetch_desc(&tmap_do_a); tma_prefetch_desc(&tmap_do_b);
+      tma_prefetch_desc(&tmap_dqkv_a); tma_prefetch_desc(&tmap_dqkv_b);
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else if (warp == 1 && lane == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 2);
+    for (int k = 0; k < 3; ++k) mbar_init(&empty[k], 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&st_full[k], 1);
+      mbar_init(&math_done[k], 8);
+      mbar_init(&dl_full[k], 2);
+      mbar_init(&dl_free[k], 8);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_free, 4);
+    for (int k = 0; k < 2; ++k) { mbar_init(&dq_full[k], 1); mbar_init(&dq_free[k], 4); }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const int row0 = b * G.T + 1 + f * n;
+      const uint32_t pe = (i & 1) ^ 1;
+      mbar_wait(&empty[0], pe);
+      DBG2(i, 100);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[0], 2u * kTileBytes);
+        tma_load_2d(Ks, &tmap_qkv_a, &full[0], HDIM + h * SD, row0);
+        tma_load_2d(Vs, &tmap_qkv_a, &full[0], 2 * HDIM + h * SD, row0);
+      }
+      mbar_wait(&empty[1], pe);
+      DBG2(i, 101);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[1], 2u * kTileBytes);
+        tma_load_2d(Qs, &tmap_qkv_a, &full[1], h * SD, row0);
+        tma_load_2d(Ds, &tmap_do_a, &full[1], h * SD, row0);
+      }
+      mbar_wait(&empty[2], pe);
+      DBG2(i, 102);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[2], 4u * rem * 128u);
+        if (rem > 0) {
+          tma_load_2d(Ks + kTileBytes, &tmap_qkv_b, &full[2], HDIM + h * SD, row0 + 128);
+          tma_load_2d(Vs + kTileBytes, &tmap_qkv_b, &full[2], 2 * HDIM + h * SD, row0 + 128);
+          tma_load_2d(Qs + kTileBytes, &tmap_qkv_b, &full[2], h * SD, row0 + 128);
+          tma_load_2d(Ds + kTileBytes, &tmap_do_b, &full[2], h * SD, row0 + 128);
+        }
+      }
+      {
+        // CLS token rows (q, k, v, dO) -> row n of each operand
+        const int m = lane >> 3, c = lane & 7;
+        const __nv_bfloat16* src = (m < 3)
+            ? G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + m * HDIM + h * SD + c * 8
+            : G.dout + static_cast<long long>(b) * G.T * G.ld_dout + h * SD + c * 8;
+        const uint4 val = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>(smem + m * kMatBytes + n * 128 + ((c ^ (n & 7)) << 4)) = val;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[2]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // One thread feeds ~160 instructions per group to the tensor pipe, which needs ~70 clk for each: the issue path
+    // itself has to stay well under that. The eight sub-units of a group are unrolled, so every operand offset, TMEM
+    // column and barrier parity below is a compile-time constant added to a descriptor built once.
+    constexpr uint32_t idesc_sd = make_idesc_bf16(128, 64, 0u, 0u);    // S^T, dP^T: both operands K-major
+    constexpr uint32_t idesc_kn = make_idesc_bf16(128, SD, 0u, 1u);    // dV, dK: A K-major (TMEM / smem), B MN-major
+    constexpr uint32_t idesc_mn = make_idesc_bf16(128, SD, 1u, 1u);    // dQ: A MN-major smem, B MN-major
+    const uint64_t kK = make_smem_desc_sw128(smem_u32(Ks), 0, 1024), kV = make_smem_desc_sw128(smem_u32(Vs), 0, 1024),
+                   kQ = make_smem_desc_sw128(smem_u32(Qs), 0, 1024), kD = make_smem_desc_sw128(smem_u32(Ds), 0, 1024),
+                   kR = make_smem_desc_sw128(smem_u32(ring), 0, 1024);
+    const uint64_t mK = make_smem_desc_sw128(smem_u32(Ks), kMatBytes, 1024), mQ = make_smem_desc_sw128(smem_u32(Qs), kMatBytes, 1024),
+                   mD = make_smem_desc_sw128(smem_u32(Ds), kMatBytes, 1024),
+                   mR = make_smem_desc_sw128(smem_u32(ring), kTileBytes, 1024);
+    // This CTA owns the SM's whole tensor memory (512 columns, 1 CTA / SM), so the allocation starts at column 0, lane 0.
+    // Using the literal address keeps every tcgen05.mma operand in uniform registers: with a base loaded from shared
+    // memory the compiler wraps each instruction in an elect / R2UR.BROADCAST loop (~9 instructions per MMA), and the
+    // issue thread, not the tensor pipe, sets the pace of these 67-clock instructions.
+    if (tmem_base != 0) __trap();
+    constexpr uint32_t tmem0 = 0;
+    constexpr uint32_t t_dv = tmem0 + 256, t_dk = tmem0 + 320, t_dq = tmem0 + 384;
+    const int my_groups = (G.groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto off = [](uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); };   // start-address field: bits [0, 14)
+
+    // S^T and dP^T of sub-unit v of group iteration `it` into TMEM buffer v & 1
+    auto issue_sdp = [&](int it, int v) {
+      const int kt = v >> 2, qq = v & 3;
+      DBG2(it, v * 4 + 0);
+      if (v == 0) { mbar_wait(&full[0], it & 1); mbar_wait(&full[1], it & 1); }
+      if (v == 2) mbar_wait(&full[2], it & 1);
+      DBG2(it, v * 4 + 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t t_s = tmem0 + (v & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(t_s, off(kK, kt * kTileBytes + k * 32), off(kQ, qq * 8192 + k * 32), idesc_sd, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(t_s + 64, off(kV, kt * kTileBytes + k * 32), off(kD, qq * 8192 + k * 32), idesc_sd, k > 0 ? 1u : 0u);
+        tc_commit(&st_full[v & 1]);
+      }
+      __syncwarp();
+    };
+    // gradient products of sub-unit v
+    auto issue_grads = [&](int it, int v) {
+      const int kt = v >> 2, qq = v & 3;
+      DBG2(it, v * 4 + 2);
+      mbar_wait(&math_done[v & 1], (v >> 1) & 1);
+      DBG2(it, v * 4 + 3);
+      if (qq == 0) mbar_wait(acc_free, (kt & 1) ^ 1);   // the first accumulation into dV / dK of a key tile overwrites them
+      if (kt == 0 && (qq & 1)) mbar_wait(&dq_free[qq >> 1], (it & 1) ^ 1);   // ... and so does the first one into a dQ half
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t t_p = tmem0 + (v & 1) * 128;               // P^T (bf16): queries 0..31 at +0, 32..63 at +32
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {                           // k = 16 queries per step
+          const uint32_t first = (qq > 0 || ks > 0) ? 1u : 0u;
+          tc_mma_bf16_ts(t_dv, t_p + (ks < 2 ? ks * 8 : 32 + (ks - 2) * 8), off(mD, (qq * 64 + ks * 16) * 128), idesc_kn, first);
+          tc_mma_bf16(t_dk, off(kR, (v & 3) * kTileBytes + ks * 32), off(mQ, (qq * 64 + ks * 16) * 128), idesc_kn, first);
+        }
+        if (qq & 1) {                                              // dQ of the pair (v - 1, v): 128 queries
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)                           // k = 16 keys per step, A = dS^T read MN-major
+            tc_mma_bf16(t_dq + (qq >> 1) * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
+                        off(mK, (kt * 128 + ks * 16) * 128), idesc_mn, (kt > 0 || ks > 0) ? 1u : 0u);
+        }
+        if (qq == 3) tc_commit(acc_full);
+        if (v == 3) tc_commit(&empty[0]);
+        if (v == 5) { tc_commit(&dq_full[0]); tc_commit(&empty[1]); }
+        if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty[2]); }
+      }
+      __syncwarp();
+    };
+    if (my_groups > 0) issue_sdp(0, 0);
+    for (int it = 0; it < my_groups; ++it) {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) {
+        issue_sdp(it, v + 1);
+        issue_grads(it, v);
+      }
+      if (it + 1 < my_groups) {
+        // the next sub-unit opens a new group: if its operands have not landed yet, do not hold this group's last
+        // gradient products back
+        bool first = mbar_try_wait(&full[0], (it + 1) & 1) && mbar_try_wait(&full[1], (it + 1) & 1);
+        first = __shfl_sync(0xffffffffu, first ? 1 : 0, 0) != 0;
+        if (first) { issue_sdp(it + 1, 0); issue_grads(it, 7); }
+        else { issue_grads(it, 7); issue_sdp(it + 1, 0); }
+      } else {
+        issue_grads(it, 7);
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ lse2 / delta of the next group (global only)
+    const int t64 = (warp - 2) * 32 + lane;
+    const int part = t64 & 3, rsub = t64 >> 2;                    // 4 threads per query row, 16 rows per pass
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const long long tok_base = static_cast<long long>(b) * G.T;
+      const long long tok0 = tok_base + 1 + f * n;
+      mbar_wait(&dl_free[i & 1], ((i >> 1) & 1) ^ 1);
+      if (warp == 2) DBG2(i, 60);
+      float* l2 = lse2_s + (i & 1) * 256;
+      float* dl = del_s + (i & 1) * 256;
+      const float* lse_g = G.lse + (static_cast<long long>(b) * G.H + h) * G.T;
+#pragma unroll 1
+      for (int p0 = 0; p0 < 16; p0 += 4) {
+        // 4 rows per thread in flight: all 17 loads of a batch are issued before the first use (no branches: rows past
+        // the CLS query row are clamped onto it and zeroed afterwards)
+        uint4 o[4][2], d[4][2];
+        float lv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = (p0 + u) * 16 + rsub;
+          const int rc = r < n ? r : n;
+          const long long tok = (rc == n) ? tok_base : tok0 + rc;
+          const __nv_bfloat16* op = G.out + tok * G.ld_out + h * SD + part * 16;
+          const __nv_bfloat16* dp = G.dout + tok * G.ld_dout + h * SD + part * 16;
+          o[u][0] = __ldg(reinterpret_cast<const uint4*>(op));
+          o[u][1] = __ldg(reinterpret_cast<const uint4*>(op + 8));
+          d[u][0] = __ldg(reinterpret_cast<const uint4*>(dp));
+          d[u][1] = __ldg(reinterpret_cast<const uint4*>(dp + 8));
+          lv[u] = __ldg(lse_g + (tok - tok_base));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = (p0 + u) * 16 + rsub;
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t ow[4] = {o[u][k].x, o[u][k].y, o[u][k].z, o[u][k].w};
+            const uint32_t dw[4] = {d[u][k].x, d[u][k].y, d[u][k].z, d[u][k].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16x2(ow[e]), y = unpack_bf16x2(dw[e]);
+              acc = fmaf(x.x, y.x, acc);
+              acc = fmaf(x.y, y.y, acc);
+            }
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          if (part == 0) {
+            dl[r] = r <= n ? acc : 0.f;
+            l2[r] = r <= n ? lv[u] * kLog2e : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if (warp == 2) DBG2(i, 61);
+      if (lane == 0) mbar_arrive(&dl_full[i & 1]);
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ math warps
+    const int q4 = warp & 3;                  // TMEM lane quarter
+    const int hh = (warp - 4) >> 2;           // which 32-query half of a sub-unit
+    const int r_tile = q4 * 32 + lane;        // key row inside the key tile
+    const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
+    const int sw = r_tile & 7;
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int f = (g / G.H) % G.F;
+      const float* l2 = lse2_s + (i & 1) * 256;
+      const float* dl = del_s + (i & 1) * 256;
+      mbar_wait(&dl_full[i & 1], (i >> 1) & 1);
+#pragma unroll 1
+      for (int v = 0; v < 8; ++v) {
+        const int vg = i * 8 + v, kt = v >> 2, qq = v & 3;
+        const int key = kt * 128 + r_tile;
+        // the (CLS query, CLS key) cell is counted by frame 0 only
+        const int kill = (key == n && f != 0) ? n : -1;
+        const uint32_t t_s = tmem_base + lane_off + (vg & 1) * 128 + hh * 32;
+        uint8_t* ds_row = ring + (vg & 3) * kTileBytes + r_tile * 128;
+        if (warp == 4) DBG2(i, 32 + v * 3);
+        mbar_wait(&st_full[vg & 1], (vg >> 1) & 1);
+        if (warp == 4) DBG2(i, 33 + v * 3);
+        tc_fence_after();
+        uint32_t sv[2][16], dv[2][16];
+        tmem_ld_32x32b_x16(t_s, sv[0]);
+        tmem_ld_32x32b_x16(t_s + 64, dv[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c == 0) {
+            tmem_ld_32x32b_x16(t_s + 16, sv[1]);
+            tmem_ld_32x32b_x16(t_s + 64 + 16, dv[1]);
+          } else {
+            tmem_ld_wait();
+          }
+          const int qa0 = qq * 64 + hh * 32 + c * 16;
+          float pv[16], dsv[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 16; e4 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(l2 + qa0 + e4);
+            const float4 d4 = *reinterpret_cast<const float4*>(dl + qa0 + e4);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float p = ex2_approx(fmaf(__uint_as_float(sv[c][e4 + k]), kLog2e, -ls[k]));
+              pv[e4 + k] = p;
+              dsv[e4 + k] = p * (__uint_as_float(dv[c][e4 + k]) - dd[k]);
+            }
+          }
+          if (kill >= qa0 && kill < qa0 + 16) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (qa0 + e == kill) { pv[e] = 0.f; dsv[e] = 0.f; }
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
+          tmem_st_32x32b_x8(t_s + c * 8, pk);
+#pragma unroll
+          for (int c4 = 0; c4 < 2; ++c4) {
+            uint4 w;
+            w.x = pack_bf16x2(dsv[8 * c4 + 0], dsv[8 * c4 + 1]);
+            w.y = pack_bf16x2(dsv[8 * c4 + 2], dsv[8 * c4 + 3]);
+            w.z = pack_bf16x2(dsv[8 * c4 + 4], dsv[8 * c4 + 5]);
+            w.w = pack_bf16x2(dsv[8 * c4 + 6], dsv[8 * c4 + 7]);
+            *reinterpret_cast<uint4*>(ds_row + (((hh * 4 + c * 2 + c4) ^ sw) << 4)) = w;
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (warp == 4) DBG2(i, 34 + v * 3);
+        if (lane == 0) mbar_arrive(&math_done[vg & 1]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dl_free[i & 1]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: dV, dK per key tile, dQ per group
+    const int q4 = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
+    uint8_t* stg = stage + q4 * 4096;
+    const int s7 = lane & 7;
+    // one 64-column accumulator of this warp's 32 rows: TMEM -> registers (bf16 pairs), fp32 row kept for the CLS atomics
+    auto drain = [&](uint32_t taddr, float sc, uint32_t (&pk)[32], float* cls_dst) {
+      uint32_t a[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        tmem_ld_32x32b_x32(taddr + hf * 32, a);
+        tmem_ld_wait();
+        if (cls_dst != nullptr) {
+#pragma unroll
+          for (int d = 0; d < 32; ++d) atomicAdd(cls_dst + hf * 32 + d, __uint_as_float(a[d]) * sc);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          pk[hf * 16 + e] = pack_bf16x2(__uint_as_float(a[2 * e]) * sc, __uint_as_float(a[2 * e + 1]) * sc);
+      }
+    };
+    // 32 rows x 128 B into the warp's staging rows (128B swizzle), then ONE bulk-tensor store of the rows that are token
+    // rows of this group (whole 32-row box, or the n % 32 row box for the tile that the CLS row cuts)
+    auto store_rows = [&](const uint32_t (&pk)[32], int col, int row_global, int row_first) {
+      if (lane == 0) bulk_wait_read<0>();        // the previous store has finished reading the staging rows
+      __syncwarp();
+      uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(rowp + ((c ^ s7) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (row_first + 32 <= n) tma_store_2d(&tmap_dqkv_a, stg, col, row_global);
+        else if (row_first < n) tma_store_2d(&tmap_dqkv_b, stg, col, row_global);
+        bulk_commit();
+      }
+    };
+    int i = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+      const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
+      const int row0 = b * G.T + 1 + f * n;
+      float* cls = G.cls_acc != nullptr ? G.cls_acc + (static_cast<long long>(b) * G.H + h) * 3 * SD : nullptr;
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        const int row_first = kt * 128 + q4 * 32;
+        const bool is_cls = (row_first + lane == n) && cls != nullptr;
+        uint32_t pv[32], pk[32];
+        if (kt == 1) {
+          // query half 0 of dQ has been complete since sub-unit 5: it goes out while the second key tile is finished
+          mbar_wait(&dq_full[0], i & 1);
+          tc_fence_after();
+          drain(tmem_base + lane_off + 384, G.scale, pv, (q4 * 32 + lane == n && cls != nullptr) ? cls : nullptr);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dq_free[0]);
+          store_rows(pv, h * SD, row0 + q4 * 32, q4 * 32);
+        }
+        mbar_wait(acc_full, kt & 1);
+        if (warp == 12) DBG2(i, 64 + kt * 3);
+        tc_fence_after();
+        drain(tmem_base + lane_off + 256, 1.0f, pv, is_cls ? cls + 2 * SD : nullptr);
+        drain(tmem_base + lane_off + 320, 1.0f, pk, is_cls ? cls + SD : nullptr);
+        tc_fence_before();
+        __syncwarp();
+        if (warp == 12) DBG2(i, 65 + kt * 3);
+        if (lane == 0) mbar_arrive(acc_free);
+        store_rows(pv, 2 * HDIM + h * SD, row0 + row_first, row_first);
+        store_rows(pk, HDIM + h * SD, row0 + row_first, row_first);
+        if (warp == 12) DBG2(i, 66 + kt * 3);
+      }
+      {
+        uint32_t p1[32];
+        mbar_wait(&dq_full[1], i & 1);
+        if (warp == 12) DBG2(i, 70);
+        tc_fence_after();
+        drain(tmem_base + lane_off + 448, G.scale, p1, (128 + q4 * 32 + lane == n && cls != nullptr) ? cls : nullptr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_free[1]);
+        store_rows(p1, h * SD, row0 + 128 + q4 * 32, 128 + q4 * 32);
+        if (warp == 12) DBG2(i, 71);
+      }
+    }
+    if (lane == 0) bulk_wait<0>();               // all stores complete before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 bool space_tc_fwd_supported(const oat_attn_args* a) {
@@ -802,22 +1267,51 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
   G.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
   G.cls_acc = a->cls_acc;
   G.scale = a->scale;
-  CUtensorMap tq, td;
-  int rc = make_tmap_bf16_2d(&tq, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, a->n);
-  if (rc != OAT_OK) return rc;
-  rc = make_tmap_bf16_2d(&td, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, a->n);
-  if (rc != OAT_OK) return rc;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_space_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd smem attr: %s", cudaGetErrorString(e));
-    done = true;
-  }
   const int sms = num_sms();
   const int grid = G.groups < sms ? G.groups : sms;
-  cudaError_t e = launch_pdl(attn_space_tc_bwd_kernel, dim3(grid), dim3(kSpThreads), kBwdSmem, s, tq, td, G);
-  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd_kernel launch: %s", cudaGetErrorString(e));
-  return check_launch("attn_space_tc_bwd_kernel");
+  static const bool legacy = getenv("OAT_SPACE_BWD_V1") != nullptr;
+  if (legacy) {
+    CUtensorMap tq, td;
+    int rc = make_tmap_bf16_2d(&tq, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, a->n);
+    if (rc != OAT_OK) return rc;
+    rc = make_tmap_bf16_2d(&td, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, a->n);
+    if (rc != OAT_OK) return rc;
+    static bool done = false;
+    if (!done) {
+      cudaError_t e = cudaFuncSetAttribute(attn_space_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+      if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd smem attr: %s", cudaGetErrorString(e));
+      done = true;
+    }
+    cudaError_t e = launch_pdl(attn_space_tc_bwd_kernel, dim3(grid), dim3(kSpThreads), kBwdSmem, s, tq, td, G);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd_kernel launch: %s", cudaGetErrorString(e));
+    return check_launch("attn_space_tc_bwd_kernel");
+  }
+  // pipelined kernel: token rows [0, 128) and [128, n) of a group are separate boxes (tiles are released one by one)
+  CUtensorMap tqa, tqb, tda, tdb, tsa, tsb;
+  const int rem = a->n > 128 ? a->n - 128 : 1;
+  const int tail = (a->n & 31) ? (a->n & 31) : 32;
+  int rc = make_tmap_bf16_2d(&tqa, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, 128);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tqb, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, rem);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tda, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, 128);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tdb, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, rem);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tsa, a->dqkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_dqkv, 32);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tsb, a->dqkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_dqkv, tail);
+  if (rc != OAT_OK) return rc;
+  static bool done2 = false;
+  if (!done2) {
+    cudaError_t e = cudaFuncSetAttribute(attn_space_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2Smem);
+    if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2 smem attr: %s", cudaGetErrorString(e));
+    done2 = true;
+  }
+  cudaError_t e = launch_pdl(attn_space_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, s, tqa, tqb, tda, tdb, tsa, tsb, G);
+  if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("attn_space_tc_bwd2_kernel");
 }
 
 }  // namespace oat
+
+#ifdef OAT_SPACE_DBG
+extern "C" int oat_debug_timeline(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, oat::g_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
