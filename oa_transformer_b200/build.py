@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 if os.environ.get("OAT_GEMM_STAGES"):       # experiment knob: TMA ring depth of the GEMM (default 4)
     NVCC_FLAGS += ["-DOAT_GEMM_STAGES=%d" % int(os.environ["OAT_GEMM_STAGES"])]
 if os.environ.get("OAT_SPACE_DBG"):         # debug knob: clock64 timeline of the pipelined space-attention backward
-    NVCC_FLAGS += ["-DOAT_SPACE_DBG"]
+    NVCC_FLAGS += ["-DOAT_SPACE_DBG=%d" % int(os.environ["OAT_SPACE_DBG"])]
 
 
 def _nvcc():

@@ -765,7 +765,11 @@ attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
 // HBM needs for the group's 238 KB (10.3 k clk at 1/148 of 6.4 TB/s).
 #ifdef OAT_SPACE_DBG
 __device__ long long g_dbg[8192];
+#if OAT_SPACE_DBG == 2   // light: one timestamp per group (slot 0 only), negligible overhead
+#define DBG2(it, slot) do { if ((slot) == 0 && blockIdx.x == 0 && lane == 0 && (it) < 8) g_dbg[(it) * 128] = clock64(); } while (0)
+#else
 #define DBG2(it, slot) do { if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_dbg[(it) * 128 + (slot)] = clock64(); } while (0)
+#endif
 #else
 #define DBG2(it, slot) do { } while (0)
 #endif
@@ -790,17 +794,17 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
   float* lse2_s = reinterpret_cast<float*>(stage + kB2StageBytes);      // [2][256]
   float* del_s = lse2_s + 512;                                          // [2][256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(del_s + 512);
-  uint64_t* full = bars;             // [3] producer -> MMA: load phases A, B, C of a group
-  uint64_t* empty = bars + 3;        // [3] MMA -> producer
-  uint64_t* st_full = bars + 6;      // [2] MMA -> math: S^T, dP^T of a sub-unit ready (per TMEM buffer)
-  uint64_t* math_done = bars + 8;    // [2] math -> MMA: P^T in TMEM, dS^T in the ring
-  uint64_t* acc_full = bars + 10;    // MMA -> epilogue: dV, dK of a key tile complete
-  uint64_t* acc_free = bars + 11;    // epilogue -> MMA
-  uint64_t* dq_full = bars + 12;     // [2] MMA -> epilogue: dQ of query half 0 (after sub-unit 5) / 1 (after 7) complete
-  uint64_t* dq_free = bars + 14;     // [2] epilogue -> MMA
-  uint64_t* dl_full = bars + 16;     // [2] delta warps -> math: lse2 / delta of a group ready
-  uint64_t* dl_free = bars + 18;     // [2] math -> delta warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* full = bars;             // [4] producer -> MMA: {K0,V0}, {Q,dO rows 0..127}, {Q,dO rows 128..}, {K1,V1}
+  uint64_t* empty = bars + 4;        // [4] MMA -> producer
+  uint64_t* st_full = bars + 8;      // [2] MMA -> math: S^T, dP^T of a sub-unit ready (per TMEM buffer)
+  uint64_t* math_done = bars + 10;   // [2] math -> MMA: P^T, dS^T in TMEM, dS^T in the ring
+  uint64_t* acc_full = bars + 12;    // MMA -> epilogue: dV, dK of a key tile complete
+  uint64_t* acc_free = bars + 13;    // epilogue -> MMA
+  uint64_t* dq_full = bars + 14;     // [2] MMA -> epilogue: dQ accumulator 1 (complete after sub-unit 5) / 0 (after 7)
+  uint64_t* dq_free = bars + 16;     // [2] epilogue -> MMA
+  uint64_t* dl_full = bars + 18;     // [2] delta warps -> math: lse2 / delta of a group ready
+  uint64_t* dl_free = bars + 20;     // [2] math -> delta warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HDIM = G.H * SD;
@@ -820,8 +824,8 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
   } else if (warp == 1 && lane == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 2);
-    for (int k = 0; k < 3; ++k) mbar_init(&empty[k], 1);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 2); mbar_init(&full[3], 2);
+    for (int k = 0; k < 4; ++k) mbar_init(&empty[k], 1);
     for (int k = 0; k < 2; ++k) {
       mbar_init(&st_full[k], 1);
       mbar_init(&math_done[k], 8);
@@ -840,11 +844,48 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    // Tile sets in the order the group needs them (see the MMA issuer for the schedule): {K0,V0}, the query half of the
+    // first query pair, the other query half, {K1,V1}. Each set is re-loaded as soon as the previous group's last
+    // instruction that reads it has retired - for the first two that is well before the previous group ends.
     int i = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
       const int row0 = b * G.T + 1 + f * n;
       const uint32_t pe = (i & 1) ^ 1;
+      const int flip = i & 1;
+      // CLS token rows -> row n of two operands: (q, dO) with query half 1, (k, v) with key tile 1
+      auto cls_rows = [&](int m_lo, int m_hi) {
+        if (lane < 16) {
+          const int m = lane < 8 ? m_lo : m_hi, c = lane & 7;
+          const __nv_bfloat16* src = (m < 3)
+              ? G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + m * HDIM + h * SD + c * 8
+              : G.dout + static_cast<long long>(b) * G.T * G.ld_dout + h * SD + c * 8;
+          const uint4 val = *reinterpret_cast<const uint4*>(src);
+          *reinterpret_cast<uint4*>(smem + m * kMatBytes + n * 128 + ((c ^ (n & 7)) << 4)) = val;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      };
+      auto load_qd = [&](int half) {
+        mbar_wait(&empty[1 + half], pe);
+        if (half == 0) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[1], 2u * kTileBytes);
+            tma_load_2d(Qs, &tmap_qkv_a, &full[1], h * SD, row0);
+            tma_load_2d(Ds, &tmap_do_a, &full[1], h * SD, row0);
+          }
+        } else {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[2], 2u * rem * 128u);
+            if (rem > 0) {
+              tma_load_2d(Qs + kTileBytes, &tmap_qkv_b, &full[2], h * SD, row0 + 128);
+              tma_load_2d(Ds + kTileBytes, &tmap_do_b, &full[2], h * SD, row0 + 128);
+            }
+          }
+          cls_rows(0, 3);
+          if (lane == 0) mbar_arrive(&full[2]);
+        }
+      };
       mbar_wait(&empty[0], pe);
       DBG2(i, 100);
       if (lane == 0) {
@@ -852,36 +893,20 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         tma_load_2d(Ks, &tmap_qkv_a, &full[0], HDIM + h * SD, row0);
         tma_load_2d(Vs, &tmap_qkv_a, &full[0], 2 * HDIM + h * SD, row0);
       }
-      mbar_wait(&empty[1], pe);
+      load_qd(flip);
       DBG2(i, 101);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full[1], 2u * kTileBytes);
-        tma_load_2d(Qs, &tmap_qkv_a, &full[1], h * SD, row0);
-        tma_load_2d(Ds, &tmap_do_a, &full[1], h * SD, row0);
-      }
-      mbar_wait(&empty[2], pe);
+      load_qd(flip ^ 1);
       DBG2(i, 102);
+      mbar_wait(&empty[3], pe);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&full[2], 4u * rem * 128u);
+        mbar_arrive_expect_tx(&full[3], 2u * rem * 128u);
         if (rem > 0) {
-          tma_load_2d(Ks + kTileBytes, &tmap_qkv_b, &full[2], HDIM + h * SD, row0 + 128);
-          tma_load_2d(Vs + kTileBytes, &tmap_qkv_b, &full[2], 2 * HDIM + h * SD, row0 + 128);
-          tma_load_2d(Qs + kTileBytes, &tmap_qkv_b, &full[2], h * SD, row0 + 128);
-          tma_load_2d(Ds + kTileBytes, &tmap_do_b, &full[2], h * SD, row0 + 128);
+          tma_load_2d(Ks + kTileBytes, &tmap_qkv_b, &full[3], HDIM + h * SD, row0 + 128);
+          tma_load_2d(Vs + kTileBytes, &tmap_qkv_b, &full[3], 2 * HDIM + h * SD, row0 + 128);
         }
       }
-      {
-        // CLS token rows (q, k, v, dO) -> row n of each operand
-        const int m = lane >> 3, c = lane & 7;
-        const __nv_bfloat16* src = (m < 3)
-            ? G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + m * HDIM + h * SD + c * 8
-            : G.dout + static_cast<long long>(b) * G.T * G.ld_dout + h * SD + c * 8;
-        const uint4 val = *reinterpret_cast<const uint4*>(src);
-        *reinterpret_cast<uint4*>(smem + m * kMatBytes + n * 128 + ((c ^ (n & 7)) << 4)) = val;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[2]);
+      cls_rows(1, 2);
+      if (lane == 0) mbar_arrive(&full[3]);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -907,73 +932,93 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     const int my_groups = (G.groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto off = [](uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); };   // start-address field: bits [0, 14)
 
+    // Schedule of a group: sub-unit v = (key tile v >> 2) x (64 queries). The four 128-query steps visit the query
+    // halves in the order 0 1 1 0 in even group iterations and 1 0 0 1 in odd ones (kQH ^ flip): the operand tiles a
+    // group reads first ({K0,V0} and its first query half) are then exactly the ones the previous group stopped reading
+    // two steps / one step before its end, so their loads are never exposed, and the tiles released last ({K1,V1} and
+    // the other query half) are needed one and two steps into the next group.
     // S^T and dP^T of sub-unit v of group iteration `it` into TMEM buffer v & 1
     auto issue_sdp = [&](int it, int v) {
-      const int kt = v >> 2, qq = v & 3;
+      const int kt = v >> 2, slot = (0x6 >> (v >> 1)) & 1, flip = it & 1;      // slot: 0 1 1 0
+      const uint32_t qoff = static_cast<uint32_t>(((slot ^ flip) * 2 + (v & 1)) * 8192);
       DBG2(it, v * 4 + 0);
-      if (v == 0) { mbar_wait(&full[0], it & 1); mbar_wait(&full[1], it & 1); }
-      if (v == 2) mbar_wait(&full[2], it & 1);
+      if (v == 0) { mbar_wait(&full[0], it & 1); mbar_wait(&full[1 + flip], it & 1); }
+      if (v == 2) mbar_wait(&full[2 - flip], it & 1);
+      if (v == 4) mbar_wait(&full[3], it & 1);
       DBG2(it, v * 4 + 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t t_s = tmem0 + (v & 1) * 128;
+        const uint64_t bq = off(kQ, qoff), bd = off(kD, qoff);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(t_s, off(kK, kt * kTileBytes + k * 32), off(kQ, qq * 8192 + k * 32), idesc_sd, k > 0 ? 1u : 0u);
+          tc_mma_bf16(t_s, off(kK, kt * kTileBytes + k * 32), bq + k * 2, idesc_sd, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(t_s + 64, off(kV, kt * kTileBytes + k * 32), off(kD, qq * 8192 + k * 32), idesc_sd, k > 0 ? 1u : 0u);
+          tc_mma_bf16(t_s + 64, off(kV, kt * kTileBytes + k * 32), bd + k * 2, idesc_sd, k > 0 ? 1u : 0u);
         tc_commit(&st_full[v & 1]);
       }
       __syncwarp();
+      DBG2(it, 88 + v);
     };
-    // gradient products of sub-unit v
-    auto issue_grads = [&](int it, int v) {
-      const int kt = v >> 2, qq = v & 3;
+    // Gradient products of sub-unit v, with S^T / dP^T of sub-unit v + 2 (same TMEM buffer) slipped in right behind the
+    // eight dV / dK instructions that read P^T / dS^T out of that buffer (A operands from TMEM: no shared-memory
+    // fetch); the dQ products run under the math warps' next sub-unit.
+    auto issue_grads = [&](int it, int v, bool more) {
+      const int kt = v >> 2, slot = (0x6 >> (v >> 1)) & 1, flip = it & 1;
+      const uint32_t qoff = static_cast<uint32_t>(((slot ^ flip) * 2 + (v & 1)) * 8192);
       DBG2(it, v * 4 + 2);
       mbar_wait(&math_done[v & 1], (v >> 1) & 1);
       DBG2(it, v * 4 + 3);
-      if (qq == 0) mbar_wait(acc_free, (kt & 1) ^ 1);   // the first accumulation into dV / dK of a key tile overwrites them
-      if (kt == 0 && (qq & 1)) mbar_wait(&dq_free[qq >> 1], (it & 1) ^ 1);   // ... and so does the first one into a dQ half
+      if ((v & 3) == 0) mbar_wait(acc_free, (kt & 1) ^ 1);       // the first accumulation into dV / dK of a key tile overwrites them
+      if (v == 1) mbar_wait(&dq_free[1], (it & 1) ^ 1);           // ... and so does the first one into a dQ accumulator
+      if (v == 3) mbar_wait(&dq_free[0], (it & 1) ^ 1);
+      DBG2(it, 104 + v);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t t_p = tmem0 + (v & 1) * 128;               // P^T (bf16): queries 0..31 at +0, 32..63 at +32
+      const uint32_t t_p = tmem0 + (v & 1) * 128;                 // P^T (bf16): queries 0..31 at +0, 32..63 at +32; dS^T at +64
+      if (elect_one()) {
+        const uint64_t bd = off(mD, qoff), bq = off(mQ, qoff);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {                           // k = 16 queries per step
-          const uint32_t first = (qq > 0 || ks > 0) ? 1u : 0u;
-          tc_mma_bf16_ts(t_dv, t_p + (ks < 2 ? ks * 8 : 32 + (ks - 2) * 8), off(mD, (qq * 64 + ks * 16) * 128), idesc_kn, first);
-          tc_mma_bf16(t_dk, off(kR, (v & 3) * kTileBytes + ks * 32), off(mQ, (qq * 64 + ks * 16) * 128), idesc_kn, first);
+        for (int ks = 0; ks < 4; ++ks) {                           // k = 16 queries per step; both A operands from TMEM
+          const uint32_t a_col = ks < 2 ? ks * 8 : 32 + (ks - 2) * 8;
+          const uint32_t first = ((v & 3) > 0 || ks > 0) ? 1u : 0u;
+          tc_mma_bf16_ts(t_dv, t_p + a_col, bd + ks * 128, idesc_kn, first);        // dV += P^T dO
+          tc_mma_bf16_ts(t_dk, t_p + 64 + a_col, bq + ks * 128, idesc_kn, first);   // dK += dS^T Q
         }
-        if (qq & 1) {                                              // dQ of the pair (v - 1, v): 128 queries
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)                           // k = 16 keys per step, A = dS^T read MN-major
-            tc_mma_bf16(t_dq + (qq >> 1) * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
-                        off(mK, (kt * 128 + ks * 16) * 128), idesc_mn, (kt > 0 || ks > 0) ? 1u : 0u);
-        }
-        if (qq == 3) tc_commit(acc_full);
-        if (v == 3) tc_commit(&empty[0]);
-        if (v == 5) { tc_commit(&dq_full[0]); tc_commit(&empty[1]); }
-        if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty[2]); }
+        if ((v & 3) == 3) tc_commit(acc_full);     // dV, dK of this key tile are complete: the epilogue warps may start
       }
       __syncwarp();
-    };
-    if (my_groups > 0) issue_sdp(0, 0);
-    for (int it = 0; it < my_groups; ++it) {
+      DBG2(it, 72 + v);
+      // operands of a new group that have not landed yet must not hold this group's last products back
+      bool sdp_now = more;
+      if (more && v >= 6) {
+        sdp_now = mbar_test_wait(&full[0], (it + 1) & 1) && mbar_test_wait(&full[1 + (flip ^ 1)], (it + 1) & 1);
+        sdp_now = __shfl_sync(0xffffffffu, sdp_now ? 1 : 0, 0) != 0;
+      }
+      if (sdp_now) issue_sdp(v < 6 ? it : it + 1, (v + 2) & 7);
+      if (elect_one()) {
+        if (v & 1) {                                               // dQ of the pair (v - 1, v): 128 queries
 #pragma unroll
-      for (int v = 0; v < 7; ++v) {
-        issue_sdp(it, v + 1);
-        issue_grads(it, v);
+          for (int ks = 0; ks < 8; ++ks)                           // k = 16 keys per step, A = dS^T read MN-major
+            tc_mma_bf16(t_dq + slot * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
+                        off(mK, (kt * 128 + ks * 16) * 128), idesc_mn, (kt > 0 || ks > 0) ? 1u : 0u);
+        }
+        if (v == 3) tc_commit(&empty[0]);
+        if (v == 5) { tc_commit(&dq_full[0]); tc_commit(&empty[2 - flip]); }     // accumulator 1 and its query half
+        if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty[3]); tc_commit(&empty[1 + flip]); }
       }
-      if (it + 1 < my_groups) {
-        // the next sub-unit opens a new group: if its operands have not landed yet, do not hold this group's last
-        // gradient products back
-        bool first = mbar_try_wait(&full[0], (it + 1) & 1) && mbar_try_wait(&full[1], (it + 1) & 1);
-        first = __shfl_sync(0xffffffffu, first ? 1 : 0, 0) != 0;
-        if (first) { issue_sdp(it + 1, 0); issue_grads(it, 7); }
-        else { issue_grads(it, 7); issue_sdp(it + 1, 0); }
-      } else {
-        issue_grads(it, 7);
-      }
+      __syncwarp();
+      DBG2(it, 80 + v);
+      if (more && !sdp_now) issue_sdp(it + 1, (v + 2) & 7);
+    };
+    // (the sub-unit loop is NOT unrolled: this kernel runs five different roles at once and its code has to stay
+    // resident in the instruction caches - fully unrolled it was 130 KB and 16-20 % of the math warps' stall samples
+    // were instruction fetches)
+    if (my_groups > 0) { issue_sdp(0, 0); issue_sdp(0, 1); }
+    for (int it = 0; it < my_groups; ++it) {
+      const bool more = it + 1 < my_groups;
+#pragma unroll 1
+      for (int v = 0; v < 8; ++v) issue_grads(it, v, v < 6 || more);
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ lse2 / delta of the next group (global only)
@@ -1026,8 +1071,8 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
           acc += __shfl_xor_sync(0xffffffffu, acc, 1);
           acc += __shfl_xor_sync(0xffffffffu, acc, 2);
           if (part == 0) {
-            dl[r] = r <= n ? acc : 0.f;
-            l2[r] = r <= n ? lv[u] * kLog2e : 0.f;
+            dl[r] = r <= n ? -acc : 0.f;                    // negated: the math warps add them
+            l2[r] = r <= n ? -lv[u] * kLog2e : 0.f;
           }
         }
       }
@@ -1039,78 +1084,100 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     // ------------------------------------------------------------------ math warps
     const int q4 = warp & 3;                  // TMEM lane quarter
     const int hh = (warp - 4) >> 2;           // which 32-query half of a sub-unit
-    const int r_tile = q4 * 32 + lane;        // key row inside the key tile
-    const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
-    const int sw = r_tile & 7;
+    const int tr = lane >> 2, tq = lane & 3;  // fragment coordinates: key rows tr, tr + 8 (+16, +24), query pair tq
+    const uint32_t la0 = static_cast<uint32_t>(q4 * 32) << 16, la1 = static_cast<uint32_t>(q4 * 32 + 16) << 16;
     int i = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
       const int f = (g / G.H) % G.F;
+      const int flip = i & 1;
       const float* l2 = lse2_s + (i & 1) * 256;
       const float* dl = del_s + (i & 1) * 256;
       mbar_wait(&dl_full[i & 1], (i >> 1) & 1);
-#pragma unroll 1
-      for (int v = 0; v < 8; ++v) {
-        const int vg = i * 8 + v, kt = v >> 2, qq = v & 3;
-        const int key = kt * 128 + r_tile;
-        // the (CLS query, CLS key) cell is counted by frame 0 only
-        const int kill = (key == n && f != 0) ? n : -1;
-        const uint32_t t_s = tmem_base + lane_off + (vg & 1) * 128 + hh * 32;
-        uint8_t* ds_row = ring + (vg & 3) * kTileBytes + r_tile * 128;
-        if (warp == 4) DBG2(i, 32 + v * 3);
-        mbar_wait(&st_full[vg & 1], (vg >> 1) & 1);
-        if (warp == 4) DBG2(i, 33 + v * 3);
-        tc_fence_after();
-        uint32_t sv[2][16], dv[2][16];
-        tmem_ld_32x32b_x16(t_s, sv[0]);
-        tmem_ld_32x32b_x16(t_s + 64, dv[0]);
-        tmem_ld_wait();
+      // This warp's block of a sub-unit: 32 keys (TMEM lanes q4*32 ..) x 32 queries (columns hh*32 ..), read in the
+      // mma-fragment layout (16x256b): a thread holds 4 keys x 8 queries, so it needs lse / delta of 8 queries only
+      // (eight 8-byte shared-memory loads per sub-unit; with one key row per thread it would be 64 values = 16 broadcast
+      // LDS.128, 4 k wavefronts per group - a quarter of the kernel's shared-memory time).
+      // A tcgen05.ld takes ~220 clk to come back, so the two 16-key halves of a block are software-pipelined: the
+      // loads of one half are in flight while the other half is computed (tcgen05.wait::ld has no groups: a load is
+      // issued right AFTER the wait that precedes the compute step it overlaps).
+      uint32_t S0[16], D0[16], S1[16], D1[16];
+      auto ld_half = [&](int v, int kh, uint32_t (&Sx)[16], uint32_t (&Dx)[16]) {
+        const uint32_t t_s = tmem_base + (v & 1) * 128 + hh * 32 + (kh ? la1 : la0);   // S^T; dP^T at +64
+        tmem_ld_16x256b_x4(t_s, Sx);
+        tmem_ld_16x256b_x4(t_s + 64, Dx);
+      };
+      // one half: P^T, dS^T of 2 key rows x 8 queries per thread -> TMEM (A operands of dV, dK) and the ring (dQ)
+      auto compute_half = [&](int v, int kh, int qq, uint32_t (&Sx)[16], uint32_t (&Dx)[16], const uint64_t (&nls)[4],
+                              const uint64_t (&ndl)[4]) {
+        const int kt = v >> 2;
+        // the (CLS query, CLS key) cell is counted by frame 0 only: a score of -inf makes P and dS exactly 0 there
+        if (f != 0 && (n >> 7) == kt && ((n & 127) >> 4) == q4 * 2 + kh && (n >> 5) == qq * 2 + hh) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c == 0) {
-            tmem_ld_32x32b_x16(t_s + 16, sv[1]);
-            tmem_ld_32x32b_x16(t_s + 64 + 16, dv[1]);
-          } else {
-            tmem_ld_wait();
-          }
-          const int qa0 = qq * 64 + hh * 32 + c * 16;
-          float pv[16], dsv[16];
-#pragma unroll
-          for (int e4 = 0; e4 < 16; e4 += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(l2 + qa0 + e4);
-            const float4 d4 = *reinterpret_cast<const float4*>(dl + qa0 + e4);
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float p = ex2_approx(fmaf(__uint_as_float(sv[c][e4 + k]), kLog2e, -ls[k]));
-              pv[e4 + k] = p;
-              dsv[e4 + k] = p * (__uint_as_float(dv[c][e4 + k]) - dd[k]);
-            }
-          }
-          if (kill >= qa0 && kill < qa0 + 16) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (qa0 + e == kill) { pv[e] = 0.f; dsv[e] = 0.f; }
-          }
-          uint32_t pk[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
-          tmem_st_32x32b_x8(t_s + c * 8, pk);
-#pragma unroll
-          for (int c4 = 0; c4 < 2; ++c4) {
-            uint4 w;
-            w.x = pack_bf16x2(dsv[8 * c4 + 0], dsv[8 * c4 + 1]);
-            w.y = pack_bf16x2(dsv[8 * c4 + 2], dsv[8 * c4 + 3]);
-            w.z = pack_bf16x2(dsv[8 * c4 + 4], dsv[8 * c4 + 5]);
-            w.w = pack_bf16x2(dsv[8 * c4 + 6], dsv[8 * c4 + 7]);
-            *reinterpret_cast<uint4*>(ds_row + (((hh * 4 + c * 2 + c4) ^ sw) << 4)) = w;
+          for (int k = 0; k < 16; ++k) {
+            const int key = kt * 128 + q4 * 32 + kh * 16 + tr + 8 * ((k >> 1) & 1);
+            const int qry = qq * 64 + hh * 32 + 2 * tq + 8 * (k >> 2) + (k & 1);
+            if (key == n && qry == n) Sx[k] = 0xff800000u;
           }
         }
+        const uint64_t l2e = f2_pack(kLog2e, kLog2e);
+        uint8_t* blk = ring + (v & 3) * kTileBytes + (q4 * 32 + kh * 16 + tr) * 128 + 4 * tq;
+        uint32_t pp[8], dd[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int rs = 0; rs < 2; ++rs) {
+            const int k = 4 * j + 2 * rs;
+            float x0, x1, d0, d1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(Sx[k]), __uint_as_float(Sx[k + 1])), l2e, nls[j]), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const uint64_t t = f2_add(f2_pack(__uint_as_float(Dx[k]), __uint_as_float(Dx[k + 1])), ndl[j]);
+            f2_unpack(f2_mul(f2_pack(p0, p1), t), d0, d1);
+            pp[2 * j + rs] = pack_bf16x2(p0, p1);
+            dd[2 * j + rs] = pack_bf16x2(d0, d1);
+            // dS^T row (key) in the ring block, 16-byte chunk hh*4 + j, word tq: conflict-free (8 rows x 4 words)
+            *reinterpret_cast<uint32_t*>(blk + rs * 1024 + (((hh * 4 + j) ^ tr) << 4)) = dd[2 * j + rs];
+          }
+        }
+        const uint32_t t_s = tmem_base + (v & 1) * 128 + hh * 32 + (kh ? la1 : la0);
+        tmem_st_16x128b_x4(t_s, pp);                                      // P^T  (A operand of dV)
+        tmem_st_16x128b_x4(t_s + 64, dd);                                 // dS^T (A operand of dK)
+      };
+      mbar_wait(&st_full[0], 0);
+      tc_fence_after();
+      ld_half(0, 0, S0, D0);
+#pragma unroll 1
+      for (int v = 0; v < 8; ++v) {
+        const int qq = (((0x6 >> (v >> 1)) & 1) ^ flip) * 2 + (v & 1);    // 64-query block this sub-unit covers
+        const int qb = qq * 64 + hh * 32 + 2 * tq;                        // first of this thread's queries
+        uint64_t nls[4], ndl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          nls[j] = *reinterpret_cast<const uint64_t*>(l2 + qb + 8 * j);    // (-lse2[q], -lse2[q + 1])
+          ndl[j] = *reinterpret_cast<const uint64_t*>(dl + qb + 8 * j);    // (-delta[q], -delta[q + 1])
+        }
+        tmem_ld_wait();
+        ld_half(v, 1, S1, D1);
+        compute_half(v, 0, qq, S0, D0, nls, ndl);
+        tmem_ld_wait();
+        // first half of the next sub-unit, if the tensor pipe has already delivered it (it usually has)
+        bool early = false;
+        if (v < 7) early = __all_sync(0xffffffffu, mbar_test_wait(&st_full[(v + 1) & 1], ((v + 1) >> 1) & 1));
+        if (early) {
+          tc_fence_after();
+          ld_half(v + 1, 0, S0, D0);
+        }
+        compute_half(v, 1, qq, S1, D1, nls, ndl);
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (warp == 4) DBG2(i, 34 + v * 3);
-        if (lane == 0) mbar_arrive(&math_done[vg & 1]);
+        if (lane == 0) mbar_arrive(&math_done[v & 1]);
+        if (v < 7 && !early) {
+          mbar_wait(&st_full[(v + 1) & 1], ((v + 1) >> 1) & 1);
+          tc_fence_after();
+          ld_half(v + 1, 0, S0, D0);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&dl_free[i & 1]);
@@ -1165,14 +1232,16 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         const bool is_cls = (row_first + lane == n) && cls != nullptr;
         uint32_t pv[32], pk[32];
         if (kt == 1) {
-          // query half 0 of dQ has been complete since sub-unit 5: it goes out while the second key tile is finished
+          // dQ accumulator 1 (query half 1 ^ flip) has been complete since sub-unit 5: it goes out while the second key
+          // tile is finished
+          const int qrow = ((i & 1) ^ 1) * 128 + q4 * 32;
           mbar_wait(&dq_full[0], i & 1);
           tc_fence_after();
-          drain(tmem_base + lane_off + 384, G.scale, pv, (q4 * 32 + lane == n && cls != nullptr) ? cls : nullptr);
+          drain(tmem_base + lane_off + 448, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&dq_free[0]);
-          store_rows(pv, h * SD, row0 + q4 * 32, q4 * 32);
+          store_rows(pv, h * SD, row0 + qrow, qrow);
         }
         mbar_wait(acc_full, kt & 1);
         if (warp == 12) DBG2(i, 64 + kt * 3);
@@ -1182,22 +1251,26 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         tc_fence_before();
         __syncwarp();
         if (warp == 12) DBG2(i, 65 + kt * 3);
-        if (lane == 0) mbar_arrive(acc_free);
-        store_rows(pv, 2 * HDIM + h * SD, row0 + row_first, row_first);
-        store_rows(pk, HDIM + h * SD, row0 + row_first, row_first);
+        if (lane == 0) mbar_arrive(acc_free);      // the accumulators are handed back BEFORE the stores: the MMA warp needs
+        store_rows(pv, 2 * HDIM + h * SD, row0 + row_first, row_first);   // them again one sub-unit into the next key tile
+        if (kt == 1) {
+          // dQ accumulator 0 (query half `flip`) completes with the group's last instruction; read it (and hand it back)
+          // before dK goes out
+          const int qrow = (i & 1) * 128 + q4 * 32;
+          mbar_wait(&dq_full[1], i & 1);
+          if (warp == 12) DBG2(i, 70);
+          tc_fence_after();
+          drain(tmem_base + lane_off + 384, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dq_free[1]);
+          store_rows(pk, HDIM + h * SD, row0 + row_first, row_first);
+          store_rows(pv, h * SD, row0 + qrow, qrow);
+          if (warp == 12) DBG2(i, 71);
+        } else {
+          store_rows(pk, HDIM + h * SD, row0 + row_first, row_first);
+        }
         if (warp == 12) DBG2(i, 66 + kt * 3);
-      }
-      {
-        uint32_t p1[32];
-        mbar_wait(&dq_full[1], i & 1);
-        if (warp == 12) DBG2(i, 70);
-        tc_fence_after();
-        drain(tmem_base + lane_off + 448, G.scale, p1, (128 + q4 * 32 + lane == n && cls != nullptr) ? cls : nullptr);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dq_free[1]);
-        store_rows(p1, h * SD, row0 + 128 + q4 * 32, 128 + q4 * 32);
-        if (warp == 12) DBG2(i, 71);
       }
     }
     if (lane == 0) bulk_wait<0>();               // all stores complete before the CTA exits

@@ -8,7 +8,7 @@
 
 using namespace oat;
 
-constexpr int kSmem = 160 * 1024;
+constexpr int kSmem = 200 * 1024;
 
 struct Res { long long issue, total; };
 
@@ -16,14 +16,19 @@ struct Res { long long issue, total; };
 //          3 SS N=64 three chains | 4 TS N=64 one chain | 5 TS N=64 + SS N=64 + SS N=64(A MN-major) interleaved (bwd grads)
 //          6 SS N=64 A MN-major one chain | 7 SS N=240 one chain (fwd S) | 8 TS N=64 chain of 15 (fwd PV)
 //          9 SS N=64 K/K one chain | 10 SS N=256 K/K one chain
-__global__ void __launch_bounds__(384, 1) probe(int variant, int reps, int noise, Res* out) {
+__global__ void __launch_bounds__(384, 1) probe(int variant, int reps, int noise, Res* out, int fill = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   __shared__ volatile int stop;
   if (threadIdx.x == 0) stop = 0;
-  for (int i = threadIdx.x; i < (kSmem - 2048) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (kSmem - 2048) / 16; i += blockDim.x) {
+    // fill 1: pseudo-random bf16 values in (-2, 2) (exponent bits 0x3f80 region), so the products are ordinary numbers
+    uint32_t h = i * 2654435761u;
+    auto w = [&](uint32_t x) { x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15; return (x & 0x807f807fu) | 0x3f003f00u; };
+    reinterpret_cast<uint4*>(smem)[i] = fill ? make_uint4(w(h), w(h + 1), w(h + 2), w(h + 3)) : make_uint4(0, 0, 0, 0);
+  }
   fence_proxy_async_smem();
   if (threadIdx.x < 32) tmem_alloc<512>(&slot);
   if (threadIdx.x == 32) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -31,7 +36,7 @@ __global__ void __launch_bounds__(384, 1) probe(int variant, int reps, int noise
   __syncthreads();
   tc_fence_after();
   const uint32_t t = slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {
     const uint32_t a = smem_u32(smem), b = a + 32768, c = a + 65536, d = a + 98304;
     const uint32_t i128 = make_idesc_bf16(128, 128, 0, 0), i64kn = make_idesc_bf16(128, 64, 0, 1),
                    i64mn = make_idesc_bf16(128, 64, 1, 1), i240 = make_idesc_bf16(128, 240, 0, 0),
@@ -104,6 +109,34 @@ __global__ void __launch_bounds__(384, 1) probe(int variant, int reps, int noise
           for (int k = 0; k < 8; ++k)
             tc_mma_bf16(t, make_smem_desc_sw128(a + (k & 3) * 32, 0, 1024), make_smem_desc_sw128(b + (k & 3) * 32, 0, 1024), i64kk, k > 0);
           break;
+        case 11: {
+          // one group of the pipelined space-attention backward, exactly as its MMA warp issues it (160 instructions)
+          const uint32_t Q = a, K = a + 32768, V = a + 65536, D = a + 98304, R = a + 131072;
+          const uint32_t isd = make_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int vn = (v + 1) & 7, ktn = vn >> 2, qqn = vn & 3, kt = v >> 2, qq = v & 3;
+            const uint32_t ts = t + (vn & 1) * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(ts, make_smem_desc_sw128(K + ktn * 16384 + k * 32, 0, 1024), make_smem_desc_sw128(Q + qqn * 8192 + k * 32, 0, 1024), isd, k > 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(ts + 64, make_smem_desc_sw128(V + ktn * 16384 + k * 32, 0, 1024), make_smem_desc_sw128(D + qqn * 8192 + k * 32, 0, 1024), isd, k > 0);
+            const uint32_t tp = t + (v & 1) * 128;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc_mma_bf16_ts(t + 256, tp + (ks < 2 ? ks * 8 : 32 + (ks - 2) * 8), make_smem_desc_sw128(D + (qq * 64 + ks * 16) * 128, 32768, 1024), i64kn, (qq > 0 || ks > 0));
+              tc_mma_bf16(t + 320, make_smem_desc_sw128(R + (v & 3) * 16384 + ks * 32, 0, 1024), make_smem_desc_sw128(Q + (qq * 64 + ks * 16) * 128, 32768, 1024), i64kn, (qq > 0 || ks > 0));
+            }
+            if (qq & 1) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                tc_mma_bf16(t + 384 + (qq >> 1) * 64, make_smem_desc_sw128(R + ((v - 1) & 3) * 16384 + ks * 2048, 16384, 1024),
+                            make_smem_desc_sw128(K + (kt * 128 + ks * 16) * 128, 32768, 1024), i64mn, (kt > 0 || ks > 0));
+            }
+          }
+        } break;
         case 10:
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -169,19 +202,20 @@ int main() {
   const char* names[] = {"SS N=128 K/K, 1 chain, 8 MMA", "SS N=128 K/K, 2 chains, 8 MMA", "SS N=64 K/MN, 1 chain, 8 MMA",
                          "SS N=64 K/MN, 3 chains, 24 MMA", "TS N=64, 1 chain, 8 MMA", "bwd grads TS+SS+SS(MN A), 24 MMA",
                          "SS N=64 MN/MN, 1 chain, 8 MMA", "SS N=240 K/K, 1 chain, 4 MMA", "TS N=64, 1 chain, 15 MMA",
-                         "SS N=64 K/K, 1 chain, 8 MMA", "SS N=256 K/K, 1 chain, 8 MMA"};
-  const int per[] = {8, 8, 8, 24, 8, 24, 8, 4, 15, 8, 8};
-  for (int v : {0, 2, 4, 5, 6}) {
-    for (int noise = 0; noise < 5; ++noise) {
+                         "SS N=64 K/K, 1 chain, 8 MMA", "SS N=256 K/K, 1 chain, 8 MMA", "space bwd group, 160 MMA"};
+  const int per[] = {8, 8, 8, 24, 8, 24, 8, 4, 15, 8, 8, 160};
+  for (int v : {9, 5, 11}) {
+    for (int noise = 0; noise < 10; noise += 1) {
       const int reps = 16;
+      const int fill = noise >= 5;
       Res h;
       for (int it = 0; it < 2; ++it) {
-        probe<<<1, 384, kSmem>>>(v, reps, noise, d);
+        probe<<<1, 384, kSmem>>>(v, reps, noise % 5, d, fill);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("variant %d: %s\n", v, cudaGetErrorString(e)); return 1; }
       }
       cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
-      printf("%-36s noise %d: issue %7lld clk (%.1f / MMA)   complete %7lld clk (%.1f / MMA)\n", names[v], noise, h.issue,
+      printf("%-36s noise %d (+5 = random operands): issue %7lld clk (%.1f / MMA)   complete %7lld clk (%.1f / MMA)\n", names[v], noise, h.issue,
              double(h.issue) / (reps * per[v]), h.total, double(h.total) / (reps * per[v]));
     }
   }
