@@ -765,22 +765,34 @@ attn_space_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
 // HBM needs for the group's 238 KB (10.3 k clk at 1/148 of 6.4 TB/s).
 #ifdef OAT_SPACE_DBG
 __device__ long long g_dbg[8192];
-#if OAT_SPACE_DBG == 2   // light: one timestamp per group (slot 0 only), negligible overhead
-#define DBG2(it, slot) do { if ((slot) == 0 && blockIdx.x == 0 && lane == 0 && (it) < 8) g_dbg[(it) * 128] = clock64(); } while (0)
+#if OAT_SPACE_DBG >= 2   // light: one timestamp per group (slot 0 only), negligible overhead
+#define DBG2(it, slot) do { if ((slot) == 0 && blockIdx.x == 0 && lane == 0 && (it) < 30) g_dbg[(it) * 128] = clock64(); } while (0)
 #else
 #define DBG2(it, slot) do { if (blockIdx.x == 0 && lane == 0 && (it) < 8) g_dbg[(it) * 128 + (slot)] = clock64(); } while (0)
 #endif
 #else
 #define DBG2(it, slot) do { } while (0)
 #endif
+// Dynamic group scheduler of the pipelined backward: groups are handed out by an atomic counter instead of a fixed
+// stride (measured with a fixed stride: the slowest SMs - whole TPCs, ~20 % behind the median, memory-side placement -
+// set the kernel time: 417-439 k cycles for the slowest CTA against a median of 343 k). The last CTA to finish resets
+// the counters, so the kernel is re-launchable without a memset; instances of it must not overlap (one stream).
+__device__ unsigned int g_b2_next = 0, g_b2_done = 0;
+#ifdef OAT_SPACE_DBG
+#define DBGK(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_dbg[3900 + (slot)] = clock64() - t_kernel_start; } while (0)
+#else
+#define DBGK(slot) do { } while (0)
+#endif
 constexpr int kB2Threads = 512;
 constexpr int kB2RingBytes = 4 * (kTileBytes);                   // dS^T ring: 4 blocks of [128 keys x 64 queries] bf16
 constexpr int kB2StageBytes = 4 * 4096;                          // epilogue staging: 32 rows x 128 B per epilogue warp
-constexpr int kB2Smem = kBwdOperandBytes + kB2RingBytes + kB2StageBytes + 4 * 256 * 4 + 1024 + 512;
+constexpr int kB2Smem = kBwdOperandBytes + kB2RingBytes + kB2StageBytes + 6 * 256 * 4 + 1024 + 512;
 
 __global__ void __launch_bounds__(kB2Threads, 1)
 attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const __grid_constant__ CUtensorMap tmap_qkv_b,
-                          const __grid_constant__ CUtensorMap tmap_do_a, const __grid_constant__ CUtensorMap tmap_do_b,
+                          const __grid_constant__ CUtensorMap tmap_qkv_q, const __grid_constant__ CUtensorMap tmap_qkv_p,
+                          const __grid_constant__ CUtensorMap tmap_do_q, const __grid_constant__ CUtensorMap tmap_do_p,
+                          const __grid_constant__ CUtensorMap tmap_o_q, const __grid_constant__ CUtensorMap tmap_o_p,
                           const __grid_constant__ CUtensorMap tmap_dqkv_a, const __grid_constant__ CUtensorMap tmap_dqkv_b,
                           const SpaceBwdGeom G) {
   extern __shared__ uint8_t smem_raw[];
@@ -791,69 +803,130 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
   uint8_t* Ds = smem + 3 * kMatBytes;                                   // dO
   uint8_t* ring = smem + kBwdOperandBytes;                              // dS^T blocks
   uint8_t* stage = ring + kB2RingBytes;                                 // epilogue staging
-  float* lse2_s = reinterpret_cast<float*>(stage + kB2StageBytes);      // [2][256]
-  float* del_s = lse2_s + 512;                                          // [2][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(del_s + 512);
-  uint64_t* full = bars;             // [4] producer -> MMA: {K0,V0}, {Q,dO rows 0..127}, {Q,dO rows 128..}, {K1,V1}
-  uint64_t* empty = bars + 4;        // [4] MMA -> producer
-  uint64_t* st_full = bars + 8;      // [2] MMA -> math: S^T, dP^T of a sub-unit ready (per TMEM buffer)
-  uint64_t* math_done = bars + 10;   // [2] math -> MMA: P^T, dS^T in TMEM, dS^T in the ring
-  uint64_t* acc_full = bars + 12;    // MMA -> epilogue: dV, dK of a key tile complete
-  uint64_t* acc_free = bars + 13;    // epilogue -> MMA
-  uint64_t* dq_full = bars + 14;     // [2] MMA -> epilogue: dQ accumulator 1 (complete after sub-unit 5) / 0 (after 7)
-  uint64_t* dq_free = bars + 16;     // [2] epilogue -> MMA
-  uint64_t* dl_full = bars + 18;     // [2] delta warps -> math: lse2 / delta of a group ready
-  uint64_t* dl_free = bars + 20;     // [2] math -> delta warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* lse2_s = reinterpret_cast<float*>(stage + kB2StageBytes);      // [3][256]
+  float* del_s = lse2_s + 768;                                          // [3][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(del_s + 768);
+  uint64_t* full_kv = bars;          // [2] producer -> MMA: {K,V} rows of key tile 0 / 1
+  uint64_t* empty_kv = bars + 2;     // [2] MMA -> producer
+  uint64_t* full_qd = bars + 4;      // [4] producer -> MMA: {Q,dO} rows of 64-query block 0..3
+  uint64_t* empty_qd = bars + 8;     // [4] MMA -> producer
+  uint64_t* st_full = bars + 12;     // [2] MMA -> math: S^T, dP^T of a sub-unit ready (per TMEM buffer)
+  uint64_t* math_done = bars + 14;   // [2] math -> MMA: P^T, dS^T in TMEM, dS^T in the ring
+  uint64_t* acc_full = bars + 16;    // MMA -> epilogue: dV, dK of a key tile complete
+  uint64_t* acc_free = bars + 17;    // epilogue -> MMA
+  uint64_t* dq_full = bars + 18;     // [2] MMA -> epilogue: dQ accumulator 1 (complete after sub-unit 5) / 0 (after 7)
+  uint64_t* dq_free = bars + 20;     // [2] epilogue -> MMA
+  uint64_t* dl_full = bars + 22;     // [3] delta warps -> math: lse2 / delta of a group ready
+  uint64_t* dl_free = bars + 25;     // [3] math -> delta warps
+  uint64_t* sched_full = bars + 28;  // [8] producer -> everyone: group index of an iteration published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  int* sched_g = reinterpret_cast<int*>(tmem_slot + 1);               // [8] ring of group indices (-1: no more work)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HDIM = G.H * SD;
   const int n = G.n;
   const int rem = n - 128;           // token rows of the second tile (the CLS row follows them)
   pdl_launch_dependents();
+#ifdef OAT_SPACE_DBG
+  const long long t_kernel_start = clock64();
+#endif
 
   for (int i = tid; i < (kBwdOperandBytes + kB2RingBytes) / 16; i += kB2Threads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
+  if (warp == 5) DBGK(0);
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_qkv_a); tma_prefetch_desc(&tmap_qkv_b);
-      tma_prefetch_desc(&tmap_do_a); tma_prefetch_desc(&tmap_do_b);
+      tma_prefetch_desc(&tmap_qkv_q); tma_prefetch_desc(&tmap_qkv_p);
+      tma_prefetch_desc(&tmap_do_q); tma_prefetch_desc(&tmap_do_p);
+      tma_prefetch_desc(&tmap_o_q); tma_prefetch_desc(&tmap_o_p);
       tma_prefetch_desc(&tmap_dqkv_a); tma_prefetch_desc(&tmap_dqkv_b);
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
   } else if (warp == 1 && lane == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 2); mbar_init(&full[3], 2);
-    for (int k = 0; k < 4; ++k) mbar_init(&empty[k], 1);
+    mbar_init(&full_kv[0], 1); mbar_init(&full_kv[1], 2);                 // the CLS rows of k, v arrive by hand
+    for (int k = 0; k < 4; ++k) mbar_init(&full_qd[k], k == (n >> 6) ? 2 : 1);   // ... and so do those of q, dO
+    for (int k = 0; k < 2; ++k) mbar_init(&empty_kv[k], 1);
+    for (int k = 0; k < 4; ++k) mbar_init(&empty_qd[k], 1);
     for (int k = 0; k < 2; ++k) {
       mbar_init(&st_full[k], 1);
       mbar_init(&math_done[k], 8);
+    }
+    for (int k = 0; k < 3; ++k) {
       mbar_init(&dl_full[k], 2);
       mbar_init(&dl_free[k], 8);
     }
     mbar_init(acc_full, 1); mbar_init(acc_free, 4);
     for (int k = 0; k < 2; ++k) { mbar_init(&dq_full[k], 1); mbar_init(&dq_free[k], 4); }
+    for (int k = 0; k < 8; ++k) mbar_init(&sched_full[k], 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp == 5) DBGK(1);
   pdl_wait();
+  if (warp == 5) DBGK(2);
   const uint32_t tmem_base = *tmem_slot;
+  // group of iteration i (every role but the producer, which fetches them one iteration ahead of its own loads)
+  auto group_of = [&](int i) -> int {
+    mbar_wait(&sched_full[i & 7], (i >> 3) & 1);
+    return sched_g[i & 7];
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    // Tile sets in the order the group needs them (see the MMA issuer for the schedule): {K0,V0}, the query half of the
-    // first query pair, the other query half, {K1,V1}. Each set is re-loaded as soon as the previous group's last
-    // instruction that reads it has retired - for the first two that is well before the previous group ends.
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    // Operand sets in the order the group needs them (see the MMA issuer for the schedule): {K0,V0}, the two 64-query
+    // blocks of the first query half, those of the other half, {K1,V1}. Q and dO are loaded and released per 64-query
+    // block: the blocks the next group opens with are the ones this group stops reading 3-4 sub-units before its end.
+    const int cq = n >> 6;                                   // 64-query block that holds the CLS query row
+    const int part_q = rem >= 64 ? 3 : 2;                    // the block that is cut short by the CLS row ...
+    const int part_rows = rem >= 64 ? rem - 64 : rem;        // ... and its token rows
+    auto fetch = [&](int i) -> int {              // next group from the global counter, published in ring slot i & 3
+      int g = 0;
+      if (lane == 0) {
+        g = static_cast<int>(atomicAdd(&g_b2_next, 1u));
+        if (g >= G.groups) g = -1;
+        sched_g[i & 7] = g;
+        mbar_arrive(&sched_full[i & 7]);
+      }
+      return __shfl_sync(0xffffffffu, g, 0);
+    };
+    // Two groups ahead: the delta warps work that far in front of the math warps (their ~10 k clk per group - four
+    // dependent load / reduce rounds in two warps - would otherwise sit right on the critical path), and the MMA warp
+    // looks one group ahead.
+    int g = fetch(0);
+    int g_next = g >= 0 ? fetch(1) : -1;
+    DBGK(3);
+    for (int i = 0; g >= 0; ++i) {
+      const int g_next2 = g_next >= 0 ? fetch(i + 2) : -1;
+      if (g_next >= 0 && lane == 0) {
+        // Pull the next group's q / k / v / dO / O head slices into L2 now, a whole group time before they are read.
+        // The operand tiles are single-buffered (their TMA loads start only when the previous group releases them) and
+        // the delta warps read O / dO with plain loads, four dependent round trips per group: from DRAM both are
+        // latency-bound, and on the SMs with the longest path to memory the delta warps set the pace of the kernel
+        // (measured: 398 k cycles per CTA with them, 304 k with their loads removed).
+        const int hn = g_next % G.H, rn = g_next / G.H, fn = rn % G.F, bn = rn / G.F;
+        const int rown = bn * G.T + 1 + fn * n;
+#pragma unroll
+        for (int pq = 0; pq < 4; ++pq) {
+          const int rows = pq == part_q ? part_rows : (pq < part_q ? 64 : 0);
+          if (rows > 0) {
+            const bool pt = pq == part_q;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) tma_prefetch_2d(pt ? &tmap_qkv_p : &tmap_qkv_q, m * HDIM + hn * SD, rown + pq * 64);
+            tma_prefetch_2d(pt ? &tmap_do_p : &tmap_do_q, hn * SD, rown + pq * 64);
+            tma_prefetch_2d(pt ? &tmap_o_p : &tmap_o_q, hn * SD, rown + pq * 64);
+          }
+        }
+      }
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
       const int row0 = b * G.T + 1 + f * n;
       const uint32_t pe = (i & 1) ^ 1;
       const int flip = i & 1;
-      // CLS token rows -> row n of two operands: (q, dO) with query half 1, (k, v) with key tile 1
+      // CLS token rows -> row n of two operands: (q, dO) with their 64-query block, (k, v) with key tile 1
       auto cls_rows = [&](int m_lo, int m_hi) {
         if (lane < 16) {
           const int m = lane < 8 ? m_lo : m_hi, c = lane & 7;
@@ -866,47 +939,46 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         fence_proxy_async_smem();
         __syncwarp();
       };
-      auto load_qd = [&](int half) {
-        mbar_wait(&empty[1 + half], pe);
-        if (half == 0) {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&full[1], 2u * kTileBytes);
-            tma_load_2d(Qs, &tmap_qkv_a, &full[1], h * SD, row0);
-            tma_load_2d(Ds, &tmap_do_a, &full[1], h * SD, row0);
+      auto load_qd = [&](int pq) {
+        mbar_wait(&empty_qd[pq], pe);
+        const int rows = pq == part_q ? part_rows : (pq < part_q ? 64 : 0);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_qd[pq], 2u * rows * 128u);
+          if (rows > 0) {
+            tma_load_2d(Qs + pq * 8192, pq == part_q ? &tmap_qkv_p : &tmap_qkv_q, &full_qd[pq], h * SD, row0 + pq * 64);
+            tma_load_2d(Ds + pq * 8192, pq == part_q ? &tmap_do_p : &tmap_do_q, &full_qd[pq], h * SD, row0 + pq * 64);
           }
-        } else {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&full[2], 2u * rem * 128u);
-            if (rem > 0) {
-              tma_load_2d(Qs + kTileBytes, &tmap_qkv_b, &full[2], h * SD, row0 + 128);
-              tma_load_2d(Ds + kTileBytes, &tmap_do_b, &full[2], h * SD, row0 + 128);
-            }
-          }
+        }
+        if (pq == cq) {
           cls_rows(0, 3);
-          if (lane == 0) mbar_arrive(&full[2]);
+          if (lane == 0) mbar_arrive(&full_qd[pq]);
         }
       };
-      mbar_wait(&empty[0], pe);
+      mbar_wait(&empty_kv[0], pe);
       DBG2(i, 100);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&full[0], 2u * kTileBytes);
-        tma_load_2d(Ks, &tmap_qkv_a, &full[0], HDIM + h * SD, row0);
-        tma_load_2d(Vs, &tmap_qkv_a, &full[0], 2 * HDIM + h * SD, row0);
+        mbar_arrive_expect_tx(&full_kv[0], 2u * kTileBytes);
+        tma_load_2d(Ks, &tmap_qkv_a, &full_kv[0], HDIM + h * SD, row0);
+        tma_load_2d(Vs, &tmap_qkv_a, &full_kv[0], 2 * HDIM + h * SD, row0);
       }
-      load_qd(flip);
+      load_qd(flip * 2);
+      load_qd(flip * 2 + 1);
       DBG2(i, 101);
-      load_qd(flip ^ 1);
+      load_qd((flip ^ 1) * 2);
+      load_qd((flip ^ 1) * 2 + 1);
       DBG2(i, 102);
-      mbar_wait(&empty[3], pe);
+      mbar_wait(&empty_kv[1], pe);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&full[3], 2u * rem * 128u);
+        mbar_arrive_expect_tx(&full_kv[1], 2u * rem * 128u);
         if (rem > 0) {
-          tma_load_2d(Ks + kTileBytes, &tmap_qkv_b, &full[3], HDIM + h * SD, row0 + 128);
-          tma_load_2d(Vs + kTileBytes, &tmap_qkv_b, &full[3], 2 * HDIM + h * SD, row0 + 128);
+          tma_load_2d(Ks + kTileBytes, &tmap_qkv_b, &full_kv[1], HDIM + h * SD, row0 + 128);
+          tma_load_2d(Vs + kTileBytes, &tmap_qkv_b, &full_kv[1], 2 * HDIM + h * SD, row0 + 128);
         }
       }
       cls_rows(1, 2);
-      if (lane == 0) mbar_arrive(&full[3]);
+      if (lane == 0) mbar_arrive(&full_kv[1]);
+      g = g_next;
+      g_next = g_next2;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -929,7 +1001,6 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     if (tmem_base != 0) __trap();
     constexpr uint32_t tmem0 = 0;
     constexpr uint32_t t_dv = tmem0 + 256, t_dk = tmem0 + 320, t_dq = tmem0 + 384;
-    const int my_groups = (G.groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto off = [](uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); };   // start-address field: bits [0, 14)
 
     // Schedule of a group: sub-unit v = (key tile v >> 2) x (64 queries). The four 128-query steps visit the query
@@ -937,36 +1008,52 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     // group reads first ({K0,V0} and its first query half) are then exactly the ones the previous group stopped reading
     // two steps / one step before its end, so their loads are never exposed, and the tiles released last ({K1,V1} and
     // the other query half) are needed one and two steps into the next group.
-    // S^T and dP^T of sub-unit v of group iteration `it` into TMEM buffer v & 1
-    auto issue_sdp = [&](int it, int v) {
-      const int kt = v >> 2, slot = (0x6 >> (v >> 1)) & 1, flip = it & 1;      // slot: 0 1 1 0
+    // The issue thread's own instruction stream is the critical path of this kernel (the tensor pipe needs ~45-80 clk per
+    // instruction, the thread needs ~6 clk per instruction of its own and shares its scheduler with three busy warps):
+    // everything is unrolled to literal operands, and a sub-unit is ONE elected block - waits first, then up to 24
+    // tcgen05.mma back to back.
+    // MMAs of S^T and dP^T of sub-unit v (group iteration `it`) into TMEM buffer v & 1; the caller has waited for the operands
+    auto sdp_mmas = [&](int it, int v) {
+      const int kt = v >> 2, slot = (0x6 >> (v >> 1)) & 1, flip = it & 1;      // slot (dQ accumulator): 0 1 1 0
       const uint32_t qoff = static_cast<uint32_t>(((slot ^ flip) * 2 + (v & 1)) * 8192);
-      DBG2(it, v * 4 + 0);
-      if (v == 0) { mbar_wait(&full[0], it & 1); mbar_wait(&full[1 + flip], it & 1); }
-      if (v == 2) mbar_wait(&full[2 - flip], it & 1);
-      if (v == 4) mbar_wait(&full[3], it & 1);
-      DBG2(it, v * 4 + 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t t_s = tmem0 + (v & 1) * 128;
-        const uint64_t bq = off(kQ, qoff), bd = off(kD, qoff);
+      const uint32_t t_s = tmem0 + (v & 1) * 128;
+      const uint64_t bq = off(kQ, qoff), bd = off(kD, qoff);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(t_s, off(kK, kt * kTileBytes + k * 32), bq + k * 2, idesc_sd, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(t_s, off(kK, kt * kTileBytes + k * 32), bq + k * 2, idesc_sd, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(t_s + 64, off(kV, kt * kTileBytes + k * 32), bd + k * 2, idesc_sd, k > 0 ? 1u : 0u);
-        tc_commit(&st_full[v & 1]);
-      }
-      __syncwarp();
-      DBG2(it, 88 + v);
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(t_s + 64, off(kV, kt * kTileBytes + k * 32), bd + k * 2, idesc_sd, k > 0 ? 1u : 0u);
+      tc_commit(&st_full[v & 1]);
     };
+    auto sdp_wait = [&](int it, int v) {            // operand sets sub-unit v is the first to read
+      const int flip = it & 1;
+      if (v == 0 || v == 4) mbar_wait(&full_kv[v >> 2], it & 1);
+      if (v < 4) mbar_wait(&full_qd[((v >> 1) ^ flip) * 2 + (v & 1)], it & 1);
+    };
+    auto sdp_ready = [&](int it, int v) {           // the same, as a non-blocking question
+      const int flip = it & 1;
+      bool ok = true;
+      if (v == 0 || v == 4) ok = mbar_test_wait(&full_kv[v >> 2], it & 1);
+      if (v < 4) ok = ok && mbar_test_wait(&full_qd[((v >> 1) ^ flip) * 2 + (v & 1)], it & 1);
+      return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    };
+    // Schedule of a group: sub-unit v = (key tile v >> 2) x (64 queries). The four 128-query steps visit the query
+    // halves in the order 0 1 1 0 in even group iterations and 1 0 0 1 in odd ones (slot ^ flip): the operand tiles a
+    // group reads first ({K0,V0} and its first query half) are then the ones the previous group stopped reading
+    // two steps / one step before its end, and the tiles released last ({K1,V1} and the other query half) are needed
+    // one and two steps into the next group.
     // Gradient products of sub-unit v, with S^T / dP^T of sub-unit v + 2 (same TMEM buffer) slipped in right behind the
     // eight dV / dK instructions that read P^T / dS^T out of that buffer (A operands from TMEM: no shared-memory
     // fetch); the dQ products run under the math warps' next sub-unit.
     auto issue_grads = [&](int it, int v, bool more) {
       const int kt = v >> 2, slot = (0x6 >> (v >> 1)) & 1, flip = it & 1;
       const uint32_t qoff = static_cast<uint32_t>(((slot ^ flip) * 2 + (v & 1)) * 8192);
+      const int it2 = v < 6 ? it : it + 1, v2 = (v + 2) & 7;       // the sub-unit whose S^T / dP^T go out with this one
+      if (v == 0) DBG2(it, 0);
+      // operands of a new group that have not landed yet must not hold this group's last products back
+      bool sdp_now = more;
+      if (more && v2 <= 4) sdp_now = sdp_ready(it2, v2);
       DBG2(it, v * 4 + 2);
       mbar_wait(&math_done[v & 1], (v >> 1) & 1);
       DBG2(it, v * 4 + 3);
@@ -975,8 +1062,8 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
       if (v == 3) mbar_wait(&dq_free[0], (it & 1) ^ 1);
       DBG2(it, 104 + v);
       tc_fence_after();
-      const uint32_t t_p = tmem0 + (v & 1) * 128;                 // P^T (bf16): queries 0..31 at +0, 32..63 at +32; dS^T at +64
       if (elect_one()) {
+        const uint32_t t_p = tmem0 + (v & 1) * 128;               // P^T (bf16): queries 0..31 at +0, 32..63 at +32; dS^T at +64
         const uint64_t bd = off(mD, qoff), bq = off(mQ, qoff);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {                           // k = 16 queries per step; both A operands from TMEM
@@ -986,53 +1073,63 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
           tc_mma_bf16_ts(t_dk, t_p + 64 + a_col, bq + ks * 128, idesc_kn, first);   // dK += dS^T Q
         }
         if ((v & 3) == 3) tc_commit(acc_full);     // dV, dK of this key tile are complete: the epilogue warps may start
-      }
-      __syncwarp();
-      DBG2(it, 72 + v);
-      // operands of a new group that have not landed yet must not hold this group's last products back
-      bool sdp_now = more;
-      if (more && v >= 6) {
-        sdp_now = mbar_test_wait(&full[0], (it + 1) & 1) && mbar_test_wait(&full[1 + (flip ^ 1)], (it + 1) & 1);
-        sdp_now = __shfl_sync(0xffffffffu, sdp_now ? 1 : 0, 0) != 0;
-      }
-      if (sdp_now) issue_sdp(v < 6 ? it : it + 1, (v + 2) & 7);
-      if (elect_one()) {
+        // the last reads of a 64-query block of Q / dO: blocks of accumulator 1's half after sub-units 4, 5, the other
+        // half after 6, 7
+        if (v >= 4) tc_commit(&empty_qd[((v < 6 ? 1 : 0) ^ flip) * 2 + (v & 1)]);
+        if (sdp_now) sdp_mmas(it2, v2);
         if (v & 1) {                                               // dQ of the pair (v - 1, v): 128 queries
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)                           // k = 16 keys per step, A = dS^T read MN-major
             tc_mma_bf16(t_dq + slot * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
                         off(mK, (kt * 128 + ks * 16) * 128), idesc_mn, (kt > 0 || ks > 0) ? 1u : 0u);
         }
-        if (v == 3) tc_commit(&empty[0]);
-        if (v == 5) { tc_commit(&dq_full[0]); tc_commit(&empty[2 - flip]); }     // accumulator 1 and its query half
-        if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty[3]); tc_commit(&empty[1 + flip]); }
+        if (v == 3) tc_commit(&empty_kv[0]);
+        if (v == 5) tc_commit(&dq_full[0]);                                      // accumulator 1
+        if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty_kv[1]); }
       }
       __syncwarp();
       DBG2(it, 80 + v);
-      if (more && !sdp_now) issue_sdp(it + 1, (v + 2) & 7);
+      if (more && !sdp_now) {
+        sdp_wait(it2, v2);
+        tc_fence_after();
+        if (elect_one()) sdp_mmas(it2, v2);
+        __syncwarp();
+      }
     };
-    // (the sub-unit loop is NOT unrolled: this kernel runs five different roles at once and its code has to stay
-    // resident in the instruction caches - fully unrolled it was 130 KB and 16-20 % of the math warps' stall samples
-    // were instruction fetches)
-    if (my_groups > 0) { issue_sdp(0, 0); issue_sdp(0, 1); }
-    for (int it = 0; it < my_groups; ++it) {
-      const bool more = it + 1 < my_groups;
-#pragma unroll 1
+    auto issue_sdp = [&](int it, int v) {
+      sdp_wait(it, v);
+      tc_fence_after();
+      if (elect_one()) sdp_mmas(it, v);
+      __syncwarp();
+    };
+    // (only THIS role is unrolled over the sub-units; the math and epilogue warps loop - with every role unrolled the
+    // kernel was 130 KB of code and 16-20 % of the math warps' stall samples were instruction fetches)
+    bool have = group_of(0) >= 0;
+    DBGK(4);
+    if (have) { issue_sdp(0, 0); issue_sdp(0, 1); }
+    DBGK(5);
+    for (int it = 0; have; ++it) {
+      const bool more = group_of(it + 1) >= 0;
+#pragma unroll
       for (int v = 0; v < 8; ++v) issue_grads(it, v, v < 6 || more);
+      have = more;
     }
+    DBGK(6);
   } else if (warp < 4) {
     // ------------------------------------------------------------------ lse2 / delta of the next group (global only)
     const int t64 = (warp - 2) * 32 + lane;
     const int part = t64 & 3, rsub = t64 >> 2;                    // 4 threads per query row, 16 rows per pass
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
+      const int g = group_of(i);
+      if (g < 0) break;
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
       const long long tok_base = static_cast<long long>(b) * G.T;
       const long long tok0 = tok_base + 1 + f * n;
-      mbar_wait(&dl_free[i & 1], ((i >> 1) & 1) ^ 1);
+      const int db = i % 3, dph = (i / 3) & 1;       // lse2 / delta buffer of this group and its phase
+      mbar_wait(&dl_free[db], dph ^ 1);
       if (warp == 2) DBG2(i, 60);
-      float* l2 = lse2_s + (i & 1) * 256;
-      float* dl = del_s + (i & 1) * 256;
+      float* l2 = lse2_s + db * 256;
+      float* dl = del_s + db * 256;
       const float* lse_g = G.lse + (static_cast<long long>(b) * G.H + h) * G.T;
 #pragma unroll 1
       for (int p0 = 0; p0 < 16; p0 += 4) {
@@ -1078,7 +1175,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
       }
       __syncwarp();
       if (warp == 2) DBG2(i, 61);
-      if (lane == 0) mbar_arrive(&dl_full[i & 1]);
+      if (lane == 0) mbar_arrive(&dl_full[db]);
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ math warps
@@ -1086,13 +1183,15 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     const int hh = (warp - 4) >> 2;           // which 32-query half of a sub-unit
     const int tr = lane >> 2, tq = lane & 3;  // fragment coordinates: key rows tr, tr + 8 (+16, +24), query pair tq
     const uint32_t la0 = static_cast<uint32_t>(q4 * 32) << 16, la1 = static_cast<uint32_t>(q4 * 32 + 16) << 16;
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
+      const int g = group_of(i);
+      if (g < 0) break;
       const int f = (g / G.H) % G.F;
       const int flip = i & 1;
-      const float* l2 = lse2_s + (i & 1) * 256;
-      const float* dl = del_s + (i & 1) * 256;
-      mbar_wait(&dl_full[i & 1], (i >> 1) & 1);
+      const int db = i % 3, dph = (i / 3) & 1;
+      const float* l2 = lse2_s + db * 256;
+      const float* dl = del_s + db * 256;
+      mbar_wait(&dl_full[db], dph);
       // This warp's block of a sub-unit: 32 keys (TMEM lanes q4*32 ..) x 32 queries (columns hh*32 ..), read in the
       // mma-fragment layout (16x256b): a thread holds 4 keys x 8 queries, so it needs lse / delta of 8 queries only
       // (eight 8-byte shared-memory loads per sub-unit; with one key row per thread it would be 64 values = 16 broadcast
@@ -1180,7 +1279,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&dl_free[i & 1]);
+      if (lane == 0) mbar_arrive(&dl_free[db]);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps: dV, dK per key tile, dQ per group
@@ -1189,6 +1288,8 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     uint8_t* stg = stage + q4 * 4096;
     const int s7 = lane & 7;
     // one 64-column accumulator of this warp's 32 rows: TMEM -> registers (bf16 pairs), fp32 row kept for the CLS atomics
+    // (parking that row in shared memory to add it after the hand-back was tried: the dependent LDS -> RED chain of the
+    // one thread that owns the row stalls its whole warp far longer than 64 back-to-back REDs from registers)
     auto drain = [&](uint32_t taddr, float sc, uint32_t (&pk)[32], float* cls_dst) {
       uint32_t a[32];
 #pragma unroll
@@ -1221,8 +1322,9 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         bulk_commit();
       }
     };
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
+      const int g = group_of(i);
+      if (g < 0) break;
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
       const int row0 = b * G.T + 1 + f * n;
       float* cls = G.cls_acc != nullptr ? G.cls_acc + (static_cast<long long>(b) * G.H + h) * 3 * SD : nullptr;
@@ -1273,11 +1375,24 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         if (warp == 12) DBG2(i, 66 + kt * 3);
       }
     }
+    if (warp == 12) DBGK(7);
     if (lane == 0) bulk_wait<0>();               // all stores complete before the CTA exits
+    if (warp == 12) DBGK(8);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&g_b2_done, 1u) == gridDim.x - 1) {   // last CTA out: every CTA has drawn its end-of-work ticket
+      g_b2_next = 0;
+      g_b2_done = 0;
+      __threadfence();
+    }
+  }
+#ifdef OAT_SPACE_DBG
+  if (tid == 0) g_dbg[4096 + blockIdx.x] = clock64() - t_kernel_start;
+#endif
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1360,13 +1475,19 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
     return check_launch("attn_space_tc_bwd_kernel");
   }
   // pipelined kernel: token rows [0, 128) and [128, n) of a group are separate boxes (tiles are released one by one)
-  CUtensorMap tqa, tqb, tda, tdb, tsa, tsb;
-  const int rem = a->n > 128 ? a->n - 128 : 1;
+  CUtensorMap tqa, tqb, tqq, tqp, tdq, tdp, toq, top, tsa, tsb;
+  const int rem_rows = a->n - 128;
+  const int rem = rem_rows > 0 ? rem_rows : 1;
+  const int part = (rem_rows >= 64 ? rem_rows - 64 : rem_rows) > 0 ? (rem_rows >= 64 ? rem_rows - 64 : rem_rows) : 1;
   const int tail = (a->n & 31) ? (a->n & 31) : 32;
   int rc = make_tmap_bf16_2d(&tqa, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, 128);
   if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tqb, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, rem);
-  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tda, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, 128);
-  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tdb, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, rem);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tqq, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, 64);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tqp, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, part);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tdq, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, 64);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tdp, a->dout, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_dout, part);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&toq, a->out, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_out, 64);
+  if (rc == OAT_OK) rc = make_tmap_bf16_2d(&top, a->out, 1ull * a->H * SD, 1ull * a->B * a->T, a->ld_out, part);
   if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tsa, a->dqkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_dqkv, 32);
   if (rc == OAT_OK) rc = make_tmap_bf16_2d(&tsb, a->dqkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_dqkv, tail);
   if (rc != OAT_OK) return rc;
@@ -1376,7 +1497,7 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2 smem attr: %s", cudaGetErrorString(e));
     done2 = true;
   }
-  cudaError_t e = launch_pdl(attn_space_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, s, tqa, tqb, tda, tdb, tsa, tsb, G);
+  cudaError_t e = launch_pdl(attn_space_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, s, tqa, tqb, tqq, tqp, tdq, tdp, toq, top, tsa, tsb, G);
   if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("attn_space_tc_bwd2_kernel");
 }

@@ -91,6 +91,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
       "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a 2D tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(desc), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1,
                                             int32_t c2) {
   asm volatile(

@@ -18,9 +18,21 @@ ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
 for _ in range(3):
     ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 1024)()
-lib().oat_debug_timeline(buf, 1024)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc)
+e1.record(); torch.cuda.synchronize()
+print("event time per call: %.1f us" % (e0.elapsed_time(e1) * 100))
+buf = (ctypes.c_longlong * 4400)()
+lib().oat_debug_timeline(buf, 4400)
+cyc = sorted(buf[4096 + k] for k in range(148))
+print('kernel cycles per CTA: min %d median %d max %d' % (cyc[0], cyc[74], cyc[-1]))
+print('per CTA (k):', [int(buf[4096 + k] // 1000) for k in range(148)])
 print("group start-to-start cycles (CTA 0):", [buf[(i + 1) * 128] - buf[i * 128] for i in range(0, 7)])
+print("CTA 0 milestones (cycles from CTA start): zero-fill %d | barriers+TMEM ready %d | pdl_wait %d | first group fetched %d | MMA warp has group %d | first S/dP issued %d | last MMA issued %d | epilogue done %d | stores drained %d | exit %d" % tuple([buf[3900 + k] for k in range(9)] + [buf[4096]]))
+if os.environ.get("LIGHT"):
+    print("all groups:", [int(buf[(i + 1) * 128] - buf[i * 128]) for i in range(0, 24)])
 if os.environ.get("LIGHT"):
     sys.exit(0)
 for i in range(1, 5):
@@ -28,11 +40,8 @@ for i in range(1, 5):
     b = lambda k, j=i: buf[j * 128 + k] - t0
     print("group %d (t=0: MMA warp starts S/dP of sub-unit 0; previous group's t0 at %d)" % (i, buf[(i - 1) * 128] - t0))
     for v in range(8):
-        print("  v%d: MMA sdp start=%6d ops ready=%6d | grads: wait math from=%6d seen=%6d || math: wait from=%6d st_full seen=%6d done=%6d (math %d)" % (
-            v, b(v * 4), b(v * 4 + 1), b(v * 4 + 2), b(v * 4 + 3), b(32 + v * 3), b(33 + v * 3), b(34 + v * 3), b(34 + v * 3) - b(33 + v * 3)))
-    for v in range(8):
-        print("  v%d MMA thread: math_done seen %6d | free-waits done %6d | dV/dK issued %6d | dQ+commits issued %6d || sdp(v): start %6d ops ready %6d issued %6d" % (
-            v, b(v * 4 + 3), b(104 + v), b(72 + v), b(80 + v), b(v * 4), b(v * 4 + 1), b(88 + v)))
+        print("  v%d: MMA thread: waits for math from=%6d seen=%6d all waits done=%6d MMAs issued=%6d || math warp 4 done=%6d" % (
+            v, b(v * 4 + 2), b(v * 4 + 3), b(104 + v), b(80 + v), b(34 + v * 3)))
     print("  producer: empty A/B/C seen at %d %d %d | delta warps: start %d done %d" % (b(100), b(101), b(102), b(60), b(61)))
     print("  epilogue: kt0 acc_full %d read %d stored %d | kt1 %d %d %d | dq_full %d stored %d" % (
         b(64), b(65), b(66), b(67), b(68), b(69), b(70), b(71)))
