@@ -61,9 +61,13 @@ __device__ __forceinline__ void ld32_wait(uint32_t taddr, uint32_t (&v)[32]) {
   tmem_ld_wait();
 }
 
-template <int NCH>
+// dynamic group scheduler of the forward kernel (same scheme as the pipelined backward, see g_b2_next)
+__device__ unsigned int g_fw_next = 0, g_fw_done = 0;
+
+template <int KS>   // KS = 16-key steps of the P V product = padded key count / 16
 __global__ void __launch_bounds__(kSpThreads, 1)
 attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGeom G) {
+  constexpr int NCH = (KS + 1) / 2;            // 32-key chunks of a score row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
@@ -73,7 +77,9 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
   uint64_t* p_full = bars + 6;     // [2] softmax -> MMA (P in TMEM)
   uint64_t* o_full = bars + 8;     // [2] MMA -> softmax (O ready)
   uint64_t* buf_free = bars + 10;  // [2] softmax -> MMA (TMEM region drained)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* sched_full = bars + 12; // [4] producer -> everyone: group index of an iteration published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  int* sched_g = reinterpret_cast<int*>(tmem_slot + 1);   // [4] ring of group indices (-1: no more work)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HDIM = G.H * SD;
@@ -95,6 +101,7 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
       mbar_init(&o_full[i], 1);
       mbar_init(&buf_free[i], 4);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&sched_full[i], 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -102,11 +109,28 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
   tc_fence_after();
   pdl_wait();                   // shared memory cleared, barriers and TMEM ready: now wait for the qkv GEMM
   const uint32_t tmem_base = *tmem_slot;
+  // Groups are handed out by an atomic counter (see g_b2_next: a fixed stride lets the SMs with the longest path to
+  // memory set the kernel time); the producer draws them one iteration ahead and publishes them in a small ring.
+  auto group_of = [&](int i) -> int {
+    mbar_wait(&sched_full[i & 3], (i >> 2) & 1);
+    return sched_g[i & 3];
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    auto fetch = [&](int i) -> int {
+      int g = 0;
+      if (lane == 0) {
+        g = static_cast<int>(atomicAdd(&g_fw_next, 1u));
+        if (g >= G.groups) g = -1;
+        sched_g[i & 3] = g;
+        mbar_arrive(&sched_full[i & 3]);
+      }
+      return __shfl_sync(0xffffffffu, g, 0);
+    };
+    int g = fetch(0);
+    for (int i = 0; g >= 0; ++i) {
+      const int g_next = fetch(i + 1);
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
@@ -129,22 +153,25 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      g = g_next;
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (lane 0 issues everything)
-    const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(G.nkp), 0u, 0u);
-    const uint32_t idesc_o = make_idesc_bf16(128, SD, 0u, 1u);   // B = V is MN-major ([key][d], d contiguous)
-    const int ksteps = G.nkp >> 4;
+    // ------------------------------------------------------------------ MMA issuer (one elected lane issues everything)
+    // Literal TMEM addresses (this CTA owns all 512 columns, so the allocation starts at 0) and an elected block keep
+    // every tcgen05.mma operand in uniform registers: the 15 P V instructions of a tile go out back to back.
+    if (tmem_base != 0) __trap();
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(KS * 16), 0u, 0u);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, SD, 0u, 1u);   // B = V is MN-major ([key][d], d contiguous)
     auto issue_pv = [&](int j, uint32_t v_addr, uint32_t par, int release_stage) {
       mbar_wait(&p_full[j], par);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + j * 256 + 128;
-        const uint32_t a_tmem = tmem_base + j * 256;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t bdesc = make_smem_desc_sw128(v_addr + ks * 2048, kMatBytes, 1024);
-          tc_mma_bf16_ts(d_tmem, a_tmem + ks * 8, bdesc, idesc_o, ks > 0 ? 1u : 0u);
-        }
+      if (elect_one()) {
+        const uint32_t d_tmem = j * 256 + 128;
+        const uint32_t a_tmem = j * 256;
+        const uint64_t bdesc = make_smem_desc_sw128(v_addr, kMatBytes, 1024);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          tc_mma_bf16_ts(d_tmem, a_tmem + ks * 8, bdesc + ks * 128, idesc_o, ks > 0 ? 1u : 0u);
         tc_commit(&o_full[j]);
         if (release_stage >= 0) tc_commit(&empty[release_stage]);
       }
@@ -153,7 +180,8 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
     uint32_t prev_v = 0;
     int prev_stage = -1;
     int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    for (;; ++i) {
+      if (group_of(i) < 0) break;
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1, par = i & 1;
       const uint32_t q_addr = smem_u32(smem + s * kStageBytes);
@@ -164,13 +192,12 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
       for (int j = 0; j < 2; ++j) {
         mbar_wait(&buf_free[j], par ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
+          const uint64_t adesc = make_smem_desc_sw128(q_addr + j * kTileBytes, 0, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(k_addr, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(q_addr + j * kTileBytes + k * 32, 0, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(k_addr + k * 32, 0, 1024);
-            tc_mma_bf16(tmem_base + j * 256, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(j * 256, adesc + k * 2, bdesc + k * 2, idesc_s, k > 0 ? 1u : 0u);
           tc_commit(&s_full[j]);
         }
         __syncwarp();
@@ -191,8 +218,9 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
     const int r_tile = q * 32 + lane;
     const int r = j * 128 + r_tile;            // query index inside the group; r == n is the CLS query
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 256;
-    int i = 0;
-    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
+      const int g = group_of(i);
+      if (g < 0) break;
       const int s = i & 1;
       const uint32_t par = i & 1;
       const int h = g % G.H, rest = g / G.H, f = rest % G.F, b = rest / G.F;
@@ -200,16 +228,15 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
       const int limit = (r == G.n && f != 0) ? G.n : G.nk;
       mbar_wait(&s_full[j], par);
       tc_fence_after();
-      uint32_t v[32];
       // ONE pass over the score row. Reading S out of TMEM is what bounds this kernel (64 B/clk per SM: a 128 x 240 fp32
       // tile costs ~1.9 k clk per pass), so the row maximum is not found in a pass of its own: chunk by chunk (32 keys),
       // p = 2^(s*log2e - m2) against a running reference m2 that starts as the maximum of the first chunk and is only
       // moved when a later chunk exceeds it by more than 2^8 (then the few P chunks already written are re-scaled in
       // TMEM - rare, and exact: softmax is shift-invariant and bf16 / fp32 carry the exponent). P never exceeds 2^8.
+      // A tcgen05.ld takes ~220 clk to come back: the next chunk's load is issued right after the wait for the current
+      // one (tcgen05.wait::ld has no groups), so it is in flight while the current chunk is computed.
       float m2 = -INFINITY, sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        ld32_wait(t_row + c * 32, v);
+      auto chunk = [&](const int c, uint32_t (&v)[32]) {
         float cm = -INFINITY;
         if (c < NCH - 1) {
 #pragma unroll
@@ -256,6 +283,19 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
           pk[e >> 1] = pack_bf16x2(p0, p1);
         }
         tmem_st_32x32b_x16(t_row + c * 16, pk);
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(t_row, va);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld_wait();
+        if (c & 1) {
+          if (c + 1 < NCH) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, va);
+          chunk(c, vb);
+        } else {
+          if (c + 1 < NCH) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
+          chunk(c, va);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -323,6 +363,14 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&g_fw_done, 1u) == gridDim.x - 1) {   // last CTA out re-arms the scheduler for the next launch
+      g_fw_next = 0;
+      g_fw_done = 0;
+      __threadfence();
+    }
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -345,9 +393,9 @@ __global__ void __launch_bounds__(SD) attn_cls_combine_kernel(const SpaceGeom G)
   if (d == 0 && G.lse != nullptr) G.lse[static_cast<long long>(bh) * G.T] = (M + log2f(L)) * kLn2;
 }
 
-template <int NCH>
+template <int KS>
 int launch_space_tc(const CUtensorMap& tm, const SpaceGeom& G, cudaStream_t s) {
-  auto kern = attn_space_tc_fwd_kernel<NCH>;
+  auto kern = attn_space_tc_fwd_kernel<KS>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem);
@@ -814,7 +862,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
   uint64_t* math_done = bars + 14;   // [2] math -> MMA: P^T, dS^T in TMEM, dS^T in the ring
   uint64_t* acc_full = bars + 16;    // MMA -> epilogue: dV, dK of a key tile complete
   uint64_t* acc_free = bars + 17;    // epilogue -> MMA
-  uint64_t* dq_full = bars + 18;     // [2] MMA -> epilogue: dQ accumulator 1 (complete after sub-unit 5) / 0 (after 7)
+  uint64_t* dq_full = bars + 18;     // [2] MMA -> epilogue: dQ of the query half that completes after sub-unit 5 / after 7
   uint64_t* dq_free = bars + 20;     // [2] epilogue -> MMA
   uint64_t* dl_full = bars + 22;     // [3] delta warps -> math: lse2 / delta of a group ready
   uint64_t* dl_free = bars + 25;     // [3] math -> delta warps
@@ -1058,8 +1106,11 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
       mbar_wait(&math_done[v & 1], (v >> 1) & 1);
       DBG2(it, v * 4 + 3);
       if ((v & 3) == 0) mbar_wait(acc_free, (kt & 1) ^ 1);       // the first accumulation into dV / dK of a key tile overwrites them
-      if (v == 1) mbar_wait(&dq_free[1], (it & 1) ^ 1);           // ... and so does the first one into a dQ accumulator
-      if (v == 3) mbar_wait(&dq_free[0], (it & 1) ^ 1);
+      // ... and so does the first one into a dQ accumulator. The accumulator follows the query half (half 0 -> columns
+      // 384.., half 1 -> 448..), so the one this group finishes LAST (sub-unit 7) is the one the next group starts
+      // SECOND (sub-unit 3): the epilogue warps get three sub-units to drain it instead of one.
+      if (v == 1) mbar_wait(&dq_free[0], (it & 1) ^ 1);           // half `flip`: the previous group's early one
+      if (v == 3) mbar_wait(&dq_free[1], (it & 1) ^ 1);           // half `1 ^ flip`: the previous group's late one
       DBG2(it, 104 + v);
       tc_fence_after();
       if (elect_one()) {
@@ -1080,11 +1131,11 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
         if (v & 1) {                                               // dQ of the pair (v - 1, v): 128 queries
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)                           // k = 16 keys per step, A = dS^T read MN-major
-            tc_mma_bf16(t_dq + slot * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
+            tc_mma_bf16(t_dq + (slot ^ flip) * SD, off(mR, ((v - 1) & 3) * kTileBytes + ks * 2048),
                         off(mK, (kt * 128 + ks * 16) * 128), idesc_mn, (kt > 0 || ks > 0) ? 1u : 0u);
         }
         if (v == 3) tc_commit(&empty_kv[0]);
-        if (v == 5) tc_commit(&dq_full[0]);                                      // accumulator 1
+        if (v == 5) tc_commit(&dq_full[0]);                                      // query half 1 ^ flip is complete
         if (v == 7) { tc_commit(&dq_full[1]); tc_commit(&empty_kv[1]); }
       }
       __syncwarp();
@@ -1339,7 +1390,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
           const int qrow = ((i & 1) ^ 1) * 128 + q4 * 32;
           mbar_wait(&dq_full[0], i & 1);
           tc_fence_after();
-          drain(tmem_base + lane_off + 448, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
+          drain(tmem_base + lane_off + 384 + ((i & 1) ^ 1) * 64, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&dq_free[0]);
@@ -1362,7 +1413,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
           mbar_wait(&dq_full[1], i & 1);
           if (warp == 12) DBG2(i, 70);
           tc_fence_after();
-          drain(tmem_base + lane_off + 384, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
+          drain(tmem_base + lane_off + 384 + (i & 1) * 64, G.scale, pv, (qrow + lane == n && cls != nullptr) ? cls : nullptr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&dq_free[1]);
@@ -1422,12 +1473,15 @@ int launch_space_tc_fwd(const oat_attn_args* a, cudaStream_t s) {
   CUtensorMap tm;
   int rc = make_tmap_bf16_2d(&tm, a->qkv, 3ull * a->H * SD, 1ull * a->B * a->T, a->ld_qkv, a->n);
   if (rc != OAT_OK) return rc;
-  const int nch = (G.nkp + 31) / 32;
-  switch (nch) {
-    case 5: rc = launch_space_tc<5>(tm, G, s); break;
-    case 6: rc = launch_space_tc<6>(tm, G, s); break;
-    case 7: rc = launch_space_tc<7>(tm, G, s); break;
-    case 8: rc = launch_space_tc<8>(tm, G, s); break;
+  switch (G.nkp >> 4) {
+    case 9: rc = launch_space_tc<9>(tm, G, s); break;
+    case 10: rc = launch_space_tc<10>(tm, G, s); break;
+    case 11: rc = launch_space_tc<11>(tm, G, s); break;
+    case 12: rc = launch_space_tc<12>(tm, G, s); break;
+    case 13: rc = launch_space_tc<13>(tm, G, s); break;
+    case 14: rc = launch_space_tc<14>(tm, G, s); break;
+    case 15: rc = launch_space_tc<15>(tm, G, s); break;
+    case 16: rc = launch_space_tc<16>(tm, G, s); break;
     default: return set_error(OAT_ERR_ARG, "attn_space_tc: unsupported key count %d", G.nk);
   }
   if (rc != OAT_OK) return rc;

@@ -283,6 +283,47 @@ def test_space_attention_tcgen05_fwd(B, F, n, H):
     assert (l_tc - l_old).abs().max() < 2e-3, (l_tc - l_old).abs().max()
 
 
+@pytest.mark.parametrize("B,F,n,H", [(6, 8, 232, 12), (5, 5, 196, 7), (5, 7, 128, 9), (4, 6, 250, 8), (9, 4, 191, 5),
+                                     (7, 4, 193, 6)])
+def test_space_attention_tcgen05_bwd_pipelined_many_groups(B, F, n, H, monkeypatch):
+    """The pipelined tcgen05 backward (dynamic group scheduler, operands released tile by tile, query halves visited in
+    alternating order, dQ accumulators handed over between groups) with several groups per SM, launched three times in a
+    row (the scheduler's counters re-arm themselves), against the mma.sync kernel on the same inputs. Geometries: the
+    bench one, 64-query blocks cut by the CLS row at every position (n = 128, 191, 193, 196, 250)."""
+    from oa_transformer_b200 import ops
+    assert B * F * H > 148
+    T = 1 + F * n
+    qkv16 = _qkv(B, T, H, 31, scale=1.2)
+    dout16 = torch.randn(B, T, H * 64, generator=gen(32)).to(BF)
+    qkv = qkv16.reshape(B * T, 3 * H * 64).cuda()
+    dout = dout16.reshape(B * T, H * 64).cuda()
+    out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
+    lse = torch.zeros(B * H * T, device="cuda")
+    ws = torch.empty(ops.attn_fwd_workspace_floats(ops.MODE_SPACE, B, H, F, n), device="cuda")
+    ops.attn_fwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
+    acc = torch.empty(B * H * 3 * 64, device="cuda")
+    res = []
+    for rep in range(3):
+        dqkv = torch.full_like(qkv, float("nan"))
+        ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc)
+        torch.cuda.synchronize()
+        res.append(dqkv.float().view(B, T, 3, H * 64))
+    monkeypatch.setenv("OAT_SPACE_BWD_LEGACY", "1")
+    ref = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, qkv, out, lse, dout, ref, 0.125, acc)
+    torch.cuda.synchronize()
+    ref = ref.float().view(B, T, 3, H * 64)
+    assert torch.isfinite(ref).all()
+    for r in res:
+        assert torch.isfinite(r).all()          # every row of every group was written
+        for i, name in enumerate("qkv"):
+            assert rel(r[:, :, i], ref[:, :, i]) < 2e-3, (name, rel(r[:, :, i], ref[:, :, i]))
+            assert rel(r[:, 0, i], ref[:, 0, i]) < 2e-3, (name, "cls", rel(r[:, 0, i], ref[:, 0, i]))
+    # Launch-to-launch: the dynamic scheduler decides which SM iteration a group lands in, and with it the order in which
+    # the group's query halves are accumulated into dV / dK (fp32, in TMEM): equal to fp32 rounding, not bit-identical.
+    assert rel(res[0], res[1]) < 1e-4 and rel(res[0], res[2]) < 1e-4
+
+
 @pytest.mark.parametrize("late", ["ramp", "spike", "cls"])
 def test_space_attention_single_pass_softmax_reference_moves(late):
     """The forward softmax runs ONE pass over each score row with a running reference (first-chunk maximum, moved only
