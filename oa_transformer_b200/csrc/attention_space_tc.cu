@@ -61,12 +61,22 @@ __device__ __forceinline__ void ld32_wait(uint32_t taddr, uint32_t (&v)[32]) {
   tmem_ld_wait();
 }
 
-// dynamic group scheduler of the forward kernel (same scheme as the pipelined backward, see g_b2_next)
-__device__ unsigned int g_fw_next = 0, g_fw_done = 0;
+// Dynamic group scheduler (forward and pipelined backward): groups are handed out by an atomic counter instead of a
+// fixed stride - with a fixed stride the slowest SMs (whole TPCs ~20 % behind the median: memory-side placement) set the
+// kernel time (measured on the backward: 417-439 k cycles for the slowest CTA against a median of 343 k). Each launch
+// takes the next {next, done} counter pair of a small pool, so launches in flight on different streams never share
+// one; the last CTA of a launch to finish re-arms its pair (no memset between launches).
+constexpr int kSchedSlots = 32;
+__device__ unsigned int g_sched[2][kSchedSlots][2];      // [forward | backward][slot][next, done]
+static unsigned int next_sched_slot(int which) {
+  static unsigned int counters[2] = {0, 0};
+  return __atomic_fetch_add(&counters[which], 1u, __ATOMIC_RELAXED) % kSchedSlots;
+}
 
 template <int KS>   // KS = 16-key steps of the P V product = padded key count / 16
 __global__ void __launch_bounds__(kSpThreads, 1)
-attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGeom G) {
+attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGeom G, const int sched_slot) {
+  unsigned int* const sched = g_sched[0][sched_slot];
   constexpr int NCH = (KS + 1) / 2;            // 32-key chunks of a score row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,8 +119,8 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
   tc_fence_after();
   pdl_wait();                   // shared memory cleared, barriers and TMEM ready: now wait for the qkv GEMM
   const uint32_t tmem_base = *tmem_slot;
-  // Groups are handed out by an atomic counter (see g_b2_next: a fixed stride lets the SMs with the longest path to
-  // memory set the kernel time); the producer draws them one iteration ahead and publishes them in a small ring.
+  // Groups are handed out by an atomic counter (see g_sched); the producer draws them one iteration ahead and publishes
+  // them in a small ring.
   auto group_of = [&](int i) -> int {
     mbar_wait(&sched_full[i & 3], (i >> 2) & 1);
     return sched_g[i & 3];
@@ -121,7 +131,7 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
     auto fetch = [&](int i) -> int {
       int g = 0;
       if (lane == 0) {
-        g = static_cast<int>(atomicAdd(&g_fw_next, 1u));
+        g = static_cast<int>(atomicAdd(&sched[0], 1u));
         if (g >= G.groups) g = -1;
         sched_g[i & 3] = g;
         mbar_arrive(&sched_full[i & 3]);
@@ -365,9 +375,9 @@ attn_space_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const SpaceGe
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(&g_fw_done, 1u) == gridDim.x - 1) {   // last CTA out re-arms the scheduler for the next launch
-      g_fw_next = 0;
-      g_fw_done = 0;
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out re-arms the pair for a later launch
+      sched[0] = 0;
+      sched[1] = 0;
       __threadfence();
     }
   }
@@ -404,7 +414,7 @@ int launch_space_tc(const CUtensorMap& tm, const SpaceGeom& G, cudaStream_t s) {
   }
   const int sms = num_sms();
   const int grid = G.groups < sms ? G.groups : sms;
-  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kSpThreads), kSpSmem, s, tm, G);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kSpThreads), kSpSmem, s, tm, G, static_cast<int>(next_sched_slot(0)));
   if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_fwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("attn_space_tc_fwd_kernel");
 }
@@ -821,11 +831,6 @@ __device__ long long g_dbg[8192];
 #else
 #define DBG2(it, slot) do { } while (0)
 #endif
-// Dynamic group scheduler of the pipelined backward: groups are handed out by an atomic counter instead of a fixed
-// stride (measured with a fixed stride: the slowest SMs - whole TPCs, ~20 % behind the median, memory-side placement -
-// set the kernel time: 417-439 k cycles for the slowest CTA against a median of 343 k). The last CTA to finish resets
-// the counters, so the kernel is re-launchable without a memset; instances of it must not overlap (one stream).
-__device__ unsigned int g_b2_next = 0, g_b2_done = 0;
 #ifdef OAT_SPACE_DBG
 #define DBGK(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_dbg[3900 + (slot)] = clock64() - t_kernel_start; } while (0)
 #else
@@ -842,7 +847,8 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
                           const __grid_constant__ CUtensorMap tmap_do_q, const __grid_constant__ CUtensorMap tmap_do_p,
                           const __grid_constant__ CUtensorMap tmap_o_q, const __grid_constant__ CUtensorMap tmap_o_p,
                           const __grid_constant__ CUtensorMap tmap_dqkv_a, const __grid_constant__ CUtensorMap tmap_dqkv_b,
-                          const SpaceBwdGeom G) {
+                          const SpaceBwdGeom G, const int sched_slot) {
+  unsigned int* const sched = g_sched[1][sched_slot];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
@@ -935,7 +941,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
     auto fetch = [&](int i) -> int {              // next group from the global counter, published in ring slot i & 3
       int g = 0;
       if (lane == 0) {
-        g = static_cast<int>(atomicAdd(&g_b2_next, 1u));
+        g = static_cast<int>(atomicAdd(&sched[0], 1u));
         if (g >= G.groups) g = -1;
         sched_g[i & 7] = g;
         mbar_arrive(&sched_full[i & 7]);
@@ -1435,9 +1441,9 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(&g_b2_done, 1u) == gridDim.x - 1) {   // last CTA out: every CTA has drawn its end-of-work ticket
-      g_b2_next = 0;
-      g_b2_done = 0;
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out: every CTA has drawn its end-of-work ticket
+      sched[0] = 0;
+      sched[1] = 0;
       __threadfence();
     }
   }
@@ -1551,7 +1557,8 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
     if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2 smem attr: %s", cudaGetErrorString(e));
     done2 = true;
   }
-  cudaError_t e = launch_pdl(attn_space_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, s, tqa, tqb, tqq, tqp, tdq, tdp, toq, top, tsa, tsb, G);
+  cudaError_t e = launch_pdl(attn_space_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, s, tqa, tqb, tqq, tqp, tdq, tdp, toq, top, tsa, tsb, G,
+                              static_cast<int>(next_sched_slot(1)));
   if (e != cudaSuccess) return set_error(OAT_ERR_CUDA, "attn_space_tc_bwd2_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("attn_space_tc_bwd2_kernel");
 }
