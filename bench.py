@@ -65,7 +65,7 @@ def load_gemm_traffic():
 
 def traffic_table_path():
     """Newest committed ncu traffic table (scripts/ncu_traffic_table.py output)."""
-    for name in ("r2_kernel_traffic.json", "r1_kernel_traffic.json"):
+    for name in ("r2c_kernel_traffic.json", "r2_kernel_traffic.json", "r1_kernel_traffic.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             return path
