@@ -133,7 +133,7 @@ constexpr int kClsParts = 2 * kTimeWarps;    // partials per CTA (two 16-row til
 //   key side     P^T, dS^T by movmatrix;  s_cj = k_j.q_cls, dp_cj = v_j.dO_cls -> P_cj, dS_cj
 //                dK  = dS^T Q + dS_cj q_cls          dV = P^T dO + P_cj dO_cls
 //   CLS rows     dQ_cls += sum_j dS_cj k_j,  dK_cls += sum_i ds_i0 q_i,  dV_cls += sum_i p_i0 dO_i  (row-vector x matrix
-//                MMAs whose A operand has a single non-zero row) -> shared-memory atomics -> one global atomic per CTA.
+//                MMAs whose A operand has a single non-zero row) -> per-warp shared accumulators -> one global atomic per CTA.
 // One ldmatrix.x4 of a staged (16 rows x 16 dims) block is both the A fragment of that block and the B fragments of
 // its two 8-row halves, so Q, K, V, dO are read from shared memory once for all score-type products.
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
@@ -225,13 +225,18 @@ __device__ __forceinline__ void store_acc_rows(uint8_t* arr, int R0, int lane, c
     }
   }
 }
-// row 0 of the accumulator tile (lanes 0-3) -> shared accumulators
+// row 0 of the accumulator tile (lanes 0-3) -> this warp's private shared accumulators. Lane t owns dims 8j + 2t, +1 of
+// its warp's slot for the whole kernel, so a plain read-add-write does (shared fp32 atomicAdd is a CAS loop: 96 of them
+// per warp were a third of the kernel's stall samples).
 __device__ __forceinline__ void add_row0(float* dst, int lane, const float (&acc)[8][4]) {
   if (lane < 4) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(dst + 8 * j + 2 * lane, acc[j][0]);
-      atomicAdd(dst + 8 * j + 2 * lane + 1, acc[j][1]);
+      float2* p = reinterpret_cast<float2*>(dst + 8 * j + 2 * lane);
+      float2 v = *p;
+      v.x += acc[j][0];
+      v.y += acc[j][1];
+      *p = v;
     }
   }
 }
@@ -384,22 +389,31 @@ __global__ void __launch_bounds__(kRows, MINB) attn_time_fwd_kernel(const TimeGe
 
 
 // Merges the per-tile partials of the CLS query with the (CLS query, CLS key) pair; writes out row 0 and lse[0].
-// One CTA per (batch, head): 4 slices of 64 threads walk the partials 4-way interleaved, then combine through smem.
-constexpr int kCombSlices = 4;
+// One CTA per (batch, head): 8 slices of 64 threads walk the partials 8-way interleaved (all loads of a slice are
+// independent: the kernel is a latency chain otherwise), warp 0 meanwhile scores the (CLS, CLS) pair, then slice 0
+// combines through shared memory.
+constexpr int kCombSlices = 8;
 __global__ void __launch_bounds__(kCombSlices * TD) attn_time_cls_combine_kernel(const TimeGeom G) {
-  __shared__ float sM[kCombSlices], sL[kCombSlices], sO[kCombSlices][TD];
+  __shared__ float sM[kCombSlices], sL[kCombSlices], sO[kCombSlices][TD], sScc;
   const int bh = blockIdx.x, b = bh / G.H, h = bh - b * G.H;
   const int d = threadIdx.x & (TD - 1), slice = threadIdx.x >> 6;
   const int HD3 = G.H * TD;
   const int parts = G.chunks * kClsParts;
   const float* part = G.cls_part + static_cast<long long>(bh) * parts * kClsPartT;
   const __nv_bfloat16* base = G.qkv + static_cast<long long>(b) * G.T * G.ld_qkv + h * TD;
+  if (threadIdx.x < 32) {                                       // q_cls . k_cls, two dims per lane
+    const float2 qc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * threadIdx.x));
+    const float2 kc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + HD3 + 2 * threadIdx.x));
+    const float scc = warp_sum(qc.x * kc.x + qc.y * kc.y);
+    if (threadIdx.x == 0) sScc = scc;
+  }
   // slice-local max, then the running sums relative to it
   float m = -INFINITY;
+#pragma unroll 8
   for (int p = slice; p < parts; p += kCombSlices) m = fmaxf(m, part[p * kClsPartT]);
   float l = 0.f, o = 0.f;
   if (m > -INFINITY) {
-#pragma unroll 4
+#pragma unroll 8
     for (int p = slice; p < parts; p += kCombSlices) {
       const float w = __expf(part[p * kClsPartT] - m);         // exp(-inf) = 0 for empty partials
       l = fmaf(part[p * kClsPartT + 1], w, l);
@@ -410,8 +424,7 @@ __global__ void __launch_bounds__(kCombSlices * TD) attn_time_cls_combine_kernel
   sO[slice][d] = o;
   __syncthreads();
   if (slice == 0) {
-    float scc = 0.f;
-    for (int k = 0; k < TD; ++k) scc = fmaf(__bfloat162float(base[k]), __bfloat162float(base[HD3 + k]), scc);
+    const float scc = sScc;
     float M = scc;
 #pragma unroll
     for (int s2 = 0; s2 < kCombSlices; ++s2) M = fmaxf(M, sM[s2]);
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   uint8_t* Cm = Ds + kArr;                                                  // 4 CLS matrices [8][128 B]: q, k, v, dO
   float* sLse = reinterpret_cast<float*>(Cm + 4 * 1024);                    // [kRows]
   float* sDelta = sLse + kRows;                                             // [kRows]
-  float* sAcc = sDelta + kRows;                                             // [3][64]: dq_cls, dk_cls, dv_cls
+  float* sAcc = sDelta + kRows;                                             // [warp][3][64]: dq_cls, dk_cls, dv_cls partials
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // head-fastest block order: the H CTAs that read the 128-byte head slices of the SAME token rows (one 4.6 KB qkv row
   // holds all heads) are neighbours in launch order, so they hit the same DRAM pages at about the same time
@@ -473,7 +486,8 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
       else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  for (int i = threadIdx.x; i < 3 * TD; i += kRows) sAcc[i] = 0.f;
+  for (int i = threadIdx.x; i < kTimeWarps * 3 * TD; i += kRows) sAcc[i] = 0.f;
+  float* wAcc = sAcc + warp * 3 * TD;
   uint4 oraw[8];
   {  // O chunks of the rows this lane helps with (coalesced), for delta = dO . O
     const int c = lane & 7;
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
     mma_rows_t(aK, R0, lane, dSa, acc, Rq, acc2);
     mma_cls_t(mK, lane, E0, acc);
-    add_row0(sAcc, lane, acc2);
+    add_row0(wAcc, lane, acc2);
     __syncwarp();                                               // every lane has loaded its V / K fragments of this tile
     store_acc_rows<true>(Vs, R0, lane, acc, G.scale);
     // ---- dK = dS^T Q + dS_cj q_cls (-> K rows) ; dK_cls += ds_.0 Q
@@ -607,14 +621,14 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
     mma_rows_t(aQ, R0, lane, dSTa, acc, Rk, acc2);
     mma_cls_t(mQ, lane, Ec, acc);
-    add_row0(sAcc + TD, lane, acc2);
+    add_row0(wAcc + TD, lane, acc2);
     store_acc_rows<false>(Ks, R0, lane, acc);
     // ---- dV = P^T dO + P_cj dO_cls (-> Q rows) ; dV_cls += p_.0 dO
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f; }
     mma_rows_t(aD, R0, lane, PTa, acc, Rv, acc2);
     mma_cls_t(mD, lane, Epc, acc);
-    add_row0(sAcc + 2 * TD, lane, acc2);
+    add_row0(wAcc + 2 * TD, lane, acc2);
     __syncwarp();                                               // every lane is done with the Q rows of this tile
     store_acc_rows<false>(Qs, R0, lane, acc);
   }
@@ -626,7 +640,12 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
     store_rows_warp_n<3>(arrs, dsts, G.ld_dqkv, tok, warp, lane);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * TD; i += kRows) atomicAdd(G.cls_acc + static_cast<long long>(bh) * 3 * TD + i, sAcc[i]);
+  for (int i = threadIdx.x; i < 3 * TD; i += kRows) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTimeWarps; ++w) v += sAcc[w * 3 * TD + i];
+    atomicAdd(G.cls_acc + static_cast<long long>(bh) * 3 * TD + i, v);
+  }
 }
 
 // Adds the (CLS query, CLS key) pair and writes row 0 of dqkv: dq = scale * (acc_q + dS_cc k_c), dk = acc_k + dS_cc q_c,
@@ -719,7 +738,7 @@ int launch_time_fwd(const oat_attn_args* a, cudaStream_t s, bool* cls_done) {
 int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   const TimeGeom G = make_time_geom(a);
   const int grid = a->B * a->H * G.chunks;
-  constexpr int smem = 4 * kArr + 4 * 1024 + (2 * kRows + 3 * TD) * static_cast<int>(sizeof(float));
+  constexpr int smem = 4 * kArr + 4 * 1024 + (2 * kRows + kTimeWarps * 3 * TD) * static_cast<int>(sizeof(float));
   static bool done = false;
   int rc = set_smem_once(attn_time_bwd_kernel, smem, &done, "attn_time_bwd");
   if (rc != OAT_OK) return rc;
