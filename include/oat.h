@@ -42,7 +42,12 @@ int oat_device_check(void);
  *   b_major = 0: B stored [N][ldb], K contiguous.   b_major = 1: B stored [K][ldb], N contiguous.
  * epilogue order: alpha, +bias[N], first scale_cols columns *= scale, activation, +residual[M][ldr] (fp32), store.
  *   act 0: none | 1: GELU(erf) forward - GELU of the fp32 accumulator goes to the outputs and its derivative
- *   GELU'(x) (bf16) to out2_bf16, which is exactly the aux operand of the backward GEMM | 2: multiply by aux_bf16[M][ld_aux] (the stored GELU') | 3: ReLU.
+ *   GELU'(x) (bf16) to out2_bf16, which is exactly the aux operand of the backward GEMM | 2: multiply by aux_bf16[M][ld_aux] (the stored GELU') | 3: ReLU
+ *   | 4: row dots - the bf16 output is unchanged and rowdot[(c / 64) * ld_rowdot + r] = sum over the 64-column block c / 64 of
+ *   bf16(out[r][.]) * aux_bf16[r][.] (fp32). With out = dO (the dgrad of the attention output projection) and aux = O this is
+ *   delta = rowsum(dO * O) per head of the softmax backward (what autograd derives for video_transformer.py:122-131), handed to
+ *   oat_attn_bwd through oat_attn_args.delta so that the attention backward does not read O. Needs N % 256 == 0, a bf16
+ *   output only, 16-byte aligned out_bf16 / aux_bf16 rows.
  *   accumulate = 1: atomically add into out_f32 (gradient accumulation / split-K). split_k = 0 lets the library pick.
  * Replaces: nn.Linear at video_transformer.py:102,133,46-49; Conv2d-as-GEMM :69; oa_model.py:68-75; torch.mm in
  * model/model.py:171; DistilBERT linears; and the autograd dgrad/wgrad of each. */
@@ -61,6 +66,7 @@ typedef struct oat_gemm_args {
   void* out2_bf16; int64_t ld2;
   int32_t accumulate;
   int32_t split_k;
+  float* rowdot; int64_t ld_rowdot;   /* act 4 only: [N / 64][ld_rowdot >= M] fp32 */
 } oat_gemm_args;
 int oat_gemm_bf16(const oat_gemm_args* args, oat_stream_t stream);
 
@@ -109,6 +115,9 @@ typedef struct oat_attn_args {
   float dropout_p;
   uint32_t dropout_site;
   uint64_t dropout_seed;
+  /* backward, modes 0/1, optional: delta[h * ld_delta + b*T + t] = sum_d dout[b*T + t][h*64 + d] * out[b*T + t][h*64 + d]
+   * precomputed by the GEMM that produced dout (oat_gemm_bf16 act 4). NULL: the kernels compute it from out and dout. */
+  const float* delta; int64_t ld_delta;
 } oat_attn_args;
 size_t oat_attn_fwd_workspace_floats(int32_t mode, int32_t B, int32_t H, int32_t F, int32_t n);
 int oat_attn_fwd(const oat_attn_args* args, oat_stream_t stream);

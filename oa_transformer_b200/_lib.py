@@ -33,6 +33,7 @@ class GemmArgs(ctypes.Structure):
         ("out2_bf16", c_vp), ("ld2", c_i64),
         ("accumulate", c_i32),
         ("split_k", c_i32),
+        ("rowdot", c_vp), ("ld_rowdot", c_i64),
     ]
 
 

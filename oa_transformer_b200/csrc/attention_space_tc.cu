@@ -445,6 +445,8 @@ struct SpaceBwdGeom {
   __nv_bfloat16* dqkv;
   float* cls_acc;
   float scale;
+  const float* delta;     // optional [H][ld_delta]: rowsum(dO * O) from the dO-producing GEMM (pipelined kernel only)
+  long long ld_delta;
 };
 
 constexpr int kBwdDsBytes = 2 * kTileBytes;                       // dS^T of one unit: 2 blocks of [128 keys x 64 queries]
@@ -972,7 +974,7 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
 #pragma unroll
             for (int m = 0; m < 3; ++m) tma_prefetch_2d(pt ? &tmap_qkv_p : &tmap_qkv_q, m * HDIM + hn * SD, rown + pq * 64);
             tma_prefetch_2d(pt ? &tmap_do_p : &tmap_do_q, hn * SD, rown + pq * 64);
-            tma_prefetch_2d(pt ? &tmap_o_p : &tmap_o_q, hn * SD, rown + pq * 64);
+            if (G.delta == nullptr) tma_prefetch_2d(pt ? &tmap_o_p : &tmap_o_q, hn * SD, rown + pq * 64);   // O feeds delta only
           }
         }
       }
@@ -1188,6 +1190,26 @@ attn_space_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv_a, const 
       float* l2 = lse2_s + db * 256;
       float* dl = del_s + db * 256;
       const float* lse_g = G.lse + (static_cast<long long>(b) * G.H + h) * G.T;
+      if (G.delta != nullptr) {
+        // delta came out of the epilogue of the GEMM that produced dO (oat_gemm_bf16 act 4): two 4-byte loads per query
+        // row instead of 256 bytes of O and dO (their loads cost a fifth of this kernel's cycles)
+        const float* del_g = G.delta + static_cast<long long>(h) * G.ld_delta + tok_base;
+        float lv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = u * 64 + t64;
+          const int rc = r < n ? r : n;
+          const long long tl = (rc == n) ? 0 : 1 + f * n + rc;
+          lv[u] = __ldg(lse_g + tl);
+          dv[u] = __ldg(del_g + tl);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = u * 64 + t64;
+          dl[r] = r <= n ? -dv[u] : 0.f;
+          l2[r] = r <= n ? -lv[u] * kLog2e : 0.f;
+        }
+      } else
 #pragma unroll 1
       for (int p0 = 0; p0 < 16; p0 += 4) {
         // 4 rows per thread in flight: all 17 loads of a batch are issued before the first use (no branches: rows past
@@ -1515,6 +1537,7 @@ int launch_space_tc_bwd(const oat_attn_args* a, cudaStream_t s) {
   G.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
   G.cls_acc = a->cls_acc;
   G.scale = a->scale;
+  G.delta = a->delta; G.ld_delta = a->ld_delta;
   const int sms = num_sms();
   const int grid = G.groups < sms ? G.groups : sms;
   static const bool legacy = getenv("OAT_SPACE_BWD_V1") != nullptr;

@@ -35,6 +35,8 @@ struct TimeGeom {
   float scale;
   float* cls_acc;                       // [B*H][3][64]: dq_cls (unscaled), dk_cls, dv_cls
   float* cls_part;                      // forward: [B*H][chunks*warps][2+64] partials of the CLS query (or null)
+  const float* delta;                   // backward, optional: [H][ld_delta] rowsum(dO * O) from the dO-producing GEMM
+  long long ld_delta;
 };
 
 // ------------------------------------------------------------------------------------------------ shared-memory rows
@@ -443,6 +445,8 @@ __global__ void __launch_bounds__(kCombSlices * TD) attn_time_cls_combine_kernel
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// EXT_DELTA: delta = rowsum(dO * O) arrives from the GEMM that produced dO (oat_gemm_bf16 act 4) - O is not read at all.
+template <bool EXT_DELTA>
 __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom G) {
   pdl_launch_dependents();
   pdl_wait();
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   for (int i = threadIdx.x; i < kTimeWarps * 3 * TD; i += kRows) sAcc[i] = 0.f;
   float* wAcc = sAcc + warp * 3 * TD;
   uint4 oraw[8];
-  {  // O chunks of the rows this lane helps with (coalesced), for delta = dO . O
+  if constexpr (!EXT_DELTA) {  // O chunks of the rows this lane helps with (coalesced), for delta = dO . O
     const int c = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it)
@@ -502,14 +506,18 @@ __global__ void __launch_bounds__(kRows, 3) attn_time_bwd_kernel(const TimeGeom 
   // CLS query statistics: lse_c, delta_c = dO_cls . O_cls (lane holds dims 2 * lane, +1)
   const float lse_c = lrow[0];
   float delta_c;
-  {
+  if constexpr (EXT_DELTA) {
+    const float* drow = G.delta + static_cast<long long>(h) * G.ld_delta + row0;
+    sDelta[threadIdx.x] = my_tok >= 0 ? drow[my_tok] : 0.f;
+    delta_c = drow[0];
+  } else {
     const float2 dc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dbase + 2 * lane));
     const float2 oc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(obase + 2 * lane));
     delta_c = warp_sum(dc.x * oc.x + dc.y * oc.y);
   }
   cp_async_wait_all_t();
   __syncthreads();                                              // CLS matrices + sAcc zeroing are CTA-wide
-  {
+  if constexpr (!EXT_DELTA) {
     const int c = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -688,6 +696,7 @@ static TimeGeom make_time_geom(const oat_attn_args* a) {
   G.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
   G.scale = a->scale; G.cls_acc = a->cls_acc;
   G.cls_part = nullptr;
+  G.delta = a->delta; G.ld_delta = a->ld_delta;
   return G;
 }
 
@@ -739,10 +748,15 @@ int launch_time_bwd(const oat_attn_args* a, cudaStream_t s) {
   const TimeGeom G = make_time_geom(a);
   const int grid = a->B * a->H * G.chunks;
   constexpr int smem = 4 * kArr + 4 * 1024 + (2 * kRows + kTimeWarps * 3 * TD) * static_cast<int>(sizeof(float));
-  static bool done = false;
-  int rc = set_smem_once(attn_time_bwd_kernel, smem, &done, "attn_time_bwd");
-  if (rc != OAT_OK) return rc;
-  if (launch_pdl(attn_time_bwd_kernel, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_bwd_kernel");
+  static bool done0 = false, done1 = false;
+  int rc;
+  if (G.delta != nullptr) {
+    if ((rc = set_smem_once(attn_time_bwd_kernel<true>, smem, &done1, "attn_time_bwd")) != OAT_OK) return rc;
+    if (launch_pdl(attn_time_bwd_kernel<true>, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_bwd_kernel");
+  } else {
+    if ((rc = set_smem_once(attn_time_bwd_kernel<false>, smem, &done0, "attn_time_bwd")) != OAT_OK) return rc;
+    if (launch_pdl(attn_time_bwd_kernel<false>, dim3(grid), dim3(kRows), smem, s, G) != cudaSuccess) return check_launch("attn_time_bwd_kernel");
+  }
   rc = check_launch("attn_time_bwd_kernel");
   if (rc != OAT_OK) return rc;
   attn_time_cls_finalize_kernel<<<a->B * a->H, 32, 0, s>>>(G);

@@ -167,6 +167,7 @@ bool skinny_gemm_supported(const oat_gemm_args* a) {
   // chip on the tcgen05 kernel is ~10x faster there (measured: 1.5 vs 37 us for K = 6144, N = 768), at the price of
   // floating-point atomics
   if (a->accumulate) return false;
+  if (a->act == 4) return false;       // row dots live in the tcgen05 kernel's epilogue
   auto even = [](const void* p, long long ld, int esz) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % (2 * esz)) == 0 && ld % 2 == 0); };
   return even(a->out_f32, a->ld_f32, 4) && even(a->residual, a->ldr, 4) && even(a->out_bf16, a->ld_bf16, 2) &&
          even(a->out2_bf16, a->ld2, 2) && even(a->aux_bf16, a->ld_aux, 2);

@@ -58,6 +58,8 @@ struct GemmParams {
   float scale;
   float alpha;
   int accumulate;
+  float* rowdot;      // EPI_ROWDOT: rowdot[(col / 64) * ld_rowdot + row] = sum over the 64-column block of bf16(out) * aux
+  long long ld_rowdot;
   int idle_wait;      // epilogue warps sleep between polls while the k-loop runs (experiment knob OAT_GEMM_IDLE_WAIT)
 };
 
@@ -77,7 +79,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 // Epilogue specialisations (compile-time, so the per-element instruction count stays small - the K=768 GEMMs give the
 // epilogue only ~6 k cycles per 128x256 tile): the generic one keeps every runtime switch of oat_gemm_args.
-enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI_MULAUX = 4, EPI_ATOMIC = 5 };
+enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_F32_RES = 2, EPI_GELU = 3, EPI_MULAUX = 4, EPI_ATOMIC = 5, EPI_ROWDOT = 6 };
 
 constexpr int kBoxBytes = 32 * 128;              // one epilogue box: 32 rows x 128 B (64 bf16 or 32 fp32 columns)
 
@@ -88,7 +90,7 @@ template <int BLOCK_N, int EPI, bool TWO>
 struct GemmSmem {
   static constexpr bool kTmaEpi = EPI != EPI_GENERIC;
   // boxes per epilogue warp: output (+ second output for GELU') (+ residual / aux input)
-  static constexpr int kBoxes = !kTmaEpi ? 0 : (EPI == EPI_BF16 || EPI == EPI_ATOMIC) ? 1 : 2;
+  static constexpr int kBoxes = !kTmaEpi ? 0 : (EPI == EPI_BF16 || EPI == EPI_ATOMIC) ? 1 : 2;   // ROWDOT: output + aux input
   static constexpr int kEpiBytes = kTmaEpi ? kEpiWarps * kBoxes * kBoxBytes : kEpiWarps * kStagingFloats * 4;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kLoadN = TWO ? BLOCK_N / 2 : BLOCK_N;          // B rows staged by this CTA
@@ -300,7 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr bool kF32Out = EPI == EPI_F32_RES || EPI == EPI_ATOMIC;
     constexpr int CW = kF32Out ? 32 : 64;   // columns per 128-byte box row
     constexpr int kChunksT = BLOCK_N / CW;
-    constexpr bool kHasIn = EPI == EPI_F32_RES || EPI == EPI_MULAUX;
+    constexpr bool kHasIn = EPI == EPI_F32_RES || EPI == EPI_MULAUX || EPI == EPI_ROWDOT;
     uint8_t* box_o = epi_smem + (warp - 2) * (S::kBoxes * kBoxBytes);
     uint8_t* box_x = box_o + kBoxBytes;     // second output (GELU') or input (residual / aux); only if kBoxes == 2
     const uint32_t row_sw = static_cast<uint32_t>(lane & 7) << 4;
@@ -318,8 +320,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = (m_blk * kPair + static_cast<int>(cta_rank)) * BLOCK_M + q * 32;
       const int col0 = n_blk * BLOCK_N;
       const bool first_split = (split == 0);
-      const bool use_bias = (EPI == EPI_BF16 || EPI == EPI_F32_RES || EPI == EPI_GELU) && p.bias != nullptr && first_split;
-      const bool use_in = kHasIn && (EPI == EPI_MULAUX || (p.residual != nullptr && first_split));
+      const bool use_bias = (EPI == EPI_BF16 || EPI == EPI_F32_RES || EPI == EPI_GELU || EPI == EPI_ROWDOT) && p.bias != nullptr && first_split;
+      const bool use_in = kHasIn && (EPI == EPI_MULAUX || EPI == EPI_ROWDOT || (p.residual != nullptr && first_split));
       if (use_in && lane == 0) {              // first input box of the tile: in flight while the MMAs finish
         mbar_arrive_expect_tx(my_in_bar, kBoxBytes);
         tma_load_2d(box_x, &tmap_x, my_in_bar, col0 + half * CW, row0);
@@ -423,6 +425,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             sts128(my_o + off, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
             sts128(my_x + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
           }
+        } else if constexpr (EPI == EPI_ROWDOT) {
+          // the output row as stored (bf16) dotted with the aux row over this 64-column block: delta = dO . O of the
+          // attention backward (one head per block), so that kernel need not read O at all
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t o4[4] = {pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]))};
+            const uint32_t w[4] = {xin[j].x, xin[j].y, xin[j].z, xin[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              dot = fmaf(__uint_as_float(o4[k] << 16), __uint_as_float(w[k] << 16), dot);
+              dot = fmaf(__uint_as_float(o4[k] & 0xffff0000u), __uint_as_float(w[k] & 0xffff0000u), dot);
+            }
+            sts128(my_o + ((static_cast<uint32_t>(j) << 4) ^ row_sw), o4[0], o4[1], o4[2], o4[3]);
+          }
+          if (row0 + lane < p.M) p.rowdot[static_cast<long long>(col >> 6) * p.ld_rowdot + row0 + lane] = dot;
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -639,6 +660,8 @@ static int pick_epi(const oat_gemm_args* a) {
     return (b16_ok && !f32 && a->residual == nullptr && a->scale_cols == 0 && tma_ok(a->out2_bf16, a->ld2, 2)) ? EPI_GELU : EPI_GENERIC;
   if (a->act == 2)
     return (b16_ok && !f32 && a->residual == nullptr && a->bias == nullptr && a->scale_cols == 0 && tma_ok(a->aux_bf16, a->ld_aux, 2)) ? EPI_MULAUX : EPI_GENERIC;
+  if (a->act == 4)      // validated by the caller (oat_gemm_bf16): TMA-able bf16 output and aux, no fp32 output / residual / scale
+    return EPI_ROWDOT;
   if (a->act != 0) return EPI_GENERIC;
   if (b16_ok && !f32 && a->residual == nullptr) return EPI_BF16;
   if (f32_ok && !b16 && a->scale_cols == 0 && (a->residual == nullptr || tma_ok(a->residual, a->ldr, 4))) return EPI_F32_RES;
@@ -659,11 +682,11 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   if (rc != OAT_OK) return rc;
   to = ta;
   tx = ta;
-  if (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_MULAUX) rc = make_tmap_2d(&to, a->out_bf16, a->N, a->M, a->ld_bf16, 32, false);
+  if (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_MULAUX || EPI == EPI_ROWDOT) rc = make_tmap_2d(&to, a->out_bf16, a->N, a->M, a->ld_bf16, 32, false);
   if (EPI == EPI_F32_RES || EPI == EPI_ATOMIC) rc = make_tmap_2d(&to, a->out_f32, a->N, a->M, a->ld_f32, 32, true);
   if (rc != OAT_OK) return rc;
   if (EPI == EPI_GELU) rc = make_tmap_2d(&tx, a->out2_bf16, a->N, a->M, a->ld2, 32, false);
-  if (EPI == EPI_MULAUX) rc = make_tmap_2d(&tx, a->aux_bf16, a->N, a->M, a->ld_aux, 32, false);
+  if (EPI == EPI_MULAUX || EPI == EPI_ROWDOT) rc = make_tmap_2d(&tx, a->aux_bf16, a->N, a->M, a->ld_aux, 32, false);
   if (EPI == EPI_F32_RES && a->residual != nullptr) rc = make_tmap_2d(&tx, a->residual, a->N, a->M, a->ldr, 32, true);
   if (rc != OAT_OK) return rc;
 
@@ -693,6 +716,7 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.aux_bf16 = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16); p.ld_aux = a->ld_aux;
   p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
   p.accumulate = a->accumulate;
+  p.rowdot = a->rowdot; p.ld_rowdot = a->ld_rowdot;
   {
     const char* e = getenv("OAT_GEMM_IDLE_WAIT");
     p.idle_wait = (e != nullptr && atoi(e) != 0) ? 1 : 0;
@@ -752,6 +776,16 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
   OAT_REQUIRE(a->act != 1 || a->out2_bf16 != nullptr, "oat_gemm_bf16: GELU forward needs out2_bf16");
   OAT_REQUIRE(a->act != 2 || a->aux_bf16 != nullptr, "oat_gemm_bf16: GELU backward needs aux_bf16");
   OAT_REQUIRE(a->scale_cols % 4 == 0, "oat_gemm_bf16: scale_cols must be a multiple of 4");
+  if (a->act == 4) {
+    OAT_REQUIRE(a->rowdot != nullptr && a->aux_bf16 != nullptr && a->out_bf16 != nullptr && a->out_f32 == nullptr &&
+                    a->residual == nullptr && a->scale_cols == 0 && a->accumulate == 0 && a->alpha == 1.0f,
+                "oat_gemm_bf16: act 4 (row dots) needs rowdot, aux_bf16 and a bf16 output only");
+    OAT_REQUIRE(a->N % 256 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 && (a->ld_bf16 * 2) % 16 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0 && (a->ld_aux * 2) % 16 == 0 &&
+                    (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0),
+                "oat_gemm_bf16: act 4 needs N %% 256 == 0 and 16-byte aligned out_bf16 / aux_bf16 rows");
+    OAT_REQUIRE(a->ld_rowdot >= a->M, "oat_gemm_bf16: ld_rowdot must be >= M");
+  }
   cudaStream_t s = as_stream(stream);
   const bool amn = a->a_major != 0, bmn = a->b_major != 0;
   {
@@ -780,6 +814,7 @@ extern "C" int oat_gemm_bf16(const oat_gemm_args* a, oat_stream_t stream) {
     case EPI_GELU: OAT_GEMM_EPI(AM, BM, EPI_GELU);                                    \
     case EPI_MULAUX: OAT_GEMM_EPI(AM, BM, EPI_MULAUX);                                \
     case EPI_ATOMIC: OAT_GEMM_EPI(AM, BM, EPI_ATOMIC);                                \
+    case EPI_ROWDOT: OAT_GEMM_EPI(AM, BM, EPI_ROWDOT);                                \
     default: return launch_gemm<256, AM, BM, EPI_GENERIC, false>(a, s);               \
   }
   switch (code) {

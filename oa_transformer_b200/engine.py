@@ -42,6 +42,9 @@ SPLIT = os.environ.get("OAT_SPLIT", "1") != "0"               # split-bf16 forwa
 # on the benchmark step - the step is GPU-bound and the host already runs 3x ahead of the device, so there is no launch
 # gap to reclaim; worth turning on when the host is the slower side (small batches, busy hosts).
 GRAPH = os.environ.get("OAT_GRAPH", "0") != "0"
+# delta = rowsum(dO * O) of the attention backward from the epilogue of the dO-producing GEMM (oat_gemm_bf16 act 4) instead
+# of re-reading O inside the attention kernels. OAT_DELTA_EPI=0: the attention kernels compute it themselves.
+DELTA_EPI = os.environ.get("OAT_DELTA_EPI", "1") != "0"
 MAX_GRAPHS = 8
 
 
@@ -521,6 +524,15 @@ class VideoEngine:
         dtr = bufs.get("dtr", (M, D), F32)
         acc = bufs.get("cls_acc", (B * H * 3 * HEAD_DIM,), F32)
         dyb = bufs.get("dy.b", (M, D), F32)
+        # delta = rowsum(dO * O) per head comes out of the epilogue of the GEMM that produces dO (the dgrad of the output
+        # projection), so the attention backward kernels never read O
+        delta = bufs.get("attn_delta", (H, M), F32) if (DELTA_EPI and D % 256 == 0) else None
+
+        def dgrad_proj(dy_, w_, o_):
+            if delta is None:
+                ops.gemm(dy_, w_, b_major=1, out_bf16=da)
+            else:
+                ops.gemm(dy_, w_, b_major=1, act=ops.ACT_ROWDOT, aux=o_, rowdot=delta, out_bf16=da)
 
         for i in reversed(range(depth)):
             b = "%sblocks.%d." % (prefix, i)
@@ -538,18 +550,20 @@ class VideoEngine:
                               dx_bf16=dsr16[k], dgamma=grads[b + "norm2.weight"], dbeta=grads[b + "norm2.bias"],
                               dxsum=grads[b + "attn.proj.bias"])
             # ---- sr = x + proj_s(space_attn(qkv_s(norm1(tr))))
-            ops.gemm(dsr16[k], L["wproj_s"], b_major=1, out_bf16=da)
+            dgrad_proj(dsr16[k], L["wproj_s"], L["a_s"])
             wgrad(dsr16[k], L["a_s"], b + "attn.proj", bias=False)
-            ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv_s[k], Q_SCALE, acc)
+            ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv_s[k], Q_SCALE, acc,
+                         delta=delta)
             ops.gemm(dqkv_s[k], L["wqkv_s"], b_major=1, out_bf16=dh)
             wgrad(dqkv_s[k], L["h1"], b + "attn.qkv", ext=L["h1x"])
             ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16[k],
                               dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"],
                               dxsum=grads[b + "timeattn.proj.bias"])
             # ---- tr = x + proj_t(time_attn(qkv_t(norm3(x))))
-            ops.gemm(dtr16[k], L["wproj_t"], b_major=1, out_bf16=da)
+            dgrad_proj(dtr16[k], L["wproj_t"], L["a_t"])
             wgrad(dtr16[k], L["a_t"], b + "timeattn.proj", bias=False)
-            ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc)
+            ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc,
+                         delta=delta)
             ops.gemm(dqkv_t[k], L["wqkv_t"], b_major=1, out_bf16=dh)
             wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv", ext=L["h3x"])
             if i == region_at:      # x_i also fed region_norm: dsr += region_norm'(dtokens), in place, before the sum below

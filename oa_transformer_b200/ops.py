@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, check, lib, ptr, stream_ptr
 
-ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU, ACT_ROWDOT = 0, 1, 2, 3, 4
 
 # Kernel-launch accounting (bench.py reports it) and an optional per-launch CUDA-event profiler for the roofline lines.
 LAUNCHES = 0
@@ -47,10 +47,11 @@ def _ld(t):
 
 
 def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scale=1.0, act=ACT_NONE, aux=None,
-         residual=None, out_f32=None, out_bf16=None, out2_bf16=None, accumulate=False, split_k=0):
+         residual=None, out_f32=None, out_bf16=None, out2_bf16=None, accumulate=False, split_k=0, rowdot=None):
     """C[M,N] = alpha * A(M,K) . B(N,K)^T with the fused epilogue of oat_gemm_bf16 (include/oat.h).
 
     a_major=0: A is [M,K]; a_major=1: A is stored [K,M] (M contiguous). Same for B with N.
+    act=ACT_ROWDOT: rowdot (fp32 [N // 64, >= M]) receives the per-64-column-block dots of the bf16 output rows with aux.
     """
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if a_major == 0:
@@ -89,6 +90,9 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
         a.out2_bf16, a.ld2 = ptr(out2_bf16), _ld(out2_bf16)
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
+    if rowdot is not None:
+        assert act == ACT_ROWDOT and rowdot.dtype == torch.float32 and rowdot.shape[0] == N // 64 and rowdot.shape[1] >= M
+        a.rowdot, a.ld_rowdot = ptr(rowdot), _ld(rowdot)
     _count(1)
     # products with <= 64 rows take the mma.sync weight-stream kernel (gemm_skinny.cu) unless they accumulate: a different
     # kernel, profiled under its own name so that "gemm" is the tcgen05 kernel only
@@ -152,6 +156,7 @@ class AttnArgs(ctypes.Structure):
         ("scale", _f32),
         ("cls_acc", _vp),
         ("dropout_p", _f32), ("dropout_site", ctypes.c_uint32), ("dropout_seed", ctypes.c_uint64),
+        ("delta", _vp), ("ld_delta", _i64),
     ]
 
 
@@ -210,8 +215,12 @@ def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None, dro
         check(lib().oat_attn_fwd(ctypes.byref(a), stream_ptr()), "oat_attn_fwd")
 
 
-def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None):
+def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None, delta=None):
+    """delta (fp32 [H, >= B*T], modes 0/1): rowsum(dout * out) per head from the GEMM that produced dout (gemm act=ACT_ROWDOT)."""
     a = _attn_args(mode, B, T, H, F, n, qkv, out, lse, key_mask)
+    if delta is not None:
+        assert mode != MODE_PLAIN and delta.dtype == torch.float32 and delta.shape[0] == H and delta.shape[1] >= B * T
+        a.delta, a.ld_delta = ptr(delta), _ld(delta)
     _set_dropout(a, mode, dropout)
     assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16
     a.dout, a.ld_dout = ptr(dout), dout.stride(0)

@@ -26,6 +26,9 @@ def timeit(fn, iters=5):
 for name, mode in (("space", ops.MODE_SPACE), ("time", ops.MODE_TIME)):
     f = timeit(lambda: ops.attn_fwd(mode, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws))
     b = timeit(lambda: ops.attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc))
+    # with delta = rowsum(dO * O) handed in (engine: the projection dgrad's act-4 epilogue writes it)
+    delta = (dout.float() * out.float()).view(M, H, 64).sum(-1).t().contiguous()
+    bd = timeit(lambda: ops.attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, 0.125, acc, delta=delta))
     by, fl = ops.attn_core_work(mode, B, T, H, F, n)
-    print(json.dumps({"mode": name, "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "fwd_GBps": round(by / f / 1e6, 1),
+    print(json.dumps({"mode": name, "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "bwd_ext_delta_ms": round(bd, 4), "fwd_GBps": round(by / f / 1e6, 1),
                       "fwd_TFLOPs": round(fl / f / 1e9, 1), "bwd_TFLOPs_5mm": round(2.5 * fl / b / 1e9, 1)}))

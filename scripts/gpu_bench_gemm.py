@@ -47,6 +47,8 @@ def main():
     bias3 = torch.randn(3 * D, device=dev)
     bias1 = torch.randn(D, device=dev)
     bias4 = torch.randn(4 * D, device=dev)
+    aux1 = torch.randn(M, D, device=dev).to(BF)
+    rowdot = torch.empty(D // 64, M, device=dev)
     dw_qkv = torch.zeros(3 * D, D, device=dev)
     dw_1 = torch.zeros(4 * D, D, device=dev)
     dw_2 = torch.zeros(D, 4 * D, device=dev)
@@ -61,6 +63,7 @@ def main():
         "dgrad_fc1 [M,768,3072]  B mn-major bf16 out": (lambda: ops.gemm(x4, w1, b_major=1, out_bf16=o16_1), 2.0 * M * 4 * D * D),
         "dgrad_qkv [M,768,2304]  B mn-major bf16 out": (lambda: ops.gemm(x3, wqkv, b_major=1, out_bf16=o16_1), 2.0 * M * 3 * D * D),
         "dgrad_proj[M,768,768]   B mn-major bf16 out": (lambda: ops.gemm(x, wproj, b_major=1, out_bf16=o16_1), 2.0 * M * D * D),
+        "dgrad_proj_rowdot [M,768,768] + delta = rowsum(dO*O)": (lambda: ops.gemm(x, wproj, b_major=1, act=ops.ACT_ROWDOT, aux=aux1, rowdot=rowdot, out_bf16=o16_1), 2.0 * M * D * D),
         "wgrad_qkv [2304,768,M]  both mn-major splitK": (lambda: ops.gemm(x3, x, a_major=1, b_major=1, out_f32=dw_qkv, accumulate=True), 2.0 * M * 3 * D * D),
         "wgrad_fc1 [3072,768,M]": (lambda: ops.gemm(x4, x, a_major=1, b_major=1, out_f32=dw_1, accumulate=True), 2.0 * M * 4 * D * D),
         "wgrad_fc2 [768,3072,M]": (lambda: ops.gemm(x, x4, a_major=1, b_major=1, out_f32=dw_2, accumulate=True), 2.0 * M * 4 * D * D),

@@ -8,7 +8,7 @@ import torch
 
 from oracle import oracle as O
 
-ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU, ACT_ROWDOT = 0, 1, 2, 3, 4
 MODE_SPACE, MODE_TIME, MODE_PLAIN = 0, 1, 2
 LAUNCHES = 0
 GRAPH_REPLAYS = 0
@@ -84,7 +84,7 @@ def relu_bwd(x, dy_bf16, dx, *, rows, cols, ldx, lddx=None):
 
 
 def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scale=1.0, act=ACT_NONE, aux=None,
-         residual=None, out_f32=None, out_bf16=None, out2_bf16=None, accumulate=False, split_k=0):
+         residual=None, out_f32=None, out_bf16=None, out2_bf16=None, accumulate=False, split_k=0, rowdot=None):
     assert A.dtype == BF and B.dtype == BF
     a = A.float() if a_major == 0 else A.float().t()
     b = B.float() if b_major == 0 else B.float().t()
@@ -111,6 +111,9 @@ def gemm(A, B, *, a_major=0, b_major=0, alpha=1.0, bias=None, scale_cols=0, scal
             out_f32.copy_(c)
     if out_bf16 is not None:
         out_bf16.copy_(c.to(BF))
+    if act == ACT_ROWDOT:          # per-64-column-block dots of the stored (bf16) output rows with aux
+        M_, N_ = c.shape
+        rowdot[:, :M_] = (c.to(BF).float() * aux.float()).view(M_, N_ // 64, 64).sum(-1).t()
     _count(1)
 
 
@@ -241,7 +244,10 @@ def attn_fwd(mode, B, T, H, F, n, qkv, out, lse, key_mask=None, cls_ws=None, dro
     _count(1)
 
 
-def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None):
+def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None, key_mask=None, dropout=None, delta=None):
+    if delta is not None:          # the schedule must hand over delta = rowsum(dO * O) per head of THIS attention
+        ref = (dout.float() * out.float()).view(B * T, H, 64).sum(-1).t()
+        assert torch.allclose(delta[:, :B * T], ref, rtol=1e-4, atol=1e-5), "attn_bwd: stale or wrong delta"
     with torch.enable_grad():         # may run inside an autograd.Function.backward (grad mode off)
         x = qkv.float().view(B, T, 3, H, 64).clone().requires_grad_(True)
         q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))

@@ -29,10 +29,12 @@ def engine_on_fake_ops(monkeypatch):
     return engine
 
 
-@pytest.mark.parametrize("frames,objects", [(2, 3), (3, 0)])
-def test_video_engine_schedule_matches_oracle(engine_on_fake_ops, frames, objects):
+@pytest.mark.parametrize("frames,objects,dim,heads", [(2, 3, 128, 2), (3, 0, 128, 2), (2, 2, 256, 4)])
+def test_video_engine_schedule_matches_oracle(engine_on_fake_ops, frames, objects, dim, heads):
+    """dim 256: the backward hands delta = rowsum(dO * O) from the projection dgrad (gemm act 4) to the attention backward
+    (the stand-in's attn_bwd asserts that the delta it receives belongs to that attention's dO and O)."""
     engine = engine_on_fake_ops
-    dim, heads, depth, B = 128, 2, 2, 2
+    depth, B = 2, 2
     spec = video_tower_spec(depth=depth, dim=dim, frames=frames, grid=2, patch=16, objects=objects > 0)
     spec["vid_proj.0.weight"], spec["vid_proj.0.bias"] = (32, dim), (32,)
     w = fill_seeded(spec, 3, 0.05)

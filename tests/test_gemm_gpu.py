@@ -74,6 +74,31 @@ def test_gemm_gelu_forward_backward():
     assert torch.allclose(dU.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("M", [100, 300, 1857 * 2])
+def test_gemm_rowdot_epilogue(M):
+    """act 4: the bf16 output is the plain product and rowdot[h, r] = sum over head h's 64 columns of bf16(out) * aux -
+    delta = rowsum(dO * O) of the attention backward from the epilogue of the dO-producing GEMM."""
+    from oa_transformer_b200 import ops
+    N, K = 768, 768
+    dY = _mk((M, K), 21)
+    W = (_mk((K, N), 22).float() * 0.05).to(torch.bfloat16)          # proj.weight [out = K, in = N]: MN-major B operand
+    O_ = _mk((M, N), 23)
+    plain = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dY, W, b_major=1, out_bf16=plain)
+    out = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ld = M + 5
+    rowdot = torch.full((N // 64, ld), -3.0, device="cuda")
+    ops.gemm(dY, W, b_major=1, act=ops.ACT_ROWDOT, aux=O_, rowdot=rowdot, out_bf16=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)                                   # the output itself is untouched by the extra work
+    ref = (out.float() * O_.float()).view(M, N // 64, 64).sum(-1).t()
+    assert torch.allclose(rowdot[:, :M], ref, rtol=1e-5, atol=1e-4), (rowdot[:, :M] - ref).abs().max().item()
+    assert bool((rowdot[:, M:] == -3.0).all())                       # nothing written past row M
+    with pytest.raises(Exception):                                   # needs 256-column granularity
+        ops.gemm(dY, W[:, :192].contiguous(), b_major=1, act=ops.ACT_ROWDOT, aux=O_[:, :192].contiguous(),
+                 rowdot=rowdot[:3], out_bf16=out[:, :192].contiguous())
+
+
 def test_gemm_wgrad_splitk_accumulate():
     from oa_transformer_b200 import ops
     T, Nout, Kin = 5000, 768, 768

@@ -242,6 +242,41 @@ def test_divided_attention_fwd_bwd(mode, B, F, n, H):
     assert rel(out[:, 0], ref.detach()[:, 0]) < 4e-3
 
 
+@pytest.mark.parametrize("mode,B,F,n,H", [("space", 2, 3, 232, 3), ("space", 4, 4, 232, 12), ("space", 1, 3, 255, 2),
+                                          ("time", 2, 8, 232, 12), ("time", 1, 6, 19, 2), ("time", 2, 1, 196, 12),
+                                          ("space", 2, 2, 16, 2)])
+def test_attention_bwd_with_delta_from_the_gemm_epilogue(mode, B, F, n, H):
+    """oat_attn_args.delta: rowsum(dO * O) per head handed in (as the dO-producing GEMM's act-4 epilogue writes it, layout
+    [H, ld >= B*T]) must give the gradients the kernels get when they compute delta from O themselves."""
+    from oa_transformer_b200 import ops
+    m = ops.MODE_SPACE if mode == "space" else ops.MODE_TIME
+    T = 1 + F * n
+    qkv = _qkv(B, T, H, 31).reshape(B * T, 3 * H * 64).cuda()
+    dout = torch.randn(B * T, H * 64, generator=gen(32)).to(BF).cuda()
+    out = torch.zeros(B * T, H * 64, device="cuda", dtype=BF)
+    lse = torch.zeros(B * H * T, device="cuda")
+    ws = torch.empty(max(1, ops.attn_fwd_workspace_floats(m, B, H, F, n)), device="cuda")
+    ops.attn_fwd(m, B, T, H, F, n, qkv, out, lse, None, cls_ws=ws)
+    g0, g1 = torch.zeros_like(qkv), torch.zeros_like(qkv)
+    acc = torch.empty(B * H * 3 * 64, device="cuda")
+    ops.attn_bwd(m, B, T, H, F, n, qkv, out, lse, dout, g0, 0.125, acc)
+    ld = B * T + 3
+    delta = torch.full((H, ld), float("nan"), device="cuda")
+    delta[:, :B * T] = (dout.float() * out.float()).view(B * T, H, 64).sum(-1).t()
+    # O poisoned: with delta given the patch rows must not depend on it any more (the CLS-row finalize still reads row 0)
+    out_p = out.clone()
+    out_p.view(B, T, H * 64)[:, 1:] = 1e4
+    ops.attn_bwd(m, B, T, H, F, n, qkv, out_p, lse, dout, g1, 0.125, acc, delta=delta)
+    torch.cuda.synchronize()
+    uses_delta = mode == "time" or n >= 128          # small space groups run the generic kernel, which ignores delta
+    if uses_delta:
+        assert rel(g1.float(), g0.float()) < 1e-3, rel(g1.float(), g0.float())
+    else:
+        ops.attn_bwd(m, B, T, H, F, n, qkv, out, lse, dout, g1, 0.125, acc, delta=delta)
+        torch.cuda.synchronize()
+        assert torch.equal(g1, g0)
+
+
 @pytest.mark.parametrize("B,F,n,H", [(2, 8, 232, 12), (1, 5, 21, 2), (2, 16, 40, 1)])
 def test_time_attention_fused_cls_matches_separate_pass(B, F, n, H):
     """The CLS query fused into the time kernel (per-warp partials + combine) vs the separate all-keys pass."""
