@@ -19,6 +19,7 @@ cpu_baseline: the CPU oracle (a port of the reference algorithm, oracle/oracle.p
          GPU box, so the pinned port is what runs - `kind: "port"`).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -348,7 +349,10 @@ def run_ours(args):
     # fresh views of the book, so p.grad ALIASES the book (no clone) and the in-place all-reduce is the all-reduce of
     # p.grad; step() waits for the handles before it returns (multi_gpu_check verifies p.grad across ranks).
     pending = []
-    layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "0") != "0"     # experiment: all-reduce block by block during backward
+    # block by block during the video backward (OAT_LAYER_REDUCE=0: one all-reduce per tower at the end). The GEMM's
+    # dynamic tile scheduler keeps the chain at full speed next to the NCCL CTAs (measured at N = 2: 59.8 vs 60.5 ms
+    # per step; with the static tile stride the same overlap cost 2 ms: 62.2)
+    layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "1") != "0"
     reduced = set()
 
     def book_range(book, prefix):
@@ -451,9 +455,11 @@ def run_ours(args):
                 yield host
 
         host_ms = {"stage_next_batch": 0.0, "enqueue_step": 0.0, "wait_for_loss": 0.0}
+        step_walls = []
+        pool = {}             # the prefetcher's two device buffer sets, kept across the warm-up and the timed loop
 
         def run_e2e(n):
-            it = iter(DevicePrefetcher(host_batches(n), device))
+            it = iter(DevicePrefetcher(host_batches(n), device, pool=pool))
             while True:
                 t0 = time.perf_counter()
                 try:
@@ -468,6 +474,7 @@ def run_ours(args):
                 host_ms["stage_next_batch"] += (t1 - t0) * 1e3
                 host_ms["enqueue_step"] += (t2 - t1) * 1e3
                 host_ms["wait_for_loss"] += (t3 - t2) * 1e3
+                step_walls.append((t3 - t0) * 1e3)
 
         run_e2e(2)
         barrier()
@@ -483,12 +490,18 @@ def run_ours(args):
         barrier()
         for k in host_ms:
             host_ms[k] = 0.0
+        del step_walls[:]
+        # every step ends with a host sync (the loss read-back), so a collector pause lands in the step time one to
+        # one: collect now and keep the cyclic GC off inside the timed loop (what timeit does)
+        gc.collect()
+        gc.disable()
         t0 = time.perf_counter()
         e0.record()
         run_e2e(K)
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) / K * 1e3
+        gc.enable()
         ems = max(e0.elapsed_time(e1) / K, wall)
         t = torch.tensor([ems], device=device, dtype=torch.float64)
         if world > 1:
@@ -496,6 +509,8 @@ def run_ours(args):
         e2e = {"value": world * B / (float(t) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 4, "ms_per_step": float(t), "bare_h2d_copy_ms": h2d_ms,
                "host_ms_per_step": {k: round(v / K, 2) for k, v in host_ms.items()},
+               "step_wall_ms_min_median_max": [round(sorted(step_walls)[0], 2), round(sorted(step_walls)[len(step_walls) // 2], 2),
+                                               round(sorted(step_walls)[-1], 2)] if step_walls else None,
                "h2d": "pinned host batch -> device on a copy stream, one step ahead (double-buffered), every step"}
 
     # ---------------- per-launch roofline numbers from one extra instrumented step (rank 0 only)

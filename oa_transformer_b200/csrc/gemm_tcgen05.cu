@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "oat_host.h"
 #include "oat_ptx.cuh"
 
@@ -60,6 +62,7 @@ struct GemmParams {
   int accumulate;
   float* rowdot;      // EPI_ROWDOT: rowdot[(col / 64) * ld_rowdot + row] = sum over the 64-column block of bf16(out) * aux
   long long ld_rowdot;
+  unsigned int* sched;  // CTA pairs: {next tile, pairs done} of this launch (dynamic tile scheduler); null = static stride
   int idle_wait;      // epilogue warps sleep between polls while the k-loop runs (experiment knob OAT_GEMM_IDLE_WAIT)
 };
 
@@ -99,7 +102,7 @@ struct GemmSmem {
   // the TMA ring takes what the epilogue boxes leave of the 227 KB
   static constexpr int kStagesFit = (232448 - 2048 - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kBarrierBytes = (2 * kStages + 4 + kEpiWarps) * 8 + 16;
+  static constexpr int kBarrierBytes = (2 * kStages + 4 + kEpiWarps + 4) * 8 + 16 + 16;   // + scheduler: 4 barriers, tile ring
   static constexpr int kTotal = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
@@ -139,7 +142,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full_bar = bars + 2 * kStages; // [2]        MMA -> epilogue
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]        epilogue -> MMA
   uint64_t* in_bar = tmem_empty_bar + 2;        // [kEpiWarps] residual / aux box landed (TMA epilogues)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + kEpiWarps);
+  uint64_t* sched_full = in_bar + kEpiWarps;    // [2] scheduler -> roles: tile index of iteration it in ring[it & 1]
+  uint64_t* sched_empty = sched_full + 2;       // [2] roles of BOTH CTAs -> scheduler (the leader's pair is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_empty + 2);
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,6 +170,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_empty_bar[i], kPair * kEpiWarps);   // pair: the epilogue warps of both CTAs release the leader
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sched_full[i], 1);                         // leader: the scheduler's arrive; peer: its producer arms 4 tx bytes
+      mbar_init(&sched_empty[i], 2 * (1 + kEpiWarps));      // MMA warp + epilogue warps (leader), producer + epilogue warps (peer)
+    }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -180,11 +190,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_tiles = tiles_mn * p.split_k;
   const int kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
 
+  // ---- tile scheduler. Static: iteration `it` of worker w is tile w + it * num_workers. Dynamic (CTA pairs, p.sched): the
+  // leader's producer thread draws tiles from an atomic counter one iteration ahead and publishes them through a two-slot
+  // ring in both CTAs (local store + arrive; st.async + complete_tx into the peer), every other role reads the slot and
+  // releases it on the leader's sched_empty barrier. Pairs that become resident late (another kernel - an NCCL reduction,
+  // a side-stream GEMM - holds their SMs when the grid launches) then find the counter exhausted and exit instead of
+  // running a full static share after everybody else has finished.
+  // The first tile of a pair stays static (tile = pair index: no counter round trip in front of the first load); a late
+  // pair then still owes exactly that one tile.
+  const bool dyn = TWO && p.sched != nullptr;
+  auto consumer_tile = [&](int it) -> int {
+    if (!dyn || it == 0) {
+      const long long t = static_cast<long long>(worker) + static_cast<long long>(it) * num_workers;
+      return t < num_tiles ? static_cast<int>(t) : -1;
+    }
+    const int j = it - 1;                      // ring use j serves iteration j + 1
+    mbar_wait(&sched_full[j & 1], (j >> 1) & 1);
+    return tile_ring[j & 1];
+  };
+  auto consumer_release = [&](int it) {       // ONE thread per role, after every thread of the role has read the slot
+    if (!dyn || it == 0) return;
+    const int j = it - 1;
+    if (cta_rank == 0) mbar_arrive(&sched_empty[j & 1]);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(&sched_empty[j & 1]), 0u));
+  };
+  auto peer_arm = [&](int it) {               // peer's producer thread: its sched_full expects the leader's 4-byte st.async
+    if (dyn && it > 0) mbar_arrive_expect_tx(&sched_full[(it - 1) & 1], 4);
+  };
+  auto draw_tile = [&]() -> int {
+    const unsigned int t = atomicAdd(p.sched, 1u) + static_cast<unsigned int>(num_workers);
+    return t < static_cast<unsigned int>(num_tiles) ? static_cast<int>(t) : -1;
+  };
+  auto publish_tile = [&](int it, int t) {     // leader's producer thread only, it >= 1
+    const int j = it - 1;
+    const int slot = j & 1;
+    mbar_wait(&sched_empty[slot], ((j >> 1) & 1) ^ 1);
+    tile_ring[slot] = t;
+    st_async_u32(mapa_u32(smem_u32(const_cast<int*>(&tile_ring[slot])), 1u), static_cast<uint32_t>(t),
+                 mapa_u32(smem_u32(&sched_full[slot]), 1u));
+    mbar_arrive(&sched_full[slot]);
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const bool fetcher = dyn && cta_rank == 0;
+      int tile = consumer_tile(0), next = -1;
+      for (int it = 0; tile >= 0; ++it) {
+        if (fetcher) next = draw_tile();        // in flight while this tile's loads are issued
         const int split = tile / tiles_mn;
         const int mn = tile - split * tiles_mn;
         const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
@@ -234,6 +288,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (fetcher) {
+          publish_tile(it + 1, next);
+          tile = next;
+        } else {
+          peer_arm(it + 1);
+          tile = consumer_tile(it + 1);
+          consumer_release(it + 1);
+        }
       }
     }
   } else if (warp == 1 && cta_rank == 0) {
@@ -244,8 +306,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 0, b_lbo = B_MN ? BLOCK_K * 128 : 0;
     constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2, b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
     uint32_t stage = 0, phase = 0;
-    int local_iter = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
+    for (int local_iter = 0;; ++local_iter) {
+      const int tile = consumer_tile(local_iter);
+      __syncwarp();
+      if (lane == 0) consumer_release(local_iter);
+      if (tile < 0) break;
       const int split = tile / tiles_mn;
       const int kb0 = split * kb_per_split;
       const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
@@ -310,8 +375,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t my_x = smem_u32(box_x) + lane * 128;
     uint64_t* my_in_bar = &in_bar[warp - 2];
     uint32_t in_count = 0;                  // input boxes consumed so far (mbarrier parity)
-    int local_iter = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
+    for (int local_iter = 0;; ++local_iter) {
+      const int tile = consumer_tile(local_iter);
+      __syncwarp();
+      if (lane == 0) consumer_release(local_iter);
+      if (tile < 0) break;
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
@@ -475,8 +543,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int cc = (lane >> 3) * 4;         // 4-column group within the 16-column chunk
     constexpr int kChunks = BLOCK_N / kChunk;
     constexpr bool kGeneric = EPI == EPI_GENERIC;
-    int local_iter = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_iter) {
+    for (int local_iter = 0;; ++local_iter) {
+      const int tile = consumer_tile(local_iter);
+      if (tile < 0) break;
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks, n_blk = mn - m_blk * p.num_n_blocks;
@@ -582,9 +651,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if constexpr (TWO) tmem_dealloc_pair<kTmemCols>(tmem_base);
     else tmem_dealloc<kTmemCols>(tmem_base);
   }
+  if constexpr (TWO) {
+    // the last pair out re-arms the counter pair for a later launch (no memset between launches)
+    if (dyn && cta_rank == 0 && threadIdx.x == 0) {
+      if (atomicAdd(p.sched + 1, 1u) == static_cast<unsigned int>(num_workers) - 1u) {
+        atomicExch(p.sched, 0u);
+        atomicExch(p.sched + 1, 0u);
+      }
+    }
+  }
 }
 
+// Counter pairs {next tile, pairs done} of the dynamic tile scheduler: every CTA-pair launch takes the next pair of the pool
+// (launches in flight on different streams never share one) and its last pair out re-arms it, so no memset is needed.
+constexpr int kGemmSchedSlots = 256;
+__device__ unsigned int g_gemm_sched[kGemmSchedSlots][2];
+
 // ---------------------------------------------------------------------------------------------- host side
+static unsigned int* next_gemm_sched_slot() {
+  static const bool on = [] { const char* e = getenv("OAT_GEMM_DYNAMIC"); return e == nullptr || atoi(e) != 0; }();
+  if (!on) return nullptr;
+  static unsigned int* base = [] {
+    void* ptr = nullptr;
+    return cudaGetSymbolAddress(&ptr, g_gemm_sched) == cudaSuccess ? static_cast<unsigned int*>(ptr) : nullptr;
+  }();
+  static std::atomic<unsigned int> seq{0};
+  return base == nullptr ? nullptr : base + 2 * (seq.fetch_add(1) % kGemmSchedSlots);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -717,6 +811,7 @@ static int launch_gemm(const oat_gemm_args* a, cudaStream_t stream) {
   p.act = a->act; p.scale_cols = a->scale_cols; p.scale = a->scale; p.alpha = a->alpha;
   p.accumulate = a->accumulate;
   p.rowdot = a->rowdot; p.ld_rowdot = a->ld_rowdot;
+  p.sched = TWO ? next_gemm_sched_slot() : nullptr;
   {
     const char* e = getenv("OAT_GEMM_IDLE_WAIT");
     p.idle_wait = (e != nullptr && atoi(e) != 0) ? 1 : 0;

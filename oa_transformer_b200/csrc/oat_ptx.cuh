@@ -256,6 +256,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
+// 4-byte store into a peer CTA's shared memory that completes 4 tx bytes on that CTA's mbarrier (both shared::cluster
+// addresses of the SAME peer): data and signal travel together, a waiter on the barrier sees the value.
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t value, uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];\n" ::"r"(cluster_addr), "r"(value),
+               "r"(mbar_cluster_addr)
+               : "memory");
+}
 // TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the mbarrier at
 // `mbar_cluster_addr` (the leader CTA's barrier, a shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint32_t mbar_cluster_addr, int32_t c0,

@@ -66,9 +66,12 @@ class DevicePrefetcher:
         for data in pf: ...            # data tensors live on `device`; valid until the next-but-one batch is requested
     """
 
-    def __init__(self, batches, device):
+    def __init__(self, batches, device, pool=None):
+        """pool: optional dict kept by the caller; the two device buffer sets live in it, so prefetchers created one
+        after the other (one per epoch) re-use the same device memory instead of allocating 2 x batch bytes again."""
         self.it = iter(batches)
         self.device = device
+        self.pool = pool
         self.copy_stream = torch.cuda.Stream(device=device)
         self.slots = [None, None]          # device buffer sets
         self.ready = [None, None]          # copy-finished events
@@ -93,6 +96,8 @@ class DevicePrefetcher:
         if self.free[slot] is not None:
             self.copy_stream.wait_event(self.free[slot])
         prev = self.slots[slot]["dev"] if isinstance(self.slots[slot], dict) and "dev" in self.slots[slot] else {}
+        if not prev and self.pool is not None:
+            prev = self.pool.get(slot, {})
         dev = {}
         with torch.cuda.stream(self.copy_stream):
             for path, t in self._tensors(host):
@@ -105,6 +110,8 @@ class DevicePrefetcher:
         ev.record(self.copy_stream)
         self.ready[slot] = ev
         self.slots[slot] = {"host": host, "dev": dev}
+        if self.pool is not None:
+            self.pool[slot] = dev
 
     def __iter__(self):
         return self

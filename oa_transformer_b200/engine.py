@@ -580,9 +580,17 @@ class VideoEngine:
                 side_done[i] = ev
             hook = getattr(self, "layer_grad_hook", None)
             if hook is not None:        # every gradient of block i has been enqueued (fc2.bias came from block i+1's LN3)
-                if use_side:            # ... the weight gradients on the side stream: order the hook's work after them
-                    main.wait_event(side_done[i])
-                hook(grads, "%sblocks.%d." % (prefix, i))
+                if use_side:
+                    # ... the weight gradients on the side stream, the LayerNorm / bias gradients on the chain: the hook
+                    # runs on the side stream once it has also seen the chain up to here, so whatever it launches (a
+                    # gradient all-reduce) is ordered after both and the chain itself never waits
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        hook(grads, "%sblocks.%d." % (prefix, i))
+                else:
+                    hook(grads, "%sblocks.%d." % (prefix, i))
             dy, dyb = dyb, dy
             dy16 = dy16b
 
