@@ -349,10 +349,12 @@ def run_ours(args):
     # fresh views of the book, so p.grad ALIASES the book (no clone) and the in-place all-reduce is the all-reduce of
     # p.grad; step() waits for the handles before it returns (multi_gpu_check verifies p.grad across ranks).
     pending = []
-    # block by block during the video backward (OAT_LAYER_REDUCE=0: one all-reduce per tower at the end). The GEMM's
-    # dynamic tile scheduler keeps the chain at full speed next to the NCCL CTAs (measured at N = 2: 59.8 vs 60.5 ms
-    # per step; with the static tile stride the same overlap cost 2 ms: 62.2)
-    layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "1") != "0"
+    # OAT_LAYER_REDUCE=1: all-reduce block by block during the video backward (launched from the side stream) instead of
+    # one all-reduce per tower. With the GEMM's dynamic tile scheduler the chain keeps its speed next to the NCCL CTAs
+    # (the static tile stride lost 2 ms: 62.2 vs 59.8-60.5 ms at N = 2), but there is little left to hide: measured
+    # 58.5-58.8 vs 58.8 ms (N = 2) and 60.9 vs 60.7 ms (N = 4) against 58.0 ms without any all-reduce - within the
+    # box-to-box noise, so the simpler per-tower reduce stays the default.
+    layer_reduce = os.environ.get("OAT_LAYER_REDUCE", "0") != "0"
     reduced = set()
 
     def book_range(book, prefix):
