@@ -66,7 +66,7 @@ def load_gemm_traffic():
 
 def traffic_table_path():
     """Newest committed ncu traffic table (scripts/ncu_traffic_table.py output)."""
-    for name in ("r2c_kernel_traffic.json", "r2_kernel_traffic.json", "r1_kernel_traffic.json"):
+    for name in ("r2d_kernel_traffic.json", "r2c_kernel_traffic.json", "r2_kernel_traffic.json", "r1_kernel_traffic.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             return path
@@ -558,21 +558,23 @@ def run_ours(args):
             with open(tpath) as f:
                 ktraffic = json.load(f)
         roofline_attn = {}
-        for key, label, mult, tkey in (("attn_fwd_0", "space_fwd (tcgen05, CLS fused)", 1.0, "attn_space_fwd"),
-                                       ("attn_bwd_0", "space_bwd (tcgen05)", 2.0, "attn_space_bwd"),
-                                       ("attn_fwd_1", "time_fwd (mma.sync, CLS fused)", 1.0, "attn_time_fwd"),
-                                       ("attn_bwd_1", "time_bwd (mma.sync)", 2.0, "attn_time_bwd")):
+        # (the profiler records the backward's own algorithmic bytes: without the O rows when delta comes from the GEMM)
+        ext = "_delta" if (ktraffic and "attn_space_bwd_delta" in ktraffic and _engine.DELTA_EPI) else ""
+        for key, label, fmult, tkey in (("attn_fwd_0", "space_fwd (tcgen05, CLS fused)", 1.0, "attn_space_fwd"),
+                                        ("attn_bwd_0", "space_bwd (tcgen05)", 2.5, "attn_space_bwd" + ext),
+                                        ("attn_fwd_1", "time_fwd (mma.sync, CLS fused)", 1.0, "attn_time_fwd"),
+                                        ("attn_bwd_1", "time_bwd (mma.sync)", 2.5, "attn_time_bwd" + ext)):
             sp = agg.get(key)
             if not sp or sp["ms"] <= 0:
                 continue
-            gbs = mult * sp["bytes"] / (sp["ms"] / 1e3) / 1e9
+            gbs = sp["bytes"] / (sp["ms"] / 1e3) / 1e9
             tr = None
             if ktraffic and tkey in ktraffic:
                 tr = ktraffic[tkey]["dram_read_bytes"] + ktraffic[tkey]["dram_write_bytes"]
             roofline_attn[label] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                    "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": mult * sp["bytes"] / sp["n"],
+                                    "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": sp["bytes"] / sp["n"],
                                     "traffic": tr, "launches": sp["n"], "ms_in_step": sp["ms"],
-                                    "tflops": (1.0 if mult == 1.0 else 2.5) * sp["flops"] / (sp["ms"] / 1e3) / 1e12}
+                                    "tflops": fmult * sp["flops"] / (sp["ms"] / 1e3) / 1e12}
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"]} for k, v in agg.items()}
 
     # ---------------- CPU baseline (rank 0, N = 1 only)

@@ -188,6 +188,22 @@ def attn_core_work(mode, B, T, H, F, n):
     return (groups * 128.0 * (2 * nq + 2 * nk), groups * 4.0 * nq * nk * 64)
 
 
+def attn_bwd_core_work(mode, B, T, H, F, n, ext_delta=False):
+    """(algorithmic bytes, forward FLOPs) of one attention backward: q, dO, O, dQ rows + k, v, dK, dV rows = twice the
+    forward's bytes; with delta handed in (oat_attn_args.delta) the O rows are not read - 4 B of delta per query row are."""
+    by, fl = attn_core_work(mode, B, T, H, F, n)
+    if mode == MODE_SPACE:
+        groups, nq = B * H * F, n
+    elif mode == MODE_TIME:
+        groups, nq = B * H * n, F
+    else:
+        groups, nq = B * H, T
+    by = 2.0 * by
+    if ext_delta:
+        by += groups * nq * (4.0 - 128.0)
+    return (by, fl)
+
+
 def attn_fwd_workspace_floats(mode, B, H, F, n=1):
     """fp32 words of workspace the space / time forward needs for the partials of the fused CLS query."""
     f = lib().oat_attn_fwd_workspace_floats
@@ -228,7 +244,7 @@ def attn_bwd(mode, B, T, H, F, n, qkv, out, lse, dout, dqkv, scale, cls_acc=None
     a.scale = scale
     a.cls_acc = ptr(cls_acc)
     _count(1 if mode == MODE_PLAIN else 2)
-    with _Prof("attn_bwd_%d" % mode, attn_core_work(mode, B, T, H, F, n)):
+    with _Prof("attn_bwd_%d" % mode, attn_bwd_core_work(mode, B, T, H, F, n, delta is not None)):
         check(lib().oat_attn_bwd(ctypes.byref(a), stream_ptr()), "oat_attn_bwd")
 
 

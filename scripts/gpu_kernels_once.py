@@ -57,6 +57,8 @@ dbet = torch.zeros(D, device=dev)
 dxs = torch.zeros(D, device=dev)
 dx32 = torch.empty(M, D, device=dev)
 colacc = torch.zeros(3 * D, device=dev)
+o16_1b = (torch.randn(M, D, device=dev) * 0.5).to(BF)
+delta = torch.zeros(H, M, device=dev)
 
 cases = [
     ("gemm_fwd_qkv", lambda: ops.gemm(x, wqkv, bias=b3, scale_cols=D, scale=0.125, out_bf16=o16_3)),
@@ -79,6 +81,10 @@ cases = [
     ("layernorm_bwd", lambda: ops.layernorm_bwd(res, mean, rstd, gamma, dy_bf16=x, add1=o32, dx=dx32, dx_bf16=o16_1,
                                                 dgamma=dgam, dbeta=dbet, dxsum=dxs)),
     ("colsum", lambda: ops.colsum_bf16(x3, colacc)),
+    # delta = rowsum(dO * O) from the projection dgrad's epilogue, and the attention backward kernels fed with it
+    ("gemm_dgrad_proj_rowdot", lambda: ops.gemm(x, wproj, b_major=1, act=ops.ACT_ROWDOT, aux=o16_1b, rowdot=delta, out_bf16=o16_1)),
+    ("attn_space_bwd_delta", lambda: ops.attn_bwd(ops.MODE_SPACE, B, T, H, F, n, x3, o16_1b, lse, x, o16_3, 0.125, acc, delta=delta)),
+    ("attn_time_bwd_delta", lambda: ops.attn_bwd(ops.MODE_TIME, B, T, H, F, n, x3, o16_1b, lse, x, o16_3, 0.125, acc, delta=delta)),
 ]
 torch.cuda.synchronize()
 for name, fn in cases:

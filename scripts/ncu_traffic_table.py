@@ -3,7 +3,8 @@ The cases are matched to the captured launches in order (helper kernels - combin
 import csv, json, re, sys
 CASES = ["gemm_fwd_qkv", "gemm_fwd_proj", "gemm_fwd_fc1", "gemm_fwd_fc2", "gemm_dgrad_fc2", "gemm_dgrad_fc1",
          "gemm_dgrad_qkv", "gemm_dgrad_proj", "gemm_wgrad_proj", "gemm_wgrad_qkv", "gemm_wgrad_fc1", "gemm_wgrad_fc2",
-         "attn_space_fwd", "attn_space_bwd", "attn_time_fwd", "attn_time_bwd", "layernorm_fwd", "layernorm_bwd", "colsum"]
+         "attn_space_fwd", "attn_space_bwd", "attn_time_fwd", "attn_time_bwd", "layernorm_fwd", "layernorm_bwd", "colsum",
+         "gemm_dgrad_proj_rowdot", "attn_space_bwd_delta", "attn_time_bwd_delta"]
 HELPERS = ("combine", "finalize")
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
