@@ -173,6 +173,11 @@ int oat_assemble_tokens_bwd(const float* dx, void* dpatch_bf16, void* dobject_bf
                             float* dtemporal, float* dtype_embed, int32_t B, int32_t F, int32_t N, int32_t O,
                             int32_t D, oat_stream_t stream);
 int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int32_t cols, float* out, oat_stream_t stream);
+/* out[c] += sum_k v[k] * W[k*ldw + c] (fp32 row vector times matrix). The qkv bias gradient of VarAttention
+ * (video_transformer.py:102) needs a column sum over all token rows of dq only: softmax makes the rows of dS sum to
+ * zero, so sum_j dK_j = sum_i q_i (sum_j dS_ij) = 0, and its rows of P sum to one, so sum_j dV_j = sum_i dO_i = db_proj . W_proj
+ * (dO = dY_proj . W_proj, video_transformer.py:133) - this call, on the proj bias gradient and the fp32 proj weight. */
+int oat_vecmat_f32(const float* v, const float* W, int64_t ldw, int32_t K, int32_t N, float* out, oat_stream_t stream);
 /* Bias gradient for free: a weight-gradient GEMM dY^T . [X | 1 0 .. 0] (activation rows extended by a ones column, pitch
  * cols + 16) leaves dW in columns [0, cols) and the column sums of dY - the bias gradient - in column `cols` of its fp32
  * scratch output [rows, ld]; oat_gemm_bf16 multiplies that last, 16-wide column block with an N = 16 instruction. This

@@ -394,6 +394,19 @@ __global__ void __launch_bounds__(512) colsum_bf16_kernel(const __nv_bfloat16* _
   for (int k = 0; k < 8; ++k) atomicAdd(out + c + k, acc[k]);
 }
 
+// out[c] += sum_k v[k] * W[k][c] (fp32): a [1, K] x [K, N] product, one CTA per (128 columns, 32 k rows), partial sums by
+// atomics. Used for the v part of the qkv bias gradient, db_v = db_proj . W_proj (see oat.h).
+__global__ void __launch_bounds__(128) vecmat_f32_kernel(const float* __restrict__ v, const float* __restrict__ W, long long ldw,
+                                                         int K, int N, float* __restrict__ out) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * 32;
+  if (c >= N) return;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k = k0; k < min(K, k0 + 32); ++k) acc = fmaf(__ldg(v + k), __ldg(W + static_cast<long long>(k) * ldw + c), acc);
+  atomicAdd(out + c, acc);
+}
+
 // ------------------------------------------------------------------------------------------------ text embeddings
 // out[b*L + l] = word_emb[ids[b*L+l]] + pos_emb[l]   (fp32; the LayerNorm kernel follows)
 __global__ void text_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
@@ -578,6 +591,14 @@ extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int
                  reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, out, static_cast<int>(rows_per)) != cudaSuccess)
     return check_launch("colsum_bf16_kernel");
   return check_launch("colsum_bf16_kernel");
+}
+
+extern "C" int oat_vecmat_f32(const float* v, const float* W, int64_t ldw, int32_t K, int32_t N, float* out,
+                              oat_stream_t stream) {
+  OAT_REQUIRE(v != nullptr && W != nullptr && out != nullptr && ldw >= N, "oat_vecmat_f32: bad arguments");
+  if (K <= 0 || N <= 0) return OAT_OK;
+  vecmat_f32_kernel<<<dim3((N + 127) / 128, (K + 31) / 32), 128, 0, as_stream(stream)>>>(v, W, ldw, K, N, out);
+  return check_launch("vecmat_f32_kernel");
 }
 
 extern "C" int oat_text_embed(const int64_t* ids, const float* word_emb, const float* pos_emb, float* out,

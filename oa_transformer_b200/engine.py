@@ -45,6 +45,10 @@ GRAPH = os.environ.get("OAT_GRAPH", "0") != "0"
 # delta = rowsum(dO * O) of the attention backward from the epilogue of the dO-producing GEMM (oat_gemm_bf16 act 4) instead
 # of re-reading O inside the attention kernels. OAT_DELTA_EPI=0: the attention kernels compute it themselves.
 DELTA_EPI = os.environ.get("OAT_DELTA_EPI", "1") != "0"
+# qkv bias gradient of the video tower's attentions from a column sum over the dq columns only: the dk columns sum to zero
+# (rows of dS sum to zero) and the dv columns sum to sum_i dO_i = db_proj . W_proj (rows of P sum to one) - a third of the
+# column-sum traffic (see oat_vecmat_f32 in include/oat.h). OAT_QKV_BIAS_IDENTITY=0: column sums over all of dqkv.
+QKV_BIAS_IDENTITY = os.environ.get("OAT_QKV_BIAS_IDENTITY", "1") != "0"
 MAX_GRAPHS = 8
 
 
@@ -457,7 +461,7 @@ class VideoEngine:
             side.wait_stream(main)              # gradient book zeroed, forward finished
         side_done = {}
 
-        def wgrad(dy16, act16, name, bias=True, ext=None):
+        def wgrad(dy16, act16, name, bias=True, ext=None, proj=None):
             # bias=False: the bias gradient was already reduced (fp32) by the LayerNorm-backward kernel that produced dy.
             # ext: the activation rows extended by a ones column ([x | 1 0 .. 0]); dY^T . ext then carries the bias
             # gradient in its last column block (an N = 16 MMA) instead of a second pass over dY (oat_unpack_wgrad).
@@ -471,7 +475,13 @@ class VideoEngine:
                     return
                 ops.gemm(dy16, act16, a_major=1, b_major=1, out_f32=grads[name + ".weight"].view(dy16.shape[1], -1),
                          accumulate=True)
-                if bias:
+                if bias and proj is not None and QKV_BIAS_IDENTITY:
+                    # proj: name of the output projection behind this attention; its bias gradient (sum of dY_proj over the
+                    # token rows, from the LayerNorm backward's dxsum) is complete before the attention backward runs
+                    db = grads[name + ".bias"]
+                    ops.colsum_bf16(dy16[:, :D], db[:D])                                 # q: a real column sum
+                    ops.vecmat_f32(grads[proj + ".bias"], p[proj + ".weight"], db[2 * D:])   # v; k stays exactly zero
+                elif bias:
                     ops.colsum_bf16(dy16, grads[name + ".bias"])
             if not use_side:
                 return run()
@@ -555,7 +565,7 @@ class VideoEngine:
             ops.attn_bwd(ops.MODE_SPACE, B, T, H, Fr, n, L["qkv_s"], L["a_s"], L["lse_s"], da, dqkv_s[k], Q_SCALE, acc,
                          delta=delta)
             ops.gemm(dqkv_s[k], L["wqkv_s"], b_major=1, out_bf16=dh)
-            wgrad(dqkv_s[k], L["h1"], b + "attn.qkv", ext=L["h1x"])
+            wgrad(dqkv_s[k], L["h1"], b + "attn.qkv", ext=L["h1x"], proj=b + "attn.proj")
             ops.layernorm_bwd(L["tr"], L["m1"], L["r1"], p[b + "norm1.weight"], dy_bf16=dh, dx=dtr, dx_bf16=dtr16[k],
                               dgamma=grads[b + "norm1.weight"], dbeta=grads[b + "norm1.bias"],
                               dxsum=grads[b + "timeattn.proj.bias"])
@@ -565,7 +575,7 @@ class VideoEngine:
             ops.attn_bwd(ops.MODE_TIME, B, T, H, Fr, n, L["qkv_t"], L["a_t"], L["lse_t"], da, dqkv_t[k], Q_SCALE, acc,
                          delta=delta)
             ops.gemm(dqkv_t[k], L["wqkv_t"], b_major=1, out_bf16=dh)
-            wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv", ext=L["h3x"])
+            wgrad(dqkv_t[k], L["h3"], b + "timeattn.qkv", ext=L["h3x"], proj=b + "timeattn.proj")
             if i == region_at:      # x_i also fed region_norm: dsr += region_norm'(dtokens), in place, before the sum below
                 wn = prefix + "region_norm"
                 ops.layernorm_bwd(xs[i], S["tmean"], S["trstd"], p[wn + ".weight"], dy_f32=dtokens, add1=dsr, dx=dsr,

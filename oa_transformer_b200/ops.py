@@ -385,6 +385,15 @@ def colsum_bf16(x, out):
                                 stream_ptr()), "oat_colsum_bf16")
 
 
+def vecmat_f32(v, W, out):
+    """out[c] += sum_k v[k] * W[k, c] (fp32; W 2-D with unit inner stride)."""
+    assert v.dtype == torch.float32 and W.dtype == torch.float32 and out.dtype == torch.float32
+    K, N = W.shape
+    assert v.numel() == K and out.numel() == N and W.stride(1) == 1 and v.is_contiguous() and out.is_contiguous()
+    _count(1)
+    check(lib().oat_vecmat_f32(ptr(v), ptr(W), _i64(W.stride(0)), _i32(K), _i32(N), ptr(out), stream_ptr()), "oat_vecmat_f32")
+
+
 def unpack_wgrad(scratch, cols, dw, db):
     """dw (+)= scratch[:, :cols]; db (+)= scratch[:, cols]; scratch <- 0 (see oat_unpack_wgrad)."""
     rows = scratch.shape[0]

@@ -305,6 +305,11 @@ def colsum_bf16(x, out):
     _count(1)
 
 
+def vecmat_f32(v, W, out):
+    out += v.detach() @ W.detach()
+    _count(1)
+
+
 def unpack_wgrad(scratch, cols, dw, db):
     dw += scratch[:, :cols]
     db += scratch[:, cols]

@@ -481,6 +481,23 @@ def test_patch_embed_and_token_assembly_with_objects():
     assert rel(dtem.cpu().view(4, D), ref_tem) < 1e-5
 
 
+def test_vecmat_and_strided_colsum_for_the_qkv_bias_identity():
+    """oat_vecmat_f32 (db_v = db_proj . W_proj) and a column sum over the q slice of a [M, 3D] buffer (row pitch 3D)."""
+    from oa_transformer_b200 import ops
+    D, M = 768, 5000
+    g = gen(41)
+    v = torch.randn(D, generator=g).cuda()
+    W = torch.randn(D, D, generator=g).cuda()
+    out = torch.full((3 * D,), 2.0, device="cuda")
+    ops.vecmat_f32(v, W, out[2 * D:])
+    dqkv = torch.randn(M, 3 * D, generator=g).to(BF).cuda()
+    ops.colsum_bf16(dqkv[:, :D], out[:D])
+    torch.cuda.synchronize()
+    assert rel(out[2 * D:] - 2.0, v.double() @ W.double()) < 1e-5
+    assert rel(out[:D] - 2.0, dqkv[:, :D].double().sum(0)) < 1e-5
+    assert bool((out[D:2 * D] == 2.0).all())
+
+
 def test_colsum_and_text_embed():
     from oa_transformer_b200 import ops
     g = gen(9)
