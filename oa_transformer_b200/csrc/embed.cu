@@ -353,43 +353,69 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, __nv_bf
 // The loads go through cp.async into a per-thread ring in shared memory (8 rows deep): ptxas otherwise keeps only ~3
 // register loads in flight per thread (it schedules for 32 registers), which held the kernel at 60 % of the HBM roofline.
 // A thread only ever reads the 16 bytes it copied itself, so no block-level synchronisation is needed.
+// Narrow inputs (the dq slice of a dqkv buffer: 768 columns = 96 threads per row) would leave an SM with ~6 warps: the
+// CTA then runs several row lanes (lane y takes rows y, y + lanes, ...; 4 x 96 threads), reduced through shared memory
+// at the end, so the number of atomics per column stays what it was.
 constexpr int kColsumRing = 8;
 __global__ void __launch_bounds__(512) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                           long long rows, int cols, float* __restrict__ out,
-                                                          int rows_per_cta) {
+                                                          int rows_per_cta, int tpr) {
   extern __shared__ __align__(16) uint8_t colsum_ring[];          // [kColsumRing][blockDim.x] x 16 B
   pdl_launch_dependents();
   pdl_wait();
-  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-  if (c >= cols) return;
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
-  const long long r1 = min(rows, r0 + rows_per_cta);
+  const int lanes = blockDim.x / tpr;                             // row lanes of this CTA
+  const int tx = threadIdx.x % tpr, ly = threadIdx.x / tpr;
+  const int c = (blockIdx.y * tpr + tx) * 8;
+  const bool active = c < cols;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta + ly;
+  const long long r1 = min(rows, static_cast<long long>(blockIdx.x + 1) * rows_per_cta);
   const uint32_t slot0 = static_cast<uint32_t>(__cvta_generic_to_shared(colsum_ring)) + threadIdx.x * 16;
   const uint32_t slot_stride = blockDim.x * 16;
+  const long long step = static_cast<long long>(lanes) * ld;
   const __nv_bfloat16* src = x + r0 * ld + c;
-#pragma unroll
-  for (int u = 0; u < kColsumRing; ++u) {
-    if (r0 + u < r1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(slot0 + u * slot_stride), "l"(src + u * ld) : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  }
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  int slot = 0;
-  for (long long r = r0; r < r1; ++r) {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(kColsumRing - 1) : "memory");
-    const uint4 v = *reinterpret_cast<const uint4*>(colsum_ring + (slot * blockDim.x + threadIdx.x) * 16);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  if (active) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16x2(w[k]);
-      acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+    for (int u = 0; u < kColsumRing; ++u) {
+      if (r0 + static_cast<long long>(u) * lanes < r1)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(slot0 + u * slot_stride), "l"(src + u * step) : "memory");
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    if (r + kColsumRing < r1)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(slot0 + slot * slot_stride), "l"(src + (r - r0 + kColsumRing) * ld) : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    slot = slot + 1 == kColsumRing ? 0 : slot + 1;
+    int slot = 0;
+    long long i = 0;
+    for (long long r = r0; r < r1; r += lanes, ++i) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kColsumRing - 1) : "memory");
+      const uint4 v = *reinterpret_cast<const uint4*>(colsum_ring + (slot * blockDim.x + threadIdx.x) * 16);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+      }
+      if (r + static_cast<long long>(kColsumRing) * lanes < r1)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(slot0 + slot * slot_stride), "l"(src + (i + kColsumRing) * step) : "memory");
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      slot = slot + 1 == kColsumRing ? 0 : slot + 1;
+    }
   }
+  if (lanes > 1) {                                                // CTA-uniform
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();                                              // every ring slot is dead: the ring becomes [lanes][tpr][8] floats
+    float* red = reinterpret_cast<float*>(colsum_ring);
+    if (ly > 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[(ly * tpr + tx) * 8 + k] = acc[k];
+    }
+    __syncthreads();
+    if (ly > 0) return;
+    for (int l = 1; l < lanes; ++l) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += red[(l * tpr + tx) * 8 + k];
+    }
+  }
+  if (!active) return;
 #pragma unroll
   for (int k = 0; k < 8; ++k) atomicAdd(out + c + k, acc[k]);
 }
@@ -579,16 +605,20 @@ extern "C" int oat_colsum_bf16(const void* x_bf16, int64_t ld, int64_t rows, int
   if (rows <= 0) return OAT_OK;
   // one block spans all columns when it can (2304 -> 288 threads, 3072 -> 384): no nearly-empty second column block
   const int want = ((cols / 8 + 31) / 32) * 32;
-  const int threads = want <= 384 ? want : 256;      // ring: 8 x threads x 16 B <= 48 KB
+  const int tpr = want <= 384 ? want : 256;          // threads per row; ring: 8 x threads x 16 B <= 48 KB
+  int lanes = 384 / tpr;                             // row lanes: fill the CTA up to 384 threads
+  if (lanes < 1) lanes = 1;
+  if (lanes > 4) lanes = 4;
+  const int threads = tpr * lanes;
   // slabs: a multiple of the SM count, about 200-256 rows each
   const long long sms = num_sms();
   long long k = (rows + 256 * sms - 1) / (256 * sms);
   if (k < 1) k = 1;
   long long rows_per = (rows + k * sms - 1) / (k * sms);
   if (rows_per < 16) rows_per = 16;
-  dim3 grid(static_cast<unsigned>((rows + rows_per - 1) / rows_per), static_cast<unsigned>((cols / 8 + threads - 1) / threads));
+  dim3 grid(static_cast<unsigned>((rows + rows_per - 1) / rows_per), static_cast<unsigned>((cols / 8 + tpr - 1) / tpr));
   if (launch_pdl(colsum_bf16_kernel, grid, dim3(threads), static_cast<size_t>(kColsumRing) * threads * 16, as_stream(stream),
-                 reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, out, static_cast<int>(rows_per)) != cudaSuccess)
+                 reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, out, static_cast<int>(rows_per), tpr) != cudaSuccess)
     return check_launch("colsum_bf16_kernel");
   return check_launch("colsum_bf16_kernel");
 }

@@ -4,6 +4,6 @@ one() { (cd $1 && python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e
 import json,sys
 d=json.loads(sys.stdin.read())
 kb=d['kernel_ms_breakdown']
-print('$2', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'], {k: kb[k]['ms'] for k in ('gemm','attn_bwd_0','attn_bwd_1','attn_fwd_1')})
+print('$2', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'], {k: kb[k]['ms'] for k in ('gemm','gemm_skinny','colsum','attn_bwd_0','attn_bwd_1','attn_fwd_1')})
 "; }
 one . new; one _ab_old old; one . new; one _ab_old old
