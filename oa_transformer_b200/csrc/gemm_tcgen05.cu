@@ -17,6 +17,12 @@
 // transposed weight copy).  The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  Split-K (for the weight gradients, whose output has < 148 tiles)
 // reduces with fp32 atomics straight into the gradient buffer.
+// CTA pairs (cluster of 2, cta_group::2) take their tiles from a per-launch atomic counter (dynamic tile scheduler, see
+// the kernel body): a pair that becomes resident late - an NCCL reduction or a side-stream kernel held its SMs when the
+// grid launched - owes one tile, not a whole static share.
+// Epilogue EPI_ROWDOT (act 4): besides the bf16 output, the dot of every stored output row with an aux row per
+// 64-column block - delta = rowsum(dO * O) per head for the attention backward, out of the accumulator row the epilogue
+// thread already holds.
 //
 // This one kernel carries every dense contraction of the hot path (reference call sites:
 // OATrans/model/video_transformer.py:102,133 (qkv/proj), :46-49 (Mlp), :69 (patch conv as GEMM),
