@@ -59,6 +59,42 @@ def test_video_engine_schedule_matches_oracle(engine_on_fake_ops, frames, object
         assert rel(book[name], ref_p.grad) < 3e-2, (name, rel(book[name], ref_p.grad))
 
 
+def test_qkv_bias_gradient_from_softmax_identities(engine_on_fake_ops, monkeypatch):
+    """engine.QKV_BIAS_IDENTITY: the qkv bias gradient of the divided attentions (video_transformer.py:102) from a column sum
+    over dq only - the dk columns sum to zero (rows of dS sum to zero), the dv columns to db_proj . W_proj (rows of P sum to
+    one, dO = dY_proj . W_proj). Against the fp32 oracle it must be at least as close as the column sum over all of dqkv,
+    and its k part exactly zero (the full column sum leaves bf16 rounding noise there; the true value is ~1e-7)."""
+    engine = engine_on_fake_ops
+    dim, heads, depth, B, frames, objects = 256, 4, 2, 2, 2, 2
+    spec = video_tower_spec(depth=depth, dim=dim, frames=frames, grid=2, patch=16, objects=True)
+    spec["vid_proj.0.weight"], spec["vid_proj.0.bias"] = (32, dim), (32,)
+    w = fill_seeded(spec, 3, 0.05)
+    g = torch.Generator().manual_seed(4)
+    video = torch.randn(B, frames, 3, 32, 32, generator=g)
+    objs = O.synth_objects(B, frames, objects, g)
+    coef = torch.randn(B, 32, generator=g)
+    p = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    (O.compute_video(video, p, O.OracleCfg(heads=heads, bf16=False), objs) * coef).sum().backward()
+    err = {}
+    for ident in (True, False):
+        monkeypatch.setattr(engine, "QKV_BIAS_IDENTITY", ident)
+        eng = engine.VideoEngine(torch.device("cpu"), heads=heads)
+        params = {k: v.clone() for k, v in w.items()}
+        eng.forward(params, video, objs)
+        book = engine.GradBook([(k, torch.nn.Parameter(v)) for k, v in params.items()], torch.device("cpu"))
+        eng.backward(params, book, coef.clone())
+        for name in w:
+            if name.endswith("qkv.bias"):
+                err[(ident, name)] = rel(book[name], p[name].grad)
+                if ident:
+                    assert float(book[name][dim:2 * dim].abs().max()) == 0.0, name
+                    assert rel(book[name][2 * dim:], p[name].grad[2 * dim:]) < 2e-2, name
+    names = sorted(n for (i, n) in err if i)
+    assert len(names) == 2 * depth
+    for n in names:
+        assert err[(True, n)] <= err[(False, n)] * 1.05 + 1e-4, (n, err[(True, n)], err[(False, n)])
+
+
 @pytest.mark.parametrize("tokens,region_layer,depth", [("final", None, 2), ("region", 1, 2), ("region", 2, 2), ("region", 2, 3)])
 def test_video_engine_token_features_schedule(engine_on_fake_ops, tokens, region_layer, depth):
     """forward_features' second result (video_transformer.py:351: x[:, 1:] after the final norm) and the region variant's
