@@ -497,13 +497,15 @@ def run_ours(args):
         # one: collect now and keep the cyclic GC off inside the timed loop (what timeit does)
         gc.collect()
         gc.disable()
-        t0 = time.perf_counter()
-        e0.record()
-        run_e2e(K)
-        e1.record()
-        barrier()
-        wall = (time.perf_counter() - t0) / K * 1e3
-        gc.enable()
+        try:
+            t0 = time.perf_counter()
+            e0.record()
+            run_e2e(K)
+            e1.record()
+            barrier()
+            wall = (time.perf_counter() - t0) / K * 1e3
+        finally:
+            gc.enable()
         ems = max(e0.elapsed_time(e1) / K, wall)
         t = torch.tensor([ems], device=device, dtype=torch.float64)
         if world > 1:
