@@ -33,6 +33,29 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, n), "include/oat.h declares %s but liboat.so does not export it" % n
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """oat_gemm_args / oat_attn_args as gcc lays them out from include/oat.h vs the ctypes mirrors in _lib.py / ops.py:
+    same size and the same offset for every field (a silent mismatch would shift every pointer after it)."""
+    import ctypes
+    import subprocess
+    from oa_transformer_b200 import _lib, ops
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "oat.h"', 'int main(void) {']
+    for cname, cls in (("oat_gemm_args", _lib.GemmArgs), ("oat_attn_args", ops.AttnArgs)):
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in (("oat_gemm_args", _lib.GemmArgs), ("oat_attn_args", ops.AttnArgs)):
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_version_and_error_channel(lib):
     assert lib.oat_version() >= 100
     rc = lib.oat_gemm_bf16(None, None)
